@@ -1,0 +1,204 @@
+/*
+ * vsp_b200.h — C ABI of the B200-native (sm_100a) synthesis hot path of VSPBFR.
+ *
+ * Every entry point is `extern "C"`, takes raw device pointers + int64 sizes +
+ * an explicit `cudaStream_t` (as void*), never allocates or frees user-visible
+ * memory, never synchronises, and returns 0 on success (non-zero: call
+ * vsp_last_error()).  Entry points are re-entrant and CUDA-graph capturable.
+ *
+ * Each function cites the reference interface (file:line under the VSPBFR
+ * tree) it stands in for.  The Python host side (vspbfr_b200/op/*) binds this
+ * header with ctypes; INTEGRATION.md shows the stub a reference maintainer
+ * would add.
+ */
+#ifndef VSP_B200_H_
+#define VSP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSP_ABI_VERSION 1
+
+/* ---- bookkeeping ------------------------------------------------------- */
+
+/* ABI version of the loaded library (== VSP_ABI_VERSION it was built with). */
+int vsp_version(void);
+
+/* Thread-local, NUL-terminated message for the last non-zero return on the
+ * calling thread.  Replaces TORCH_CHECK -> RuntimeError of
+ * op/upfirdn2d.cpp:9-15 and op/fused_bias_act.cpp:10-16. */
+const char *vsp_last_error(void);
+
+/* Number of kernels this library has launched since load (all threads).
+ * bench.py reads it to report `gpu_launches`. */
+int64_t vsp_launch_count(void);
+
+/* ---- upfirdn2d --------------------------------------------------------- */
+
+/*
+ * Up-sample (zero-stuff) / FIR-filter / down-sample of `major` fp32 planes.
+ * Replaces the pybind entry `upfirdn2d.upfirdn2d(input, kernel, up_x, up_y,
+ * down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)` of op/upfirdn2d.cpp:17-30
+ * (launcher op/upfirdn2d_kernel.cu:209-368) with minor_dim == 1, i.e. the
+ * `[N*C, H, W, 1]` view op/upfirdn2d.py:297 always passes.
+ *
+ *   x     [major, in_h, in_w]   fp32, contiguous
+ *   filt  [kh, kw]              fp32, contiguous (NOT flipped; the op is a true
+ *                               convolution, op/upfirdn2d.py:388)
+ *   y     [major, out_h, out_w] fp32, out = (in*up + pad0 + pad1 - k + down)/down
+ *
+ * Optional fused epilogue (north_star "fused upfirdn+bias+lrelu"): when
+ * `act` != 0 the kernel applies y = lrelu(y + bias[plane % channels], alpha)
+ * * scale before the store (bias may be NULL = no bias).  act == 0: plain op.
+ * Negative pads crop, as in op/upfirdn2d.py:378-386.
+ */
+int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y,
+                      int64_t major, int64_t in_h, int64_t in_w,
+                      int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                      int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                      const float *bias, int64_t channels, int act,
+                      float alpha, float scale, void *stream);
+
+/* Output extent helper: (in*up + pad0 + pad1 - k + down) / down
+ * (op/upfirdn2d.py:301-302). Returns <= 0 for an empty output. */
+int64_t vsp_upfirdn2d_out_size(int64_t in, int k, int up, int down, int pad0, int pad1);
+
+/*
+ * Channels-last bf16 variant used inside fused layer chains:
+ *   x [n, in_h, in_w, c] bf16 -> y [n, out_h, out_w, c] bf16 (c % 8 == 0).
+ * Same arithmetic (fp32 accumulate), same parameter meaning.
+ */
+int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y,
+                            int64_t n, int64_t in_h, int64_t in_w, int64_t c,
+                            int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                            int pad_x0, int pad_x1, int pad_y0, int pad_y1, void *stream);
+
+/* ---- bias + activation ------------------------------------------------- */
+
+/*
+ * y[i] = act(x[i] + b[(i / step_b) % size_b]) * scale
+ * Replaces `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ * of op/fused_bias_act.cpp:18-32 / op/fused_bias_act_kernel.cu:18-105.
+ * `b` / `ref` may be NULL (the reference passes 0-element tensors,
+ * op/fused_bias_act_kernel.cu:79-80).  act*10+grad selects the branch exactly
+ * as op/fused_bias_act_kernel.cu:40-61: 30 lrelu fwd, 31 lrelu grad gated on
+ * ref > 0, 32 / 12 zero, 10 / 11 linear.
+ */
+int vsp_bias_act_f32(const float *x, const float *b, const float *ref, float *y,
+                     int64_t n, int64_t step_b, int64_t size_b,
+                     int act, int grad, float alpha, float scale, void *stream);
+
+/*
+ * First-order backward of the leaky-ReLU bias-act with the bias-gradient
+ * reduction fused in (the reference runs a separate ATen `sum`,
+ * op/fused_act.py:139-145):
+ *   dx[i]  = scale * (ref[i] > 0 ? dy[i] : alpha * dy[i])
+ *   dbias[c] = sum over i with channel(i) == c of dx[i]      (may be NULL)
+ * `dbias` [size_b] is overwritten (zeroed on `stream` inside the call).
+ */
+int vsp_bias_act_bwd_f32(const float *dy, const float *ref, float *dx, float *dbias,
+                         int64_t n, int64_t step_b, int64_t size_b,
+                         float alpha, float scale, void *stream);
+
+/* ---- layout / modulation prologues ------------------------------------- */
+
+/* NCHW fp32 -> NHWC bf16 (optionally scaled per (n, c): `scale_nc` may be NULL).
+ * x [n, c, hw] -> y [n, hw, c_pad]; channels c..c_pad-1 are zero filled. */
+int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y,
+                              int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
+
+/* NHWC bf16 -> NCHW fp32: x [n, hw, c_pad] -> y [n, c, hw]. */
+int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
+                              int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
+
+/* NCHW fp32 -> NCHW bf16, optionally scaled per (n, c) plane. */
+int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y,
+                         int64_t planes, int64_t hw, void *stream);
+
+/*
+ * Weight prologue of the modulated convolution (models/RestoreNet.py:510-520,
+ * e4e/models/stylegan2/model.py:237-254):
+ *   m[b,o,i,t]  = wscale * W[o,i,t] * s[b,i]
+ *   demod[b,o]  = rsqrt(sum_{i,t} m^2 + eps)             (if demod != NULL)
+ *   wq[b,t',o',i'] = bf16(m * (fold_demod ? demod[b,o] : 1))
+ * with the packed layout the tcgen05 kernel consumes ([group][tap][n][k],
+ * k contiguous):
+ *   transpose == 0 : n = o (Cout), k = i (Cin), t' = t            -> fprop
+ *   transpose == 1 : n = i (Cin),  k = o (Cout), t' = taps-1-t    -> dgrad
+ * `s` may be NULL (plain EqualConv2d: s == 1, batch == 1 group shared by all
+ * samples).  n is padded to n_pad rows and k to k_pad columns with zeros.
+ */
+int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void *wq,
+                              int64_t batch, int64_t cout, int64_t cin, int taps,
+                              float wscale, float eps, int transpose, int fold_demod,
+                              int64_t n_pad, int64_t k_pad, void *stream);
+
+/* ---- tcgen05 implicit-GEMM convolution --------------------------------- */
+
+/* Epilogue description shared by the conv entry points. All pointers optional. */
+typedef struct vsp_conv_epilogue {
+  const float *row_scale; /* [batch, cout]  demodulation coefficient d[b,o]        */
+  const float *noise;     /* [batch, out_h, out_w] noise image (NoiseInjection)    */
+  float noise_weight;     /* NoiseInjection.weight (scalar)                        */
+  const float *bias;      /* [cout] FusedLeakyReLU / ToRGB bias                    */
+  int act;                /* 0 = none, 3 = leaky relu (as fused_bias_act)          */
+  float alpha;            /* negative slope                                        */
+  float scale;            /* output gain (sqrt 2)                                  */
+  const void *residual;   /* same layout as the output; added after activation     */
+} vsp_conv_epilogue;
+
+/*
+ * Forward 2-D convolution as a bf16 implicit GEMM on tcgen05/TMEM fed by TMA:
+ *   M = pixels of one sample tile, N = Cout, K = taps * Cin.
+ * Replaces cuDNN via conv2d_gradfix.conv2d (op/conv2d_gradfix.py:22-42) for the
+ * grouped form ModulatedConv2d issues (models/RestoreNet.py:547-553: weights
+ * [B*Cout, Cin, k, k], groups = B) and for the plain EqualConv2d form
+ * (groups = 1, one weight group shared by every sample).
+ *
+ *   x   [batch, in_h, in_w, cin]   bf16 NHWC (cin % 16 == 0)
+ *   wq  [groups, kh*kw, cout_pad, cin] bf16 from vsp_modulate_weights_bf16;
+ *       groups == batch (per-sample weights) or 1 (shared)
+ *   out [batch, cout, out_h, out_w] fp32 NCHW           (out_nhwc_bf16 == 0)
+ *       [batch, out_h, out_w, ldo] bf16 NHWC at channel offset `co_off`
+ *                                                       (out_nhwc_bf16 == 1)
+ * out_h = (in_h + 2*pad - dil*(kh-1) - 1)/stride + 1 (same for w).
+ */
+int vsp_conv2d_fprop_bf16(const void *x, const void *wq, void *out,
+                          int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                          int64_t cin, int64_t cout, int64_t cout_pad,
+                          int kh, int kw, int stride, int pad, int dil,
+                          int out_nhwc_bf16, int64_t ldo, int64_t co_off,
+                          const vsp_conv_epilogue *epi, void *stream);
+
+/*
+ * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):
+ *   gw[g, o, i, t] = sum_{p in sample(s) of group g} dy[b,o,p] * x[b,i,p*stride + t*dil - pad]
+ * Replaces aten::cudnn_convolution_backward_weight, op/conv2d_gradfix.py:177-199.
+ *   dy [batch, cout, out_h, out_w] bf16 NCHW, x [batch, cin, in_h, in_w] bf16 NCHW
+ *   gw [groups, cout, cin, kh*kw] fp32; groups == batch (per-sample) or 1
+ *   (summed over the batch).
+ */
+int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw,
+                          int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                          int64_t cin, int64_t cout, int64_t out_h, int64_t out_w,
+                          int kh, int kw, int stride, int pad, int dil, void *stream);
+
+/*
+ * Style / shared-weight gradients of the modulated convolution from the
+ * per-sample raw weight gradient G = gw[b,o,i,t] (of the un-demodulated
+ * product z, i.e. computed from dz = demod * dy):
+ *   m = wscale*W*s ; dm = G - demod^2 * (sum_{i,t} m*G) * m      (demod != NULL)
+ *   dW[o,i,t] = wscale * sum_b s[b,i] * dm ;  ds[b,i] = wscale * sum_{o,t} W * dm
+ */
+int vsp_modconv_weight_style_grad(const float *gw, const float *w, const float *s,
+                                  const float *demod, float *dw, float *ds,
+                                  int64_t batch, int64_t cout, int64_t cin, int taps,
+                                  float wscale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSP_B200_H_ */

@@ -1,0 +1,183 @@
+"""Build + ctypes binding of the C-ABI library (include/vsp_b200.h).
+
+The shared object is built in-tree (``vspbfr_b200/libvsp_b200.so``) with
+``nvcc -gencode arch=compute_100a,code=sm_100a``; nothing here imports torch
+extensions or pybind — the boundary is plain C (SURVEY.md §8 b).  There is no
+CPU fallback: if the library is missing and cannot be built, or a kernel call
+returns non-zero, a ``RuntimeError`` is raised (the reference raises the same
+type through TORCH_CHECK, op/upfirdn2d.cpp:9-15).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libvsp_b200.so")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+SOURCES = [
+    "c_api.cu",
+    "upfirdn2d_sm100.cu",
+    "bias_act_sm100.cu",
+    "layout_sm100.cu",
+    "conv_sm100.cu",
+    "wgrad_sm100.cu",
+]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-Xptxas", "-v",
+]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "vsp_b200.h")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under csrc/ into libvsp_b200.so for sm_100a (cross-compiles without a GPU)."""
+    with _lock:
+        if not force and not _stale():
+            return LIB_PATH
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        if not os.path.exists(nvcc):
+            raise RuntimeError("vspbfr_b200: nvcc not found and libvsp_b200.so is missing or stale")
+        objs = []
+        procs = []
+        build_dir = os.path.join(_HERE, "build")
+        os.makedirs(build_dir, exist_ok=True)
+        compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
+        for src in _sources():
+            obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+            objs.append(obj)
+            if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                    and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "common.cuh"))
+                    and os.path.getmtime(obj) > os.path.getmtime(os.path.join(INCLUDE, "vsp_b200.h"))):
+                continue
+            cmd = [nvcc, *compile_flags, "-c", src, "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        log = []
+        for src, p in procs:
+            out, _ = p.communicate()
+            log.append(out)
+            if p.returncode != 0:
+                raise RuntimeError(f"vspbfr_b200: nvcc failed on {src}:\n{out}")
+        tmp = LIB_PATH + ".tmp"
+        cmd = [nvcc, "--shared", "-o", tmp, *objs, "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"vspbfr_b200: link failed:\n{r.stdout}")
+        os.replace(tmp, LIB_PATH)
+        with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
+            f.write("\n".join(log))
+        if verbose:
+            print("\n".join(log))
+        return LIB_PATH
+
+
+class ConvEpilogue(Structure):
+    """Mirror of ``vsp_conv_epilogue`` (include/vsp_b200.h)."""
+
+    _fields_ = [
+        ("row_scale", c_void_p),
+        ("noise", c_void_p),
+        ("noise_weight", c_float),
+        ("bias", c_void_p),
+        ("act", c_int),
+        ("alpha", c_float),
+        ("scale", c_float),
+        ("residual", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/vsp_b200.h declares.
+SIGNATURES = {
+    "vsp_version": (c_int, []),
+    "vsp_last_error": (c_char_p, []),
+    "vsp_launch_count": (c_int64, []),
+    "vsp_upfirdn2d_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                  c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int,
+                                  c_void_p, c_int64, c_int, c_float, c_float, c_void_p]),
+    "vsp_upfirdn2d_out_size": (c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "vsp_upfirdn2d_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
+                                        c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_int, c_void_p]),
+    "vsp_bias_act_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                 c_int, c_int, c_float, c_float, c_void_p]),
+    "vsp_bias_act_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                     c_float, c_float, c_void_p]),
+    "vsp_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vsp_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vsp_nchw_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "vsp_modulate_weights_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_int64, c_int64, c_int,
+                                          c_float, c_float, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "vsp_conv2d_fprop_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                      c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vsp_modconv_weight_style_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int64, c_int64, c_int64, c_int, c_float, c_void_p]),
+}
+
+
+def load():
+    """dlopen the library (building it first if needed) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = build()
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vsp_version() != 1:
+        raise RuntimeError(f"vspbfr_b200: ABI version mismatch ({lib.vsp_version()} != 1)")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().vsp_last_error()
+        raise RuntimeError(f"vsp_b200 {what}: {msg.decode() if msg else 'unknown error'}")
+
+
+def launch_count() -> int:
+    return int(load().vsp_launch_count())
+
+
+def stream_ptr():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
