@@ -1,0 +1,318 @@
+// layout_sm100.cu — layout conversions at the reference-visible boundary and the
+// weight prologue / weight+style gradient epilogue of the modulated convolution.
+//
+// The reference is NCHW fp32 everywhere; the tcgen05 kernels want
+// NHWC bf16 activations (K = channels contiguous) and [group][tap][n][k] bf16
+// weights.  Modulation maths follows models/RestoreNet.py:510-520.
+#include "common.cuh"
+
+namespace vsp {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- NCHW fp32 -> NHWC bf16 (64 channels x 64 pixels per block, smem transpose)
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc,
+                    __nv_bfloat16 *__restrict__ y, long long c, long long hw, long long c_pad) {
+  __shared__ float tile[64][65];
+  const long long n = blockIdx.z;
+  const long long c0 = (long long)blockIdx.y * 64, p0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int cl = ty + 4 * i;
+    const long long cc = c0 + cl, pp = p0 + tx;
+    float v = 0.f;
+    if (cc < c && pp < hw) {
+      v = ld_stream_f1(x + (n * c + cc) * hw + pp);
+      if (scale_nc != nullptr) v *= __ldg(scale_nc + n * c + cc);
+    }
+    tile[cl][tx] = v;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;  // 32 channel pairs x 8 pixels
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = py + 8 * i;
+    const long long pp = p0 + pl, cc = c0 + 2 * cx;
+    if (pp < hw && cc < c_pad) {
+      __nv_bfloat162 o = __floats2bfloat162_rn(tile[2 * cx][pl], tile[2 * cx + 1][pl]);
+      *reinterpret_cast<__nv_bfloat162 *>(y + (n * hw + pp) * c_pad + cc) = o;
+    }
+  }
+}
+
+// ---- NHWC bf16 -> NCHW fp32
+__global__ void __launch_bounds__(kThreads)
+nhwc_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long c,
+                    long long hw, long long c_pad) {
+  __shared__ float tile[64][65];  // [pixel][channel]
+  const long long n = blockIdx.z;
+  const long long c0 = (long long)blockIdx.y * 64, p0 = (long long)blockIdx.x * 64;
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = py + 8 * i;
+    const long long pp = p0 + pl, cc = c0 + 2 * cx;
+    float2 v = make_float2(0.f, 0.f);
+    if (pp < hw && cc < c_pad)
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(x + (n * hw + pp) * c_pad + cc));
+    tile[pl][2 * cx] = v.x;
+    tile[pl][2 * cx + 1] = v.y;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int cl = ty + 4 * i;
+    const long long cc = c0 + cl, pp = p0 + tx;
+    if (cc < c && pp < hw) st_stream_f1(y + (n * c + cc) * hw + pp, tile[tx][cl]);
+  }
+}
+
+// ---- NCHW fp32 -> NCHW bf16 with a per-plane scale
+__global__ void __launch_bounds__(kThreads)
+nchw_cast_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc,
+                 __nv_bfloat16 *__restrict__ y, long long hw, int vec) {
+  const long long plane = blockIdx.y;
+  const float s = scale_nc ? __ldg(scale_nc + plane) : 1.f;
+  const float *xp = x + plane * hw;
+  __nv_bfloat16 *yp = y + plane * hw;
+  const long long stride = (long long)gridDim.x * kThreads;
+  if (vec) {
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < hw / 4; i += stride) {
+      const float4 v = ld_stream_f4(reinterpret_cast<const float4 *>(xp) + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x * s, v.y * s), b = __floats2bfloat162_rn(v.z * s, v.w * s);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t *>(&a);
+      o.y = *reinterpret_cast<uint32_t *>(&b);
+      *(reinterpret_cast<uint2 *>(yp) + i) = o;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < hw; i += stride)
+      yp[i] = __float2bfloat16_rn(xp[i] * s);
+  }
+}
+
+// ---- demod[b,o] = rsqrt(sum_{i,t} (wscale*W[o,i,t]*s[b,i])^2 + eps): one warp per (b,o)
+__global__ void __launch_bounds__(kThreads)
+demod_kernel(const float *__restrict__ w, const float *__restrict__ s, float *__restrict__ demod,
+             long long batch, long long cout, long long cin, int taps, float wscale, float eps) {
+  const long long warp = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * cout) return;
+  const long long b = warp / cout, o = warp % cout;
+  const float *wr = w + o * cin * taps;
+  float acc = 0.f;
+  for (long long e = lane; e < cin * taps; e += 32) {
+    const long long i = e / taps;
+    const float m = wscale * wr[e] * (s ? __ldg(s + b * cin + i) : 1.f);
+    acc = fmaf(m, m, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) demod[warp] = rsqrtf(acc + eps);
+}
+
+// ---- pack modulated weights to bf16 [b][tap'][n_pad][k_pad]; one thread per (n', k')
+__global__ void __launch_bounds__(kThreads)
+pack_weights_kernel(const float *__restrict__ w, const float *__restrict__ s,
+                    const float *__restrict__ demod, __nv_bfloat16 *__restrict__ wq, long long cout,
+                    long long cin, int taps, float wscale, int transpose, long long n_pad,
+                    long long k_pad) {
+  const long long b = blockIdx.y;
+  const long long idx = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (idx >= n_pad * k_pad) return;
+  const long long nn = idx / k_pad, kk = idx % k_pad;
+  const long long o = transpose ? kk : nn, i = transpose ? nn : kk;
+  const bool valid = o < cout && i < cin;
+  float f = 0.f;
+  if (valid) {
+    f = wscale * (s ? __ldg(s + b * cin + i) : 1.f);
+    if (demod) f *= __ldg(demod + b * cout + o);
+  }
+  const float *wr = w + (o * cin + i) * taps;
+  __nv_bfloat16 *dst = wq + b * taps * n_pad * k_pad + idx;
+  for (int t = 0; t < taps; ++t) {
+    const int tt = transpose ? taps - 1 - t : t;
+    dst[(long long)tt * n_pad * k_pad] = __float2bfloat16_rn(valid ? wr[t] * f : 0.f);
+  }
+}
+
+// ---- c[b,o] = demod^2 * sum_{i,t} m*G   (one warp per (b,o))
+__global__ void __launch_bounds__(kThreads)
+demod_corr_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
+                  const float *__restrict__ demod, float *__restrict__ corr, long long batch,
+                  long long cout, long long cin, int taps, float wscale) {
+  const long long warp = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * cout) return;
+  const long long b = warp / cout, o = warp % cout;
+  const float *wr = w + o * cin * taps;
+  const float *gr = gw + warp * cin * taps;
+  float acc = 0.f;
+  for (long long e = lane; e < cin * taps; e += 32) {
+    const float m = wscale * wr[e] * __ldg(s + b * cin + e / taps);
+    acc = fmaf(m, gr[e], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float d = demod[warp];
+    corr[warp] = d * d * acc;
+  }
+}
+
+// ---- dW[o,i,t] = wscale * sum_b s[b,i] * (G - corr[b,o]*m)     (thread per element)
+__global__ void __launch_bounds__(kThreads)
+dweight_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
+               const float *__restrict__ corr, float *__restrict__ dw, long long batch, long long cout,
+               long long cin, int taps, float wscale) {
+  const long long e = blockIdx.x * (long long)kThreads + threadIdx.x;
+  const long long per = cout * cin * taps;
+  if (e >= per) return;
+  const long long o = e / (cin * taps), i = (e / taps) % cin;
+  const float wv = w[e];
+  float acc = 0.f;
+  for (long long b = 0; b < batch; ++b) {
+    const float sv = s ? __ldg(s + b * cin + i) : 1.f;
+    float dm = gw[b * per + e];
+    if (corr) dm -= __ldg(corr + b * cout + o) * (wscale * wv * sv);
+    acc = fmaf(sv, dm, acc);
+  }
+  dw[e] = wscale * acc;
+}
+
+// ---- ds[b,i] = wscale * sum_{o,t} W[o,i,t] * (G - corr[b,o]*m); grid (i tiles, o chunks, b)
+__global__ void __launch_bounds__(kThreads)
+dstyle_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
+              const float *__restrict__ corr, float *__restrict__ ds, long long cout, long long cin,
+              int taps, float wscale, long long o_chunk) {
+  const long long b = blockIdx.z;
+  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (i >= cin) return;
+  const long long o_lo = blockIdx.y * o_chunk;
+  const long long o_hi = min(o_lo + o_chunk, cout);
+  const float sv = __ldg(s + b * cin + i);
+  float acc = 0.f;
+  for (long long o = o_lo; o < o_hi; ++o) {
+    const float c = corr ? __ldg(corr + b * cout + o) : 0.f;
+    const float *wr = w + (o * cin + i) * taps;
+    const float *gr = gw + ((b * cout + o) * cin + i) * taps;
+    for (int t = 0; t < taps; ++t) {
+      const float wv = wr[t];
+      acc = fmaf(wv, gr[t] - c * (wscale * wv * sv), acc);
+    }
+  }
+  atomicAdd(ds + b * cin + i, wscale * acc);
+}
+
+}  // namespace
+}  // namespace vsp
+
+using namespace vsp;
+
+extern "C" int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y, int64_t n,
+                                         int64_t c, int64_t hw, int64_t c_pad, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(n >= 0 && c >= 0 && hw >= 0 && c_pad >= c && c_pad % 2 == 0, "nchw->nhwc: bad geometry");
+  if (n == 0 || c_pad == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && y, "nchw->nhwc: null pointer");
+  VSP_REQUIRE(n <= 65535 && ceil_div64(c_pad, 64) <= 65535, "nchw->nhwc: batch/channel extent too large");
+  dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
+  nchw_to_nhwc_kernel<<<grid, kThreads, 0, stream>>>(x, scale_nc, static_cast<__nv_bfloat16 *>(y), c, hw, c_pad);
+  return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y, int64_t n, int64_t c, int64_t hw,
+                                         int64_t c_pad, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(n >= 0 && c >= 0 && hw >= 0 && c_pad >= c && c_pad % 2 == 0, "nhwc->nchw: bad geometry");
+  if (n == 0 || c == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && y, "nhwc->nchw: null pointer");
+  VSP_REQUIRE(n <= 65535 && ceil_div64(c_pad, 64) <= 65535, "nhwc->nchw: batch/channel extent too large");
+  dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
+  nhwc_to_nchw_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), y, c, hw, c_pad);
+  return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y, int64_t planes,
+                                    int64_t hw, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(planes >= 0 && hw >= 0, "nchw cast: bad geometry");
+  if (planes == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && y, "nchw cast: null pointer");
+  VSP_REQUIRE(planes <= 65535LL * 65535LL, "nchw cast: too many planes");
+  const int vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(y) & 7) == 0);
+  long long bx = ceil_div64(vec ? hw / 4 : hw, kThreads);
+  if (bx > 64) bx = 64;
+  for (int64_t p0 = 0; p0 < planes; p0 += 65535) {
+    const int64_t np = planes - p0 < 65535 ? planes - p0 : 65535;
+    dim3 grid((unsigned)bx, (unsigned)np);
+    nchw_cast_kernel<<<grid, kThreads, 0, stream>>>(x + p0 * hw, scale_nc ? scale_nc + p0 : nullptr,
+                                                    static_cast<__nv_bfloat16 *>(y) + p0 * hw, hw, vec);
+    if (int rc = check_launch("nchw_cast_kernel")) return rc;
+  }
+  return 0;
+}
+
+extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void *wq,
+                                         int64_t batch, int64_t cout, int64_t cin, int taps,
+                                         float wscale, float eps, int transpose, int fold_demod,
+                                         int64_t n_pad, int64_t k_pad, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 1 && cout >= 1 && cin >= 1 && taps >= 1, "modulate_weights: bad geometry");
+  VSP_REQUIRE(w != nullptr, "modulate_weights: null weight");
+  VSP_REQUIRE(!(fold_demod && !demod), "modulate_weights: fold_demod needs a demod buffer");
+  VSP_REQUIRE(batch <= 65535, "modulate_weights: batch too large");
+  if (demod) {
+    const long long warps = batch * cout;
+    demod_kernel<<<(unsigned)ceil_div64(warps * 32, kThreads), kThreads, 0, stream>>>(w, s, demod, batch, cout, cin,
+                                                                                      taps, wscale, eps);
+    if (int rc = check_launch("demod_kernel")) return rc;
+  }
+  if (wq) {
+    const int64_t n_real = transpose ? cin : cout, k_real = transpose ? cout : cin;
+    VSP_REQUIRE(n_pad >= n_real && k_pad >= k_real, "modulate_weights: padded extents smaller than the real ones");
+    dim3 grid((unsigned)ceil_div64(n_pad * k_pad, kThreads), (unsigned)batch);
+    pack_weights_kernel<<<grid, kThreads, 0, stream>>>(w, s, fold_demod ? demod : nullptr,
+                                                       static_cast<__nv_bfloat16 *>(wq), cout, cin, taps, wscale,
+                                                       transpose, n_pad, k_pad);
+    if (int rc = check_launch("pack_weights_kernel")) return rc;
+  }
+  return 0;
+}
+
+extern "C" int vsp_modconv_weight_style_grad(const float *gw, const float *w, const float *s,
+                                             const float *demod, float *dw, float *ds, int64_t batch,
+                                             int64_t cout, int64_t cin, int taps, float wscale,
+                                             void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 1 && cout >= 1 && cin >= 1 && taps >= 1, "weight_style_grad: bad geometry");
+  VSP_REQUIRE(gw && w && s, "weight_style_grad: null pointer");
+  VSP_REQUIRE(batch <= 65535, "weight_style_grad: batch too large");
+  float *corr = nullptr;
+  if (demod) {
+    // scratch for corr[b,o]: stream-ordered allocation, freed on the same stream
+    VSP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&corr), sizeof(float) * batch * cout, stream));
+    demod_corr_kernel<<<(unsigned)ceil_div64(batch * cout * 32, kThreads), kThreads, 0, stream>>>(
+        gw, w, s, demod, corr, batch, cout, cin, taps, wscale);
+    if (int rc = check_launch("demod_corr_kernel")) return rc;
+  }
+  if (dw) {
+    dweight_kernel<<<(unsigned)ceil_div64(cout * cin * taps, kThreads), kThreads, 0, stream>>>(
+        gw, w, s, corr, dw, batch, cout, cin, taps, wscale);
+    if (int rc = check_launch("dweight_kernel")) return rc;
+  }
+  if (ds) {
+    VSP_CUDA(cudaMemsetAsync(ds, 0, sizeof(float) * batch * cin, stream));
+    long long chunks = 32;
+    if (chunks > cout) chunks = cout;
+    const long long o_chunk = ceil_div64(cout, chunks);
+    dim3 grid((unsigned)ceil_div64(cin, kThreads), (unsigned)ceil_div64(cout, o_chunk), (unsigned)batch);
+    dstyle_kernel<<<grid, kThreads, 0, stream>>>(gw, w, s, corr, ds, cout, cin, taps, wscale, o_chunk);
+    if (int rc = check_launch("dstyle_kernel")) return rc;
+  }
+  if (corr) VSP_CUDA(cudaFreeAsync(corr, stream));
+  return 0;
+}
