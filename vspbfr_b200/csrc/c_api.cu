@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <string.h>
 
 namespace vsp {
 
@@ -107,3 +108,17 @@ int64_t vsp_upfirdn2d_out_size(int64_t in, int k, int up, int down, int pad0, in
 }
 
 }  // extern "C"
+
+// Debug aid (not part of the public header): encode a 3-D fp32 map and return its 128 bytes.
+extern "C" int vsp_debug_tma_3d_f32(const void *base, uint64_t w, uint64_t h, uint64_t planes, uint32_t bw,
+                                    uint32_t bh, uint32_t bz, unsigned char *out128) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  uint64_t dims[3] = {w, h, planes};
+  uint64_t strides[3] = {0, w * 4, w * h * 4};
+  uint32_t box[3] = {bw, bh, bz};
+  int rc = vsp::encode_tma(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, nullptr,
+                           CU_TENSOR_MAP_SWIZZLE_NONE);
+  memcpy(out128, &m, 128);
+  return rc;
+}

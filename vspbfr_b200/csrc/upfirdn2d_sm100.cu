@@ -16,6 +16,8 @@
 // (tuple factors, 12-tap filters, ... used by non_leaking.py:879-905).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace vsp {
 namespace {
 
@@ -50,9 +52,13 @@ struct Cfg {
   static constexpr int SY = kRO * D / U, SX = kCO * D / U;       // thread stride in input samples
   static constexpr int WR = (QY + (kRO - 1) * D + kK - 1) / U + 1;  // window rows
   static constexpr int WC = (QX + (kCO - 1) * D + kK - 1) / U + 1;  // window cols
-  static constexpr int WCV = (SX % 4 == 0) ? round_up4(WC) : ((WC + 1) & ~1);
+  static constexpr int V = (SX % 4 == 0) ? 4 : 2;                 // LDS vector width (floats)
+  // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: a misaligned
+  // start coordinate raises "illegal instruction"), so the smem tile starts at the input
+  // column rounded DOWN to a multiple of 4 and every window is read at a shift XS in 0..3.
+  static constexpr int WCV_MAX = ((3 + WC + V - 1) / V) * V;
   static constexpr int TIH = (TY - 1) * SY + WR;
-  static constexpr int TIW = round_up4((TX - 1) * SX + WCV);
+  static constexpr int TIW = round_up4((TX - 1) * SX + WCV_MAX);
   static constexpr int TILE_FLOATS = PZ * TIH * TIW;               // what one TMA box delivers
   static constexpr int TILE_BYTES = TILE_FLOATS * 4;
   static constexpr int STAGE_FLOATS = (TILE_FLOATS + 31) & ~31;   // stages stay 128-byte aligned
@@ -78,6 +84,38 @@ __device__ __forceinline__ void lds_row(const float *p, float (&dst)[N]) {
   }
 }
 
+// Micro-tile of kRO x kCO outputs from the staged tile; XS = column shift of the window
+// inside the 16-byte-aligned tile (compile time so every LDS stays a 64/128-bit access).
+template <int U, int D, int QX, int QY, int TOW, int TOH, int PZ, int XS>
+__device__ __forceinline__ void micro_tile(const float *wp, const float (&w)[kK][kK], float (&acc)[kRO][kCO]) {
+  using C = Cfg<U, D, QX, QY, TOW, TOH, PZ>;
+  constexpr int LO = (XS / C::V) * C::V;                               // first aligned column read
+  constexpr int NV = ((XS + C::WC + C::V - 1) / C::V) * C::V - LO;     // columns read (multiple of V)
+  float win[C::WR][NV];
+#pragma unroll
+  for (int r = 0; r < C::WR; ++r) lds_row<NV, C::V>(wp + r * C::TIW + LO, win[r]);
+#pragma unroll
+  for (int r = 0; r < kRO; ++r)
+#pragma unroll
+    for (int c = 0; c < kCO; ++c) acc[r][c] = 0.f;
+  // tap order: y outer, x inner, sequential FMA (as op/upfirdn2d_kernel.cu:193-198)
+#pragma unroll
+  for (int r = 0; r < kRO; ++r)
+#pragma unroll
+    for (int jy = 0; jy < kK; ++jy) {
+      const int ty_u = QY + r * D + jy;
+      if (ty_u % U != 0) continue;
+#pragma unroll
+      for (int c = 0; c < kCO; ++c)
+#pragma unroll
+        for (int jx = 0; jx < kK; ++jx) {
+          const int tx_u = QX + c * D + jx;
+          if (tx_u % U != 0) continue;
+          acc[r][c] = fmaf(win[ty_u / U][tx_u / U + XS - LO], w[jy][jx], acc[r][c]);
+        }
+    }
+}
+
 template <int U, int D, int QX, int QY, int TOW, int TOH, int PZ>
 __global__ void __launch_bounds__(kThreads)
 upfirdn2d_tile_kernel(const UfdParams p, const __grid_constant__ CUtensorMap tmap) {
@@ -96,8 +134,10 @@ upfirdn2d_tile_kernel(const UfdParams p, const __grid_constant__ CUtensorMap tma
   const int zchunk = bid;
   const int ox0 = tile_x * TOW, oy0 = tile_y * TOH;
   // first input sample of the tile (may be negative: padding)
-  const int ix_base = (ox0 * D - p.pad_x0 - QX) / U;  // exact by construction of QX
+  const int ix_first = (ox0 * D - p.pad_x0 - QX) / U;  // exact by construction of QX
   const int iy_base = (oy0 * D - p.pad_y0 - QY) / U;
+  const int xs = ix_first & 3;                         // two's complement: also right for negatives
+  const int ix_base = ix_first - xs;                   // multiple of 4 floats = 16 bytes
 
   // flipped, zero-extended filter in registers: w[jy][jx] = filt[kh-1-jy][kw-1-jx]
   float w[kK][kK];
@@ -160,34 +200,15 @@ upfirdn2d_tile_kernel(const UfdParams p, const __grid_constant__ CUtensorMap tma
       __syncthreads();
     }
 
-    // ---- compute the 2x4 micro tile
-    float win[C::WR][C::WCV];
-    const float *wp = tile + (tz * C::TIH + ty * C::SY) * C::TIW + tx * C::SX;
-#pragma unroll
-    for (int r = 0; r < C::WR; ++r) lds_row<C::WCV, (C::SX % 4 == 0) ? 4 : 2>(wp + r * C::TIW, win[r]);
-
+    // ---- compute the 2x4 micro tile (uniform switch on the alignment shift)
     float acc[kRO][kCO];
-#pragma unroll
-    for (int r = 0; r < kRO; ++r)
-#pragma unroll
-      for (int c = 0; c < kCO; ++c) acc[r][c] = 0.f;
-
-    // tap order: y outer, x inner, sequential FMA (as op/upfirdn2d_kernel.cu:193-198)
-#pragma unroll
-    for (int r = 0; r < kRO; ++r)
-#pragma unroll
-      for (int jy = 0; jy < kK; ++jy) {
-        const int ty_u = QY + r * D + jy;
-        if (ty_u % U != 0) continue;
-#pragma unroll
-        for (int c = 0; c < kCO; ++c)
-#pragma unroll
-          for (int jx = 0; jx < kK; ++jx) {
-            const int tx_u = QX + c * D + jx;
-            if (tx_u % U != 0) continue;
-            acc[r][c] = fmaf(win[ty_u / U][tx_u / U], w[jy][jx], acc[r][c]);
-          }
-      }
+    const float *wp = tile + (tz * C::TIH + ty * C::SY) * C::TIW + tx * C::SX;
+    switch (xs) {
+      case 0: micro_tile<U, D, QX, QY, TOW, TOH, PZ, 0>(wp, w, acc); break;
+      case 1: micro_tile<U, D, QX, QY, TOW, TOH, PZ, 1>(wp, w, acc); break;
+      case 2: micro_tile<U, D, QX, QY, TOW, TOH, PZ, 2>(wp, w, acc); break;
+      default: micro_tile<U, D, QX, QY, TOW, TOH, PZ, 3>(wp, w, acc); break;
+    }
 
     // ---- epilogue + store
     const long long pl = pz0 + tz;
@@ -255,6 +276,52 @@ upfirdn2d_generic_kernel(const UfdParams p, long long total) {
       acc = (acc > 0.f ? acc : acc * p.alpha) * p.scale;
     }
     p.y[idx] = acc;
+  }
+}
+
+// Channels-last bf16 variant: one thread per (output pixel, 8-channel group), 128-bit
+// loads/stores along the contiguous channel axis, fp32 accumulation.
+__global__ void __launch_bounds__(kThreads)
+upfirdn2d_nhwc_kernel(const uint4 *__restrict__ x, const float *__restrict__ filt, uint4 *__restrict__ y,
+                      const UfdParams p, int cg, long long total) {
+  for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    const int g = (int)(idx % cg);
+    long long t = idx / cg;
+    const int ox = (int)(t % p.out_w); t /= p.out_w;
+    const int oy = (int)(t % p.out_h);
+    const long long b = t / p.out_h;
+    const int base_y = oy * p.down_y - p.pad_y0;
+    const int base_x = ox * p.down_x - p.pad_x0;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int jy = 0; jy < p.kh; ++jy) {
+      const int uy = base_y + jy;
+      if (uy < 0 || uy % p.up_y != 0) continue;
+      const int iy = uy / p.up_y;
+      if (iy >= p.in_h) continue;
+      for (int jx = 0; jx < p.kw; ++jx) {
+        const int ux = base_x + jx;
+        if (ux < 0 || ux % p.up_x != 0) continue;
+        const int ix = ux / p.up_x;
+        if (ix >= p.in_w) continue;
+        const float w = __ldg(filt + (p.kh - 1 - jy) * p.kw + (p.kw - 1 - jx));
+        const uint4 v = __ldg(x + ((b * p.in_h + iy) * (long long)p.in_w + ix) * cg + g);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          acc[2 * i] = fmaf(f.x, w, acc[2 * i]);
+          acc[2 * i + 1] = fmaf(f.y, w, acc[2 * i + 1]);
+        }
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    y[idx] = o;
   }
 }
 
@@ -345,7 +412,8 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
   p.channels = (int)(channels > 0 ? channels : 1); p.act = act; p.alpha = alpha; p.scale = scale;
   p.tiles_x = p.tiles_y = p.zgroups = p.iters = 0;
   // TMA staging needs a 16-byte aligned base and row pitch, and a non-empty input
-  p.use_tma = (in_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && in_h > 0 && in_w > 0 &&
+  static const bool no_tma = getenv("VSP_NO_TMA") != nullptr;  // debugging aid: force LDG staging
+  p.use_tma = !no_tma && (in_w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && in_h > 0 && in_w > 0 &&
               major < (1LL << 31);
 
   const bool small_filt = kh <= kK && kw <= kK;
@@ -368,4 +436,35 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
   if (blocks > cap) blocks = cap;
   upfirdn2d_generic_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(p, total);
   return check_launch("upfirdn2d_generic_kernel");
+}
+
+extern "C" int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y, int64_t n, int64_t in_h,
+                                       int64_t in_w, int64_t c, int kh, int kw, int up_x, int up_y,
+                                       int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                                       int pad_y1, void *stream_) {
+  using namespace vsp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d_nhwc: factors must be >= 1");
+  VSP_REQUIRE(kh >= 1 && kw >= 1, "upfirdn2d_nhwc: empty filter");
+  VSP_REQUIRE(c >= 0 && c % 8 == 0, "upfirdn2d_nhwc: channels must be a multiple of 8");
+  VSP_REQUIRE(in_h < (1 << 30) && in_w < (1 << 30), "upfirdn2d_nhwc: extent too large");
+  const int64_t out_h = vsp_upfirdn2d_out_size(in_h, kh, up_y, down_y, pad_y0, pad_y1);
+  const int64_t out_w = vsp_upfirdn2d_out_size(in_w, kw, up_x, down_x, pad_x0, pad_x1);
+  if (n <= 0 || c == 0 || out_h <= 0 || out_w <= 0) return 0;
+  VSP_REQUIRE(x && filt && y, "upfirdn2d_nhwc: null pointer");
+  VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+              "upfirdn2d_nhwc: tensors must be 16-byte aligned");
+  UfdParams p;
+  memset(&p, 0, sizeof(p));
+  p.in_h = (int)in_h; p.in_w = (int)in_w; p.out_h = (int)out_h; p.out_w = (int)out_w;
+  p.kh = kh; p.kw = kw; p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
+  p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  const int cg = (int)(c / 8);
+  const long long total = (long long)n * out_h * out_w * cg;
+  long long blocks = (total + kThreads - 1) / kThreads;
+  const long long cap = (long long)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  upfirdn2d_nhwc_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(
+      static_cast<const uint4 *>(x), filt, static_cast<uint4 *>(y), p, cg, total);
+  return check_launch("upfirdn2d_nhwc_kernel");
 }
