@@ -126,8 +126,9 @@ int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y,
  *   wq[b,t',o',i'] = bf16(m * (fold_demod ? demod[b,o] : 1))
  * with the packed layout the tcgen05 kernel consumes ([group][tap][n][k],
  * k contiguous):
- *   transpose == 0 : n = o (Cout), k = i (Cin), t' = t            -> fprop
- *   transpose == 1 : n = i (Cin),  k = o (Cout), t' = taps-1-t    -> dgrad
+ *   transpose == 0 : n = o (Cout), k = i (Cin)   -> fprop
+ *   transpose == 1 : n = i (Cin),  k = o (Cout)  -> dgrad (tap mirroring is expressed by the
+ *                    tap offsets of vsp_conv2d_gather_bf16, the tap index t' = t is kept)
  * `s` may be NULL (plain EqualConv2d: s == 1, batch == 1 group shared by all
  * samples).  n is padded to n_pad rows and k to k_pad columns with zeros.
  */
@@ -138,16 +139,21 @@ int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void
 
 /* ---- tcgen05 implicit-GEMM convolution --------------------------------- */
 
-/* Epilogue description shared by the conv entry points. All pointers optional. */
+/* Epilogue description shared by the conv entry points. All pointers optional.
+ * Order of application: acc * row_scale[b,n] + noise_weight * noise[b,pixel] + bias[n]
+ * -> activation * scale -> + residual + residual2. */
 typedef struct vsp_conv_epilogue {
-  const float *row_scale; /* [batch, cout]  demodulation coefficient d[b,o]        */
-  const float *noise;     /* [batch, out_h, out_w] noise image (NoiseInjection)    */
-  float noise_weight;     /* NoiseInjection.weight (scalar)                        */
-  const float *bias;      /* [cout] FusedLeakyReLU / ToRGB bias                    */
-  int act;                /* 0 = none, 3 = leaky relu (as fused_bias_act)          */
-  float alpha;            /* negative slope                                        */
-  float scale;            /* output gain (sqrt 2)                                  */
-  const void *residual;   /* same layout as the output; added after activation     */
+  const float *row_scale; /* [batch, cout]  demodulation coefficient d[b,o]            */
+  const float *noise;     /* [batch or 1, full_h, full_w] noise image (NoiseInjection) */
+  int64_t noise_bstride;  /* elements between samples of `noise` (0 = shared)          */
+  float noise_weight;     /* NoiseInjection.weight (host scalar) ...                   */
+  const float *noise_weight_dev; /* ... or, if non-NULL, a device scalar read by the kernel (no host sync) */
+  const float *bias;      /* [cout] FusedLeakyReLU / ToRGB bias                        */
+  int act;                /* 0 = none, 3 = leaky relu (as fused_bias_act)              */
+  float alpha;            /* negative slope                                            */
+  float scale;            /* output gain (sqrt 2)                                      */
+  const void *residual;   /* same layout/dtype as the output; added after activation   */
+  const void *residual2;  /* second residual (decoder skip fusion out + feat + feat2)  */
 } vsp_conv_epilogue;
 
 /*
@@ -172,6 +178,37 @@ int vsp_conv2d_fprop_bf16(const void *x, const void *wq, void *out,
                           int kh, int kw, int stride, int pad, int dil,
                           int out_nhwc_bf16, int64_t ldo, int64_t co_off,
                           const vsp_conv_epilogue *epi, void *stream);
+
+/*
+ * General "gather convolution" on the same tcgen05 kernel:
+ *   out[b, oh*os+oo_h, ow*os+oo_w, n] = sum_{t<ntaps} sum_c
+ *        x[b, oh*stride + tap_dy[t], ow*stride + tap_dx[t], c] * wq[g, tap_w[t], n, c]
+ * for oh < out_h, ow < out_w, written into an output whose spatial extent is
+ * [full_h, full_w].  Expresses input gradients (transposed weights + mirrored tap
+ * offsets: op/conv2d_gradfix.py:158-167) and the parity classes of stride-2 transposed
+ * convolutions.  wq is [groups, taps_total, cout_pad, cin].
+ */
+int vsp_conv2d_gather_bf16(const void *x, const void *wq, void *out,
+                           int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                           int64_t cin, int64_t cout, int64_t cout_pad, int taps_total,
+                           int ntaps, const int *tap_w, const int *tap_dy, const int *tap_dx,
+                           int stride, int64_t out_h, int64_t out_w,
+                           int out_nhwc_bf16, int64_t full_h, int64_t full_w,
+                           int os, int oo_h, int oo_w, int64_t ldo, int64_t co_off,
+                           const vsp_conv_epilogue *epi, void *stream);
+
+/*
+ * Stride-2 transposed convolution (padding 0) without zero-stuffing: four parity-class
+ * launches of the gather kernel. Replaces conv2d_gradfix.conv_transpose2d(stride=2,
+ * padding=0, groups=B) of models/RestoreNet.py:522-535.
+ *   x [batch, in_h, in_w, cin] bf16 NHWC -> out extent ((in_h-1)*2 + kh, (in_w-1)*2 + kw)
+ *   wq [groups, kh*kw, cout_pad, cin] (n = Cout, k = Cin, tap = kh_i*kw + kw_i, not flipped)
+ */
+int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void *out,
+                                 int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                                 int64_t cin, int64_t cout, int64_t cout_pad, int kh, int kw,
+                                 int out_nhwc_bf16, int64_t ldo, int64_t co_off,
+                                 const vsp_conv_epilogue *epi, void *stream);
 
 /*
  * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):

@@ -1,0 +1,229 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (through the C ABI).
+
+Two references: (1) the same convolution in fp32 on bf16-ROUNDED operands (isolates the kernel's
+indexing/accumulation: only summation order differs -> tight tolerance), (2) the un-rounded fp32
+result (the north_star bf16 tolerance: max-abs <= 1e-2 of the dynamic range, PSNR > 45 dB)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from vspbfr_b200.op import modconv as mc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def assert_close_tight(got, want, tol=2e-3):
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(1.0, float(want.abs().max()))
+    err = float((got - want).abs().max())
+    assert err <= tol * scale, f"max err {err} vs scale {scale}"
+
+
+def psnr(got, want):
+    peak = float(want.max() - want.min())
+    mse = float(((got - want) ** 2).mean())
+    return 10 * math.log10(peak * peak / max(mse, 1e-30))
+
+
+CASES = [
+    # b, cin, cout, h, w, k, stride, pad, dil
+    (2, 64, 64, 16, 16, 3, 1, 1, 1),
+    (1, 128, 256, 32, 32, 3, 1, 1, 1),
+    (2, 64, 16, 32, 32, 3, 1, 2, 2),
+    (2, 64, 16, 32, 32, 3, 1, 4, 4),
+    (1, 64, 16, 32, 32, 3, 1, 8, 8),
+    (2, 32, 32, 64, 64, 3, 1, 1, 1),
+    (2, 8, 24, 16, 16, 3, 1, 1, 1),
+    (2, 64, 3, 16, 16, 1, 1, 0, 1),
+    (3, 512, 512, 4, 4, 3, 1, 1, 1),
+    (2, 512, 128, 8, 8, 3, 1, 1, 1),
+    (1, 64, 64, 33, 33, 3, 1, 1, 1),
+    (1, 64, 64, 17, 40, 3, 1, 1, 1),
+    (2, 64, 128, 17, 17, 3, 2, 0, 1),
+    (1, 128, 64, 65, 65, 3, 2, 0, 1),
+    (1, 64, 64, 16, 16, 1, 2, 0, 1),
+    (1, 64, 64, 256, 256, 3, 1, 1, 1),
+    (1, 192, 320, 24, 24, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,k,stride,pad,dil", CASES)
+def test_fprop_shared_weights(b, cin, cout, h, w, k, stride, pad, dil):
+    g = torch.Generator(device="cpu").manual_seed(cin * 1000 + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(wt)
+    out = mc.conv_fprop(xq, wq, cout, k, k, stride, pad, dil)
+    want = F.conv2d(bf16r(x), bf16r(wt), None, stride, pad, dil)
+    assert_close_tight(out, want)
+
+
+def test_layout_roundtrip():
+    x = torch.randn(3, 20, 9, 11, device=DEV)
+    s = torch.rand(3, 20, device=DEV) + 0.5
+    q = mc.nchw_to_nhwc_bf16(x, s)
+    assert q.shape == (3, 9, 11, 24) and float(q[..., 20:].abs().max()) == 0.0
+    want = bf16r(x * s[:, :, None, None])
+    assert torch.equal(q[..., :20].permute(0, 3, 1, 2).float(), want)
+    assert torch.equal(mc.nhwc_bf16_to_nchw(q, 20), want)
+    assert torch.equal(mc.nchw_to_bf16(x, s).float(), want)
+
+
+@pytest.mark.parametrize("transpose", [False, True])
+def test_weight_prologue(transpose):
+    torch.manual_seed(5)
+    b, cout, cin, k = 3, 24, 40, 3
+    w = torch.randn(cout, cin, k, k, device=DEV)
+    s = torch.randn(b, cin, device=DEV)
+    scale = 1 / math.sqrt(cin * k * k)
+    wq, demod = mc.pack_weights(w, s, wscale=scale, transpose=transpose, want_demod=True, fold_demod=transpose)
+    m = scale * w[None] * s[:, None, :, None, None]
+    d = torch.rsqrt(m.pow(2).sum((2, 3, 4)) + 1e-8)
+    torch.testing.assert_close(demod, d, rtol=1e-5, atol=1e-6)
+    if transpose:
+        want = (m * d[:, :, None, None, None]).permute(0, 3, 4, 2, 1).reshape(b, k * k, cin, cout)
+    else:
+        want = m.permute(0, 3, 4, 1, 2).reshape(b, k * k, cout, cin)
+    torch.testing.assert_close(wq.float()[..., :want.shape[-1]], bf16r(want), rtol=1e-2, atol=1e-6)
+
+
+def _modconv_ref(x, w, s, demod, stride=1, pad=1, dil=1, round_ops=True):
+    b, cin = s.shape
+    cout, _, k, _ = w.shape
+    scale = 1 / math.sqrt(cin * k * k)
+    m = scale * w[None] * s[:, None, :, None, None]
+    d = torch.rsqrt(m.pow(2).sum((2, 3, 4)) + 1e-8) if demod else torch.ones(b, cout, device=x.device)
+    outs = []
+    for i in range(b):
+        if round_ops:
+            y = F.conv2d(bf16r(x[i:i + 1]), bf16r(m[i]), None, stride, pad, dil) * d[i][None, :, None, None]
+        else:
+            y = F.conv2d(x[i:i + 1], m[i] * d[i][:, None, None, None], None, stride, pad, dil)
+        outs.append(y)
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,k,dil,demod", [(2, 64, 64, 16, 3, 1, True), (3, 128, 32, 16, 3, 2, True),
+                                                       (2, 64, 3, 32, 1, 1, False), (4, 512, 512, 8, 3, 1, True)])
+def test_fprop_per_sample_weights_and_demod_epilogue(b, cin, cout, h, k, dil, demod):
+    torch.manual_seed(cin + cout)
+    x = torch.randn(b, cin, h, h, device=DEV)
+    w = torch.randn(cout, cin, k, k, device=DEV)
+    s = torch.randn(b, cin, device=DEV) * 0.5 + 1.0
+    scale = 1 / math.sqrt(cin * k * k)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, d = mc.pack_weights(w, s, wscale=scale, want_demod=demod)
+    pad = (k - 1) * dil // 2
+    out = mc.conv_fprop(xq, wq, cout, k, k, 1, pad, dil, epi=mc.make_epilogue(row_scale=d) if demod else None)
+    assert_close_tight(out, _modconv_ref(x, w, s, demod, 1, pad, dil))
+    full = _modconv_ref(x, w, s, demod, 1, pad, dil, round_ops=False)
+    peak = float(full.max() - full.min())
+    assert float((out - full).abs().max()) <= 1e-2 * peak
+    assert psnr(out, full) > 45.0
+
+
+def test_epilogue_noise_bias_act_residual_nhwc_and_nchw():
+    torch.manual_seed(9)
+    b, cin, cout, h = 2, 64, 48, 16
+    x = torch.randn(b, cin, h, h, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / 24
+    noise = torch.randn(b, 1, h, h, device=DEV)
+    bias = torch.randn(cout, device=DEV)
+    res = torch.randn(b, cout, h, h, device=DEV)
+    res2 = torch.randn(b, cout, h, h, device=DEV)
+    rs = torch.rand(b, cout, device=DEV) + 0.5
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(w)
+    base = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise + bias[None, :, None, None]
+    want = F.leaky_relu(base, 0.2) * math.sqrt(2)
+    # NCHW fp32 output, fp32 residuals
+    epi = mc.make_epilogue(row_scale=rs, noise=noise, noise_weight=0.37, bias=bias, act=3, alpha=0.2,
+                           scale=math.sqrt(2), residual=res, residual2=res2)
+    out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, 1, 1, epi=epi)
+    assert_close_tight(out, want + res + res2)
+    # device-side noise weight, shared noise image
+    nw = torch.tensor([0.37], device=DEV)
+    epi = mc.make_epilogue(row_scale=rs, noise=noise[:1], noise_weight_dev=nw, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2))
+    out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, 1, 1, epi=epi)
+    base1 = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise[:1] + bias[None, :, None, None]
+    assert_close_tight(out, F.leaky_relu(base1, 0.2) * math.sqrt(2))
+    # NHWC bf16 output with bf16 residual, written at a channel offset of a wider buffer
+    resq = mc.nchw_to_nhwc_bf16(res)  # same layout as the output (48 channels)
+    buf = torch.zeros(b, h, h, 64, dtype=torch.bfloat16, device=DEV)
+    epi = mc.make_epilogue(row_scale=rs[:, :16].contiguous(), bias=bias[:16].contiguous(), act=3, alpha=0.2, scale=math.sqrt(2))
+    wq16, _ = mc.pack_weights(w[:16].contiguous())
+    mc.conv_fprop(xq, wq16, 16, 3, 3, 1, 1, 1, epi=epi, out=buf, out_nhwc=True, co_off=32)
+    want16 = F.leaky_relu(F.conv2d(bf16r(x), bf16r(w[:16]), None, 1, 1) * rs[:, :16, None, None] + bias[None, :16, None, None], 0.2) * math.sqrt(2)
+    got = buf[..., 32:48].permute(0, 3, 1, 2).float()
+    assert_close_tight(got, want16, tol=1e-2)
+    assert float(buf[..., :32].abs().max()) == 0 and float(buf[..., 48:].abs().max()) == 0
+    epi = mc.make_epilogue(residual=resq)
+    wq48, _ = mc.pack_weights(w)
+    o2 = mc.conv_fprop(xq, wq48, cout, 3, 3, 1, 1, 1, epi=epi, out_nhwc=True)
+    want2 = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) + bf16r(res)
+    assert_close_tight(o2[..., :cout].permute(0, 3, 1, 2).float(), want2, tol=1e-2)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w_", [(2, 64, 64, 8, 8), (1, 128, 32, 16, 16), (2, 64, 64, 4, 4), (1, 64, 128, 7, 9)])
+def test_transposed_stride2(b, cin, cout, h, w_):
+    torch.manual_seed(h * 7 + cin)
+    x = torch.randn(b, cin, h, w_, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(w)
+    out = mc.conv_transpose_s2(xq, wq, cout, 3, 3)
+    want = F.conv_transpose2d(bf16r(x), bf16r(w).transpose(0, 1), None, stride=2, padding=0)
+    assert_close_tight(out, want)
+
+
+def test_dgrad_via_gather_matches_autograd():
+    torch.manual_seed(21)
+    b, cin, cout, h, k, dil = 2, 64, 96, 16, 3, 2
+    pad = dil
+    x = torch.randn(b, cin, h, h, device=DEV, requires_grad=True)
+    w = torch.randn(cout, cin, k, k, device=DEV) / 24
+    dy = torch.randn(b, cout, h, h, device=DEV)
+    y = F.conv2d(x, bf16r(w), None, 1, pad, dil)
+    (want,) = torch.autograd.grad(y, x, bf16r(dy))
+    wq_t, _ = mc.pack_weights(w, transpose=True)
+    dyq = mc.nchw_to_nhwc_bf16(dy)
+    taps = [(i, j) for i in range(k) for j in range(k)]
+    got = mc.conv_gather(dyq, wq_t, cin, [i * k + j for i, j in taps], [pad - i * dil for i, j in taps],
+                         [pad - j * dil for i, j in taps], 1, (h, h))
+    assert_close_tight(got, want)
+
+
+def test_config2_full_size_forward():
+    """BASELINE config 2: B=8, 512->512, 3x3, 64x64, demodulated."""
+    torch.manual_seed(0)
+    b, c, h = 8, 512, 64
+    x = torch.randn(b, c, h, h, device=DEV)
+    w = torch.randn(c, c, 3, 3, device=DEV)
+    s = torch.randn(b, c, device=DEV) * 0.3 + 1.0
+    scale = 1 / math.sqrt(c * 9)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, d = mc.pack_weights(w, s, wscale=scale, want_demod=True)
+    out = mc.conv_fprop(xq, wq, c, 3, 3, 1, 1, 1, epi=mc.make_epilogue(row_scale=d))
+    assert_close_tight(out, _modconv_ref(x, w, s, True))
+    full = _modconv_ref(x, w, s, True, round_ops=False)
+    peak = float(full.max() - full.min())
+    assert float((out - full).abs().max()) <= 1e-2 * peak
+    assert psnr(out, full) > 45.0

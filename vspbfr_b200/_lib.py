@@ -101,12 +101,15 @@ class ConvEpilogue(Structure):
     _fields_ = [
         ("row_scale", c_void_p),
         ("noise", c_void_p),
+        ("noise_bstride", c_int64),
         ("noise_weight", c_float),
+        ("noise_weight_dev", c_void_p),
         ("bias", c_void_p),
         ("act", c_int),
         ("alpha", c_float),
         ("scale", c_float),
         ("residual", c_void_p),
+        ("residual2", c_void_p),
     ]
 
 
@@ -137,6 +140,14 @@ SIGNATURES = {
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_conv2d_gather_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int,
+                                       c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, c_int64, c_int64,
+                                       c_int, c_int64, c_int64, c_int, c_int, c_int, c_int64, c_int64,
+                                       POINTER(ConvEpilogue), c_void_p]),
+    "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
+                                             c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                             c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),

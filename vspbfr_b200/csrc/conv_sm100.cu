@@ -51,6 +51,7 @@ struct ConvParams {
   const float *noise;
   long long noise_bstride;
   float noise_weight;
+  const float *noise_weight_dev;
   const float *bias;
   int act;
   float alpha, scale;
@@ -190,7 +191,8 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
       const long long pix = (long long)fh * p.full_w + fw;          // within one [full_h, full_w] plane
       const long long plane = (long long)p.full_h * p.full_w;
       float nz = 0.f;
-      if (p.noise != nullptr && pix_ok) nz = p.noise_weight * __ldg(p.noise + b * p.noise_bstride + pix);
+      if (p.noise != nullptr && pix_ok)
+        nz = (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) * __ldg(p.noise + b * p.noise_bstride + pix);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
@@ -237,7 +239,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
                 a += nz;
                 if (p.bias) a += __ldg(p.bias + n);
                 a = epi_act(a, p.act, p.alpha, p.scale);
-                if (res) a += __bfloat162float(res[off - (o - static_cast<__nv_bfloat16 *>(p.out)) + (o - static_cast<__nv_bfloat16 *>(p.out)) + j]);
+                if (res) a += __bfloat162float(res[off + j]);
                 if (res2) a += __bfloat162float(res2[off + j]);
               }
               v[j] = a;
@@ -323,8 +325,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
                        int ntaps, const int *tap_w, const int *tap_dy, const int *tap_dx, int stride,
                        int64_t out_h, int64_t out_w, void *out, int out_nhwc, int64_t full_h,
                        int64_t full_w, int os, int oo_h, int oo_w, int64_t ldo, int64_t co_off,
-                       const vsp_conv_epilogue *epi, const float *noise, int64_t noise_bstride,
-                       const void *residual2, cudaStream_t stream) {
+                       const vsp_conv_epilogue *epi, cudaStream_t stream) {
   VSP_REQUIRE(batch >= 1 && (groups == 1 || groups == batch), "conv: groups must be 1 or batch");
   VSP_REQUIRE(cin >= 8 && cin % 8 == 0, "conv: cin must be a multiple of 8 (pad NHWC channels), got %lld", (long long)cin);
   VSP_REQUIRE(cout >= 1 && cout_pad >= cout, "conv: bad cout");
@@ -355,9 +356,10 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   if (epi) {
     p.row_scale = epi->row_scale; p.noise_weight = epi->noise_weight; p.bias = epi->bias;
     p.act = epi->act; p.alpha = epi->alpha; p.scale = epi->scale; p.residual = epi->residual;
+    p.noise = epi->noise; p.noise_bstride = epi->noise_bstride; p.residual2 = epi->residual2;
+    p.noise_weight_dev = epi->noise_weight_dev;
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
   }
-  p.noise = noise; p.noise_bstride = noise_bstride; p.residual2 = residual2;
 
   // A operand: NHWC bf16 activations as a 4-D tensor (c, w, h, b); the box is one tap-shifted
   // patch of th x tw pixels x 64 channels; stride-2 convs use the TMA traversal stride.
@@ -367,10 +369,6 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     uint64_t strides[4] = {0, (uint64_t)cin * 2, (uint64_t)cin * in_w * 2, (uint64_t)cin * in_w * in_h * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), 1};
     uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-    if (stride == 2) {  // bounding box of the strided traversal: (n-1)*2 + 1 elements
-      box[1] = (uint32_t)((p.tw - 1) * 2 + 1);
-      box[2] = (uint32_t)((p.th - 1) * 2 + 1);
-    }
     if (int rc = encode_tma(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, es,
                             CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
@@ -405,6 +403,53 @@ extern "C" int vsp_conv2d_fprop_bf16(const void *x, const void *wq, void *out, i
     }
   if (!out_nhwc_bf16) { ldo = cout; co_off = 0; }
   return conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout_pad, kh * kw, kh * kw, tw_, dy, dx,
-                            stride, out_h, out_w, out, out_nhwc_bf16, out_h, out_w, 1, 0, 0, ldo, co_off, epi,
-                            epi ? epi->noise : nullptr, epi && epi->noise ? out_h * out_w : 0, nullptr, stream);
+                            stride, out_h, out_w, out, out_nhwc_bf16, out_h, out_w, 1, 0, 0, ldo, co_off, epi, stream);
+}
+
+extern "C" int vsp_conv2d_gather_bf16(const void *x, const void *wq, void *out, int64_t batch, int64_t groups,
+                                      int64_t in_h, int64_t in_w, int64_t cin, int64_t cout, int64_t cout_pad,
+                                      int taps_total, int ntaps, const int *tap_w, const int *tap_dy,
+                                      const int *tap_dx, int stride, int64_t out_h, int64_t out_w,
+                                      int out_nhwc_bf16, int64_t full_h, int64_t full_w, int os, int oo_h,
+                                      int oo_w, int64_t ldo, int64_t co_off, const vsp_conv_epilogue *epi,
+                                      void *stream_) {
+  using namespace vsp;
+  VSP_REQUIRE(tap_w && tap_dy && tap_dx, "conv2d_gather: null tap list");
+  VSP_REQUIRE(os >= 1 && oo_h >= 0 && oo_w >= 0, "conv2d_gather: bad output mapping");
+  VSP_REQUIRE((out_h - 1) * os + oo_h < full_h && (out_w - 1) * os + oo_w < full_w,
+              "conv2d_gather: output mapping exceeds the full extent");
+  if (!out_nhwc_bf16) { ldo = cout; co_off = 0; }
+  return conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout_pad, taps_total, ntaps, tap_w, tap_dy,
+                            tap_dx, stride, out_h, out_w, out, out_nhwc_bf16, full_h, full_w, os, oo_h, oo_w, ldo,
+                            co_off, epi, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void *out, int64_t batch,
+                                            int64_t groups, int64_t in_h, int64_t in_w, int64_t cin,
+                                            int64_t cout, int64_t cout_pad, int kh, int kw, int out_nhwc_bf16,
+                                            int64_t ldo, int64_t co_off, const vsp_conv_epilogue *epi,
+                                            void *stream_) {
+  using namespace vsp;
+  VSP_REQUIRE(kh >= 1 && kw >= 1 && kh * kw <= kMaxTaps, "conv_transpose2d_s2: kernel up to 16 taps");
+  const int64_t full_h = (in_h - 1) * 2 + kh, full_w = (in_w - 1) * 2 + kw;
+  if (!out_nhwc_bf16) { ldo = cout; co_off = 0; }
+  // out[2a+pa, 2b+pb] = sum_{kh_i = pa (mod 2), kw_i = pb (mod 2)} x[a - (kh_i-pa)/2, b - (kw_i-pb)/2] * w[kh_i, kw_i]
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      int tw_[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps], nt = 0;
+      for (int i = pa; i < kh; i += 2)
+        for (int j = pb; j < kw; j += 2) {
+          tw_[nt] = i * kw + j;
+          dy[nt] = -(i - pa) / 2;
+          dx[nt] = -(j - pb) / 2;
+          ++nt;
+        }
+      const int64_t oh = (full_h - pa + 1) / 2, ow = (full_w - pb + 1) / 2;
+      if (nt == 0 || oh <= 0 || ow <= 0) continue;  // (a class with no taps stays zero: caller pre-zeroes if kh or kw == 1)
+      if (int rc = conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout_pad, kh * kw, nt, tw_, dy, dx, 1,
+                                      oh, ow, out, out_nhwc_bf16, full_h, full_w, 2, pa, pb, ldo, co_off, epi,
+                                      static_cast<cudaStream_t>(stream_)))
+        return rc;
+    }
+  return 0;
 }

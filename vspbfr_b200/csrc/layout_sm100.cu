@@ -134,8 +134,7 @@ pack_weights_kernel(const float *__restrict__ w, const float *__restrict__ s,
   const float *wr = w + (o * cin + i) * taps;
   __nv_bfloat16 *dst = wq + b * taps * n_pad * k_pad + idx;
   for (int t = 0; t < taps; ++t) {
-    const int tt = transpose ? taps - 1 - t : t;
-    dst[(long long)tt * n_pad * k_pad] = __float2bfloat16_rn(valid ? wr[t] * f : 0.f);
+    dst[(long long)t * n_pad * k_pad] = __float2bfloat16_rn(valid ? wr[t] * f : 0.f);
   }
 }
 

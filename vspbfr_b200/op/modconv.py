@@ -1,5 +1,263 @@
-"""placeholder — filled in with the tcgen05 convolution host side."""
+"""Host side of the tcgen05 convolution: layout conversion, weight prologue, conv launches and the
+autograd Functions that implement the modulated convolution and the plain-conv primitives of
+conv2d_gradfix on top of them.
+
+Reference semantics: models/RestoreNet.py:478-555 (ModulatedConv2d.forward, fused branch),
+:334-418 (Dilated_ModulatedConv2d), op/conv2d_gradfix.py:134-223 (closed gradient set).
+Precision contract (north_star): operands are rounded to bf16, products accumulate in fp32 on
+the tensor cores, demodulation is applied in fp32 in the epilogue.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+from torch.autograd import Function
+
+from .. import _lib
+from .._lib import ConvEpilogue, ptr, stream_ptr
 
 
-def plain_conv_supported(*a, **k):
-    return False
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+# ----------------------------------------------------------------------------------------------
+# thin wrappers over the C ABI
+# ----------------------------------------------------------------------------------------------
+
+def nchw_to_nhwc_bf16(x, scale_nc=None, c_pad=None):
+    """[N,C,H,W] fp32 -> [N,H,W,c_pad] bf16 (optionally * scale_nc[n,c]); extra channels are zero."""
+    n, c, h, w = x.shape
+    c_pad = c_pad or _round_up(c, 8)
+    x = x.contiguous()
+    y = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16(ptr(x), ptr(scale_nc), ptr(y), n, c, h * w, c_pad, stream_ptr())
+        _lib.check(rc, "nchw_f32_to_nhwc_bf16")
+    return y
+
+
+def nhwc_bf16_to_nchw(x, c=None):
+    """[N,H,W,c_pad] bf16 -> [N,c,H,W] fp32."""
+    n, h, w, c_pad = x.shape
+    c = c or c_pad
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().vsp_nhwc_bf16_to_nchw_f32(ptr(x.contiguous()), ptr(y), n, c, h * w, c_pad, stream_ptr())
+        _lib.check(rc, "nhwc_bf16_to_nchw_f32")
+    return y
+
+
+def nchw_to_bf16(x, scale_nc=None):
+    """[N,C,H,W] fp32 -> same layout bf16, optionally * scale_nc[n,c]."""
+    n, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty_like(x, dtype=torch.bfloat16)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().vsp_nchw_f32_to_bf16(ptr(x), ptr(scale_nc), ptr(y), n * c, h * w, stream_ptr())
+        _lib.check(rc, "nchw_f32_to_bf16")
+    return y
+
+
+def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want_demod=False, fold_demod=False,
+                 batch=None):
+    """weight [Cout,Cin,kh,kw] fp32 (+ style [B,Cin]) -> (wq bf16 [G,taps,n_pad,k_pad], demod [G,Cout] | None).
+
+    G = B when a style is given (per-sample modulated weights), else 1.
+    """
+    cout, cin, kh, kw = weight.shape
+    taps = kh * kw
+    g = style.shape[0] if style is not None else 1
+    n_real, k_real = (cin, cout) if transpose else (cout, cin)
+    n_pad, k_pad = n_real, _round_up(k_real, 8)
+    weight = weight.contiguous()
+    if style is not None:
+        style = style.contiguous()
+    wq = torch.empty((g, taps, n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
+    demod = torch.empty((g, cout), dtype=torch.float32, device=weight.device) if (want_demod or fold_demod) else None
+    with torch.cuda.device(weight.device):
+        rc = _lib.load().vsp_modulate_weights_bf16(ptr(weight), ptr(style), ptr(demod), ptr(wq), g, cout, cin, taps,
+                                                   wscale, eps, int(transpose), int(fold_demod), n_pad, k_pad,
+                                                   stream_ptr())
+    _lib.check(rc, "modulate_weights_bf16")
+    return wq, demod
+
+
+def make_epilogue(row_scale=None, noise=None, noise_weight=0.0, noise_weight_dev=None, bias=None, act=0, alpha=0.2,
+                  scale=1.0, residual=None, residual2=None):
+    """Build a ``vsp_conv_epilogue``; returns (struct, keepalive tuple)."""
+    e = ConvEpilogue()
+    e.row_scale = row_scale.data_ptr() if row_scale is not None else None
+    e.noise = noise.data_ptr() if noise is not None else None
+    if noise is not None:
+        e.noise_bstride = 0 if noise.shape[0] == 1 else noise[0].numel()
+    e.noise_weight = float(noise_weight)
+    e.noise_weight_dev = noise_weight_dev.data_ptr() if noise_weight_dev is not None else None
+    e.bias = bias.data_ptr() if bias is not None else None
+    e.act, e.alpha, e.scale = int(act), float(alpha), float(scale)
+    e.residual = residual.data_ptr() if residual is not None else None
+    e.residual2 = residual2.data_ptr() if residual2 is not None else None
+    return e, (row_scale, noise, noise_weight_dev, bias, residual, residual2)
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def conv_out_size(n, k, stride, pad, dil):
+    return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
+
+
+def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=None, out_nhwc=False, co_off=0):
+    """out = conv(x_nhwc, wq) (+ epilogue).  x_nhwc [B,H,W,Cin_pad] bf16, wq [G,taps,cout_pad,Cin_pad] bf16."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps, cout_pad, k_pad = wq.shape
+    assert taps == kh * kw and k_pad == cin, (wq.shape, x_nhwc.shape, kh, kw)
+    oh, ow = conv_out_size(h, kh, stride, pad, dil), conv_out_size(w, kw, stride, pad, dil)
+    if out is None:
+        if out_nhwc:
+            out = torch.empty((b, oh, ow, _round_up(cout, 8)), dtype=torch.bfloat16, device=x_nhwc.device)
+            if out.shape[3] != cout:
+                out.zero_()
+        else:
+            out = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=x_nhwc.device)
+    ldo = out.shape[3] if out_nhwc else cout
+    e, keep = epi if epi is not None else (None, None)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().vsp_conv2d_fprop_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw,
+                                               stride, pad, dil, int(out_nhwc), ldo, co_off,
+                                               ctypes.byref(e) if e is not None else None, stream_ptr())
+    _lib.check(rc, "conv2d_fprop_bf16")
+    return out
+
+
+def conv_gather(x_nhwc, wq, cout, tap_w, tap_dy, tap_dx, stride, out_hw, full_hw=None, os_=1, oo=(0, 0), epi=None,
+                out=None, out_nhwc=False, co_off=0):
+    """General tap-list convolution (input gradients, parity classes); see vsp_conv2d_gather_bf16."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps_total, cout_pad, k_pad = wq.shape
+    assert k_pad == cin
+    oh, ow = out_hw
+    fh, fw = full_hw or out_hw
+    if out is None:
+        if out_nhwc:
+            out = torch.zeros((b, fh, fw, _round_up(cout, 8)), dtype=torch.bfloat16, device=x_nhwc.device)
+        else:
+            out = torch.zeros((b, cout, fh, fw), dtype=torch.float32, device=x_nhwc.device)
+    ldo = out.shape[3] if out_nhwc else cout
+    e, keep = epi if epi is not None else (None, None)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().vsp_conv2d_gather_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad,
+                                                taps_total, len(tap_w), _int_array(tap_w), _int_array(tap_dy),
+                                                _int_array(tap_dx), stride, oh, ow, int(out_nhwc), fh, fw, os_,
+                                                oo[0], oo[1], ldo, co_off,
+                                                ctypes.byref(e) if e is not None else None, stream_ptr())
+    _lib.check(rc, "conv2d_gather_bf16")
+    return out
+
+
+def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
+    """Stride-2, padding-0 transposed convolution -> extent ((H-1)*2+kh, (W-1)*2+kw)."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps, cout_pad, k_pad = wq.shape
+    assert taps == kh * kw and k_pad == cin
+    fh, fw = (h - 1) * 2 + kh, (w - 1) * 2 + kw
+    if out_nhwc:
+        out = torch.empty((b, fh, fw, _round_up(cout, 8)), dtype=torch.bfloat16, device=x_nhwc.device)
+        if out.shape[3] != cout or kh == 1 or kw == 1:
+            out.zero_()
+    else:
+        out = torch.empty((b, cout, fh, fw), dtype=torch.float32, device=x_nhwc.device)
+        if kh == 1 or kw == 1:
+            out.zero_()
+    ldo = out.shape[3] if out_nhwc else cout
+    e, keep = epi if epi is not None else (None, None)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().vsp_conv_transpose2d_s2_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad,
+                                                      kh, kw, int(out_nhwc), ldo, 0,
+                                                      ctypes.byref(e) if e is not None else None, stream_ptr())
+    _lib.check(rc, "conv_transpose2d_s2_bf16")
+    return out
+
+
+def conv_wgrad(dy_nchw_bf16, x_nchw_bf16, groups, kh, kw, stride, pad, dil):
+    """gw[g,o,i,t] = sum_p dy[b,o,p] x[b,i,p*stride + t*dil - pad]; groups == batch or 1."""
+    b, cout, oh, ow = dy_nchw_bf16.shape
+    _, cin, h, w = x_nchw_bf16.shape
+    gw = torch.empty((groups, cout, cin, kh * kw), dtype=torch.float32, device=dy_nchw_bf16.device)
+    with torch.cuda.device(dy_nchw_bf16.device):
+        rc = _lib.load().vsp_conv2d_wgrad_bf16(ptr(dy_nchw_bf16), ptr(x_nchw_bf16), ptr(gw), b, groups, h, w, cin, cout,
+                                               oh, ow, kh, kw, stride, pad, dil, stream_ptr())
+    _lib.check(rc, "conv2d_wgrad_bf16")
+    return gw
+
+
+def weight_style_grad(gw, weight, style, demod, wscale, want_dw=True, want_ds=True):
+    b, cout, cin, taps = gw.shape
+    dw = torch.empty((cout, cin, taps), dtype=torch.float32, device=gw.device) if want_dw else None
+    ds = torch.empty((b, cin), dtype=torch.float32, device=gw.device) if want_ds else None
+    with torch.cuda.device(gw.device):
+        rc = _lib.load().vsp_modconv_weight_style_grad(ptr(gw), ptr(weight.contiguous()), ptr(style.contiguous()),
+                                                       ptr(demod), ptr(dw), ptr(ds), b, cout, cin, taps, wscale,
+                                                       stream_ptr())
+    _lib.check(rc, "modconv_weight_style_grad")
+    return dw, ds
+
+
+# ----------------------------------------------------------------------------------------------
+# plain convolution primitives for conv2d_gradfix (NCHW fp32 boundary)
+# ----------------------------------------------------------------------------------------------
+
+def plain_conv_supported(input, weight_shape, stride, padding, dilation, groups, transpose):
+    """The tcgen05 path covers square stride-1/2 convs with <= 16 taps; groups == 1, or the
+    reference's grouped form (input [1, B*Cin, H, W], groups == B)."""
+    if input.dtype != torch.float32 or input.ndim != 4:
+        return False
+    if transpose:
+        return False  # transposed fprop of conv2d_gradfix goes through ATen for now
+    cout_total, cin_g, kh, kw = weight_shape
+    if kh * kw > 16 or stride[0] != stride[1] or stride[0] not in (1, 2):
+        return False
+    if padding[0] != padding[1] or dilation[0] != dilation[1]:
+        return False
+    if groups != 1 and input.shape[0] != 1:
+        return False
+    if cin_g < 8 or input.shape[2] < 1:
+        return False
+    return True
+
+
+def plain_conv_fprop(input, weight, bias, stride, padding, dilation, groups):
+    n, c_total, h, w = input.shape
+    cout_total, cin, kh, kw = weight.shape
+    cout = cout_total // groups
+    if groups == 1:
+        x = nchw_to_nhwc_bf16(input)
+        wq, _ = pack_weights(weight)
+        epi = make_epilogue(bias=bias) if bias is not None else None
+        return conv_fprop(x, wq, cout, kh, kw, stride[0], padding[0], dilation[0], epi=epi)
+    # grouped form of the modulated conv: [1, B*Cin, H, W] x [B*Cout, Cin, k, k]
+    x = nchw_to_nhwc_bf16(input.reshape(groups, cin, h, w))
+    wq = weight.reshape(groups, cout, cin, kh * kw).permute(0, 3, 1, 2)
+    k_pad = _round_up(cin, 8)
+    wq_p = torch.zeros((groups, kh * kw, cout, k_pad), dtype=torch.bfloat16, device=input.device)
+    wq_p[..., :cin] = wq.to(torch.bfloat16)
+    out = conv_fprop(x, wq_p, cout, kh, kw, stride[0], padding[0], dilation[0])
+    out = out.reshape(1, groups * cout, out.shape[2], out.shape[3])
+    if bias is not None:
+        out = out + bias.reshape(1, -1, 1, 1)
+    return out
+
+
+def plain_conv_dgrad(*a, **k):  # pragma: no cover - routed to ATen by plain_conv_supported
+    raise RuntimeError("plain_conv_dgrad: not routed to tcgen05")
+
+
+def plain_conv_wgrad(grad_output, input, weight_shape, stride, padding, dilation, groups):
+    """Returns None when the wgrad kernel does not cover the shape (caller uses ATen)."""
+    return None
