@@ -212,10 +212,11 @@ int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void *out,
 
 /*
  * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):
- *   gw[g, o, i, t] = sum_{p in sample(s) of group g} dy[b,o,p] * x[b,i,p*stride + t*dil - pad]
+ *   gw[g, t, o, i] = sum_{p in sample(s) of group g} dy[b,p,o] * x[b, p*stride + t*dil - pad, i]
  * Replaces aten::cudnn_convolution_backward_weight, op/conv2d_gradfix.py:177-199.
- *   dy [batch, cout, out_h, out_w] bf16 NCHW, x [batch, cin, in_h, in_w] bf16 NCHW
- *   gw [groups, cout, cin, kh*kw] fp32; groups == batch (per-sample) or 1
+ *   dy [batch, out_h, out_w, cout] bf16 NHWC, x [batch, in_h, in_w, cin] bf16 NHWC
+ *   (cin, cout multiples of 8); both operands are consumed channel-contiguous (MN-major UMMA).
+ *   gw [groups, kh*kw, cout, cin] fp32 (TAP-major); groups == batch (per-sample) or 1
  *   (summed over the batch).
  */
 int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw,
@@ -225,7 +226,8 @@ int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw,
 
 /*
  * Style / shared-weight gradients of the modulated convolution from the
- * per-sample raw weight gradient G = gw[b,o,i,t] (of the un-demodulated
+ * per-sample raw weight gradient G = gw[b,t,o,i] (tap-major, as written by
+ * vsp_conv2d_wgrad_bf16; of the un-demodulated
  * product z, i.e. computed from dz = demod * dy):
  *   m = wscale*W*s ; dm = G - demod^2 * (sum_{i,t} m*G) * m      (demod != NULL)
  *   dW[o,i,t] = wscale * sum_b s[b,i] * dm ;  ds[b,i] = wscale * sum_{o,t} W * dm

@@ -227,3 +227,117 @@ def test_config2_full_size_forward():
     peak = float(full.max() - full.min())
     assert float((out - full).abs().max()) <= 1e-2 * peak
     assert psnr(out, full) > 45.0
+
+
+# ---------------------------------------------------------------------------------------------
+# weight gradient (MN-major UMMA, K = pixels) and the full modulated-conv autograd Function
+# ---------------------------------------------------------------------------------------------
+from conftest import load_golden  # noqa: E402
+from vspbfr_b200 import op  # noqa: E402
+
+MOD = load_golden("modconv")
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w_,k,stride,pad,dil,groups", [
+    (2, 64, 64, 16, 16, 3, 1, 1, 1, 2),
+    (2, 64, 128, 16, 16, 3, 1, 1, 1, 1),
+    (1, 128, 256, 8, 8, 3, 1, 1, 1, 1),
+    (2, 256, 64, 32, 32, 3, 1, 2, 2, 2),
+    (1, 64, 16, 64, 64, 3, 1, 4, 4, 1),
+    (2, 32, 24, 12, 20, 3, 1, 1, 1, 2),
+    (2, 64, 8, 16, 16, 1, 1, 0, 1, 2),
+    (2, 64, 64, 17, 17, 3, 2, 0, 1, 2),
+    (1, 64, 64, 128, 128, 3, 1, 1, 1, 1),
+    (3, 512, 512, 4, 4, 3, 1, 1, 1, 3),
+])
+def test_wgrad(b, cin, cout, h, w_, k, stride, pad, dil, groups):
+    torch.manual_seed(cin + cout + h)
+    x = torch.randn(b, cin, h, w_, device=DEV)
+    oh, ow = mc.conv_out_size(h, k, stride, pad, dil), mc.conv_out_size(w_, k, stride, pad, dil)
+    dy = torch.randn(b, cout, oh, ow, device=DEV)
+    gw = mc.conv_wgrad(mc.nchw_to_nhwc_bf16(dy), mc.nchw_to_nhwc_bf16(x), groups, k, k, stride, pad, dil)
+    assert gw.shape == (groups, k * k, cout, cin)
+    wants = []
+    for bi in range(b):
+        xr = bf16r(x[bi:bi + 1]).requires_grad_(True)
+        wdummy = torch.zeros(cout, cin, k, k, device=DEV, requires_grad=True)
+        y = F.conv2d(xr, wdummy, None, stride, pad, dil)
+        (g,) = torch.autograd.grad(y, wdummy, bf16r(dy[bi:bi + 1]))
+        wants.append(g)
+    want = torch.stack(wants)                      # [b, cout, cin, k, k]
+    if groups == 1:
+        want = want.sum(0, keepdim=True)
+    want = want.reshape(groups, cout, cin, k * k).permute(0, 3, 1, 2)
+    assert_close_tight(gw, want, tol=3e-3)
+
+
+def _run_modconv(name, x, style_or_s, sd, rate=1):
+    w = torch.from_numpy(sd["weight"]).to(DEV).requires_grad_(True)
+    x = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    st = torch.from_numpy(style_or_s).to(DEV).requires_grad_(True)
+    if "modulation.weight" in sd:
+        mw = torch.from_numpy(sd["modulation.weight"]).to(DEV)
+        mb = torch.from_numpy(sd["modulation.bias"]).to(DEV)
+        s = F.linear(st, mw * (1.0 / mw.shape[1] ** 0.5), mb)
+    else:
+        s = st
+    demod = "nodemod" not in name and "torgb" not in name
+    mode = "up" if name.endswith("_up") else ("down" if name.endswith("_down") else "same")
+    blur = torch.tensor(np.outer([1, 3, 3, 1], [1, 3, 3, 1]) / 64.0, dtype=torch.float32, device=DEV)
+    xin = x
+    if mode == "down":
+        xin = op.upfirdn2d(x, blur, pad=(2, 2))
+    y = mc.modulated_conv2d(xin, w, s, demod, mode, rate)
+    if mode == "up":
+        y = op.upfirdn2d(y, blur * 4, pad=(1, 1))
+    return x, st, w, y
+
+
+@pytest.mark.parametrize("name", [str(n) for n in MOD["names"]])
+def test_modulated_conv_golden_forward_backward(name):
+    """bf16 tensor-core path vs the reference's fp32 CPU output: max-abs <= 1e-2 of the dynamic
+    range and PSNR > 45 dB (north_star), for outputs and first-order gradients."""
+    sd = {k.split(".sd.")[1]: MOD[k] for k in MOD.files if k.startswith(name + ".sd.")}
+    rate = int(name.split("_r")[1]) if name.startswith("dilated") else 1
+    x, st, w, y = _run_modconv(name, MOD[f"{name}.x"], MOD[f"{name}.style"], sd, rate)
+
+    def check(got, want_np, what):
+        want = torch.from_numpy(want_np).to(DEV)
+        assert got.shape == want.shape, (what, got.shape, want.shape)
+        peak = float(want.max() - want.min())
+        err = float((got - want).abs().max())
+        assert err <= 1e-2 * peak, f"{what}: max-abs {err} > 1e-2 * {peak}"
+        assert psnr(got, want) > 45.0, f"{what}: psnr {psnr(got, want)}"
+
+    check(y, MOD[f"{name}.y"], "y")
+    gx, gs, gw = torch.autograd.grad(y, [x, st, w], torch.from_numpy(MOD[f"{name}.go"]).to(DEV))
+    check(gx, MOD[f"{name}.gx"], "gx")
+    check(gs, MOD[f"{name}.gstyle"], "gstyle")
+    check(gw, MOD[f"{name}.gw"], "gw")
+
+
+def test_modulated_conv_double_backward_runs_and_matches_fp32():
+    """R1-style double backward through the modulated conv (create_graph=True)."""
+    torch.manual_seed(3)
+    b, cin, cout, h = 2, 16, 16, 8
+    x = torch.randn(b, cin, h, h, device=DEV, requires_grad=True)
+    w = torch.randn(1, cout, cin, 3, 3, device=DEV, requires_grad=True)
+    s = (torch.randn(b, cin, device=DEV) * 0.3 + 1).requires_grad_(True)
+
+    def penalty(fn):
+        y = fn(x, w, s)
+        (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        return torch.autograd.grad(gx.pow(2).sum(), [w, s])
+
+    got = penalty(lambda x_, w_, s_: mc.modulated_conv2d(x_, w_, s_, True, "same", 1))
+
+    def ref(x_, w_, s_):
+        scale = 1 / math.sqrt(cin * 9)
+        m = scale * w_ * s_.reshape(b, 1, cin, 1, 1)
+        m = m * torch.rsqrt(m.pow(2).sum([2, 3, 4]) + 1e-8).reshape(b, cout, 1, 1, 1)
+        return F.conv2d(x_.reshape(1, b * cin, h, h), m.reshape(b * cout, cin, 3, 3), padding=1, groups=b).reshape(b, cout, h, h)
+
+    want = penalty(ref)
+    for g, wv in zip(got, want):
+        peak = float(wv.abs().max())
+        assert float((g - wv).abs().max()) <= 3e-2 * peak

@@ -138,6 +138,7 @@ pack_weights_kernel(const float *__restrict__ w, const float *__restrict__ s,
   }
 }
 
+// Per-sample raw weight gradients arrive tap-major: G[b][t][o][i] (what wgrad_sm100.cu writes).
 // ---- c[b,o] = demod^2 * sum_{i,t} m*G   (one warp per (b,o))
 __global__ void __launch_bounds__(kThreads)
 demod_corr_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
@@ -147,12 +148,13 @@ demod_corr_kernel(const float *__restrict__ gw, const float *__restrict__ w, con
   const int lane = threadIdx.x & 31;
   if (warp >= batch * cout) return;
   const long long b = warp / cout, o = warp % cout;
-  const float *wr = w + o * cin * taps;
-  const float *gr = gw + warp * cin * taps;
   float acc = 0.f;
-  for (long long e = lane; e < cin * taps; e += 32) {
-    const float m = wscale * wr[e] * __ldg(s + b * cin + e / taps);
-    acc = fmaf(m, gr[e], acc);
+  for (int t = 0; t < taps; ++t) {
+    const float *gr = gw + ((b * taps + t) * cout + o) * cin;
+    for (long long i = lane; i < cin; i += 32) {
+      const float m = wscale * w[(o * cin + i) * taps + t] * __ldg(s + b * cin + i);
+      acc = fmaf(m, gr[i], acc);
+    }
   }
   acc = warp_sum(acc);
   if (lane == 0) {
@@ -161,7 +163,7 @@ demod_corr_kernel(const float *__restrict__ gw, const float *__restrict__ w, con
   }
 }
 
-// ---- dW[o,i,t] = wscale * sum_b s[b,i] * (G - corr[b,o]*m)     (thread per element)
+// ---- dW[o,i,t] = wscale * sum_b s[b,i] * (G - corr[b,o]*m)     (thread per (t,o,i), G order)
 __global__ void __launch_bounds__(kThreads)
 dweight_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
                const float *__restrict__ corr, float *__restrict__ dw, long long batch, long long cout,
@@ -169,8 +171,10 @@ dweight_kernel(const float *__restrict__ gw, const float *__restrict__ w, const 
   const long long e = blockIdx.x * (long long)kThreads + threadIdx.x;
   const long long per = cout * cin * taps;
   if (e >= per) return;
-  const long long o = e / (cin * taps), i = (e / taps) % cin;
-  const float wv = w[e];
+  const long long i = e % cin, o = (e / cin) % cout;
+  const int t = (int)(e / (cin * cout));
+  const long long we = (o * cin + i) * taps + t;
+  const float wv = w[we];
   float acc = 0.f;
   for (long long b = 0; b < batch; ++b) {
     const float sv = s ? __ldg(s + b * cin + i) : 1.f;
@@ -178,7 +182,7 @@ dweight_kernel(const float *__restrict__ gw, const float *__restrict__ w, const 
     if (corr) dm -= __ldg(corr + b * cout + o) * (wscale * wv * sv);
     acc = fmaf(sv, dm, acc);
   }
-  dw[e] = wscale * acc;
+  dw[we] = wscale * acc;
 }
 
 // ---- ds[b,i] = wscale * sum_{o,t} W[o,i,t] * (G - corr[b,o]*m); grid (i tiles, o chunks, b)
@@ -196,10 +200,10 @@ dstyle_kernel(const float *__restrict__ gw, const float *__restrict__ w, const f
   for (long long o = o_lo; o < o_hi; ++o) {
     const float c = corr ? __ldg(corr + b * cout + o) : 0.f;
     const float *wr = w + (o * cin + i) * taps;
-    const float *gr = gw + ((b * cout + o) * cin + i) * taps;
     for (int t = 0; t < taps; ++t) {
       const float wv = wr[t];
-      acc = fmaf(wv, gr[t] - c * (wscale * wv * sv), acc);
+      const float g = gw[((b * taps + t) * cout + o) * cin + i];
+      acc = fmaf(wv, g - c * (wscale * wv * sv), acc);
     }
   }
   atomicAdd(ds + b * cin + i, wscale * acc);

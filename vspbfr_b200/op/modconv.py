@@ -185,20 +185,21 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
     return out
 
 
-def conv_wgrad(dy_nchw_bf16, x_nchw_bf16, groups, kh, kw, stride, pad, dil):
-    """gw[g,o,i,t] = sum_p dy[b,o,p] x[b,i,p*stride + t*dil - pad]; groups == batch or 1."""
-    b, cout, oh, ow = dy_nchw_bf16.shape
-    _, cin, h, w = x_nchw_bf16.shape
-    gw = torch.empty((groups, cout, cin, kh * kw), dtype=torch.float32, device=dy_nchw_bf16.device)
-    with torch.cuda.device(dy_nchw_bf16.device):
-        rc = _lib.load().vsp_conv2d_wgrad_bf16(ptr(dy_nchw_bf16), ptr(x_nchw_bf16), ptr(gw), b, groups, h, w, cin, cout,
+def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
+    """gw[g,t,o,i] = sum_p dy[b,p,o] x[b, p*stride + t*dil - pad, i] (tap-major); groups == batch or 1.
+    dy_nhwc [B,OH,OW,Cout_pad] bf16, x_nhwc [B,H,W,Cin_pad] bf16 -> [groups, kh*kw, Cout_pad, Cin_pad] fp32."""
+    b, oh, ow, cout = dy_nhwc.shape
+    _, h, w, cin = x_nhwc.shape
+    gw = torch.empty((groups, kh * kw, cout, cin), dtype=torch.float32, device=dy_nhwc.device)
+    with torch.cuda.device(dy_nhwc.device):
+        rc = _lib.load().vsp_conv2d_wgrad_bf16(ptr(dy_nhwc), ptr(x_nhwc), ptr(gw), b, groups, h, w, cin, cout,
                                                oh, ow, kh, kw, stride, pad, dil, stream_ptr())
     _lib.check(rc, "conv2d_wgrad_bf16")
     return gw
 
 
 def weight_style_grad(gw, weight, style, demod, wscale, want_dw=True, want_ds=True):
-    b, cout, cin, taps = gw.shape
+    b, taps, cout, cin = gw.shape
     dw = torch.empty((cout, cin, taps), dtype=torch.float32, device=gw.device) if want_dw else None
     ds = torch.empty((b, cin), dtype=torch.float32, device=gw.device) if want_ds else None
     with torch.cuda.device(gw.device):
@@ -261,3 +262,127 @@ def plain_conv_dgrad(*a, **k):  # pragma: no cover - routed to ATen by plain_con
 def plain_conv_wgrad(grad_output, input, weight_shape, stride, padding, dilation, groups):
     """Returns None when the wgrad kernel does not cover the shape (caller uses ATen)."""
     return None
+
+
+# ----------------------------------------------------------------------------------------------
+# the modulated convolution (NCHW fp32 boundary, fused tcgen05 path)
+# ----------------------------------------------------------------------------------------------
+
+def _modconv_reference_form(x, weight, s, demodulate, mode, dilation, eps=1e-8):
+    """The reference's own formulation (models/RestoreNet.py:510-553: materialised per-sample
+    weights + grouped conv through conv2d_gradfix).  Differentiable to any order; used for the
+    double-backward path (create_graph=True) of ModulatedConv2dFunction."""
+    from . import conv2d_gradfix
+
+    b, cin, h, w_ = x.shape
+    _, cout, _, k, _ = weight.shape
+    wscale = 1.0 / math.sqrt(cin * k * k)
+    wm = wscale * weight * s.reshape(b, 1, cin, 1, 1)
+    if demodulate:
+        d = torch.rsqrt(wm.pow(2).sum([2, 3, 4]) + eps)
+        wm = wm * d.reshape(b, cout, 1, 1, 1)
+    xin = x.reshape(1, b * cin, h, w_)
+    if mode == "up":
+        wt = wm.transpose(1, 2).reshape(b * cin, cout, k, k)
+        out = conv2d_gradfix.conv_transpose2d(xin, wt, padding=0, stride=2, groups=b, dilation=dilation)
+    elif mode == "down":
+        out = conv2d_gradfix.conv2d(xin, wm.reshape(b * cout, cin, k, k), padding=0, stride=2, groups=b,
+                                    dilation=dilation)
+    else:
+        out = conv2d_gradfix.conv2d(xin, wm.reshape(b * cout, cin, k, k), padding=((k - 1) * dilation) // 2,
+                                    groups=b, dilation=dilation)
+    return out.reshape(b, cout, out.shape[2], out.shape[3])
+
+
+class ModulatedConv2dFunction(Function):
+    """y[b] = demod[b] * conv(x[b], wscale * W * s[b]) on tcgen05 (bf16 operands, fp32 accumulate).
+
+    mode: "same" (stride 1, padding (k-1)*dil/2), "down" (stride 2, padding 0 — the caller blurs
+    first), "up" (transposed stride 2, padding 0 — the caller blurs afterwards).
+    First-order backward runs on the same kernels (dgrad = gather conv with transposed weights,
+    wgrad = pixel-K GEMM, style/weight gradients incl. the demodulation term); when autograd asks
+    for a differentiable backward (create_graph=True) it switches to the reference formulation
+    through conv2d_gradfix, which is closed under differentiation.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, s, demodulate, mode, dilation):
+        b, cin, h, w_ = x.shape
+        _, cout, cin_w, k, _ = weight.shape
+        if cin_w != cin or s.shape != (b, cin):
+            raise RuntimeError(f"modulated_conv2d: shape mismatch x{tuple(x.shape)} w{tuple(weight.shape)} s{tuple(s.shape)}")
+        if x.device.type != "cuda":
+            raise RuntimeError("modulated_conv2d: input must be a CUDA tensor (vspbfr_b200 has no CPU path)")
+        wscale = 1.0 / math.sqrt(cin * k * k)
+        w4 = weight.reshape(cout, cin, k, k)
+        xq = nchw_to_nhwc_bf16(x)
+        wq, d = pack_weights(w4, s, wscale=wscale, want_demod=demodulate)
+        epi = make_epilogue(row_scale=d) if demodulate else None
+        if mode == "up":
+            if dilation != 1:
+                raise RuntimeError("modulated_conv2d: dilated transposed convolution is not supported")
+            out = conv_transpose_s2(xq, wq, cout, k, k, epi=epi)
+        elif mode == "down":
+            out = conv_fprop(xq, wq, cout, k, k, 2, 0, dilation, epi=epi)
+        else:
+            out = conv_fprop(xq, wq, cout, k, k, 1, ((k - 1) * dilation) // 2, dilation, epi=epi)
+        ctx.save_for_backward(x, weight, s, d if demodulate else None)
+        ctx.cfg = (demodulate, mode, dilation, wscale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, s, d = ctx.saved_tensors
+        demodulate, mode, dilation, wscale = ctx.cfg
+        if torch.is_grad_enabled():
+            # differentiable backward requested (double backward): closed-set formulation
+            with torch.enable_grad():
+                y = _modconv_reference_form(x, weight, s, demodulate, mode, dilation)
+                need = [t for t, n in zip((x, weight, s), ctx.needs_input_grad[:3]) if n]
+                grads = list(torch.autograd.grad(y, need, dy, create_graph=True, allow_unused=True))
+            out = []
+            for n in ctx.needs_input_grad[:3]:
+                out.append(grads.pop(0) if n else None)
+            return (*out, None, None, None)
+
+        b, cin, h, w_ = x.shape
+        _, cout, _, k, _ = weight.shape
+        w4 = weight.reshape(cout, cin, k, k)
+        pad = ((k - 1) * dilation) // 2
+        dzq = nchw_to_nhwc_bf16(dy, scale_nc=d)           # dz = demod * dy, channels-last bf16
+        taps = [(i, j) for i in range(k) for j in range(k)]
+        dx = dw = ds = None
+        if ctx.needs_input_grad[0]:
+            wq_t, _ = pack_weights(w4, s, wscale=wscale, transpose=True)
+            if mode == "same":
+                dx = conv_gather(dzq, wq_t, cin, [i * k + j for i, j in taps], [pad - i * dilation for i, j in taps],
+                                 [pad - j * dilation for i, j in taps], 1, (h, w_))
+            elif mode == "down":
+                dx = conv_transpose_s2(dzq, wq_t, cin, k, k)
+                if dx.shape[2] != h or dx.shape[3] != w_:   # even-sized inputs lose their last row/col to stride 2
+                    full = torch.zeros_like(x)
+                    full[:, :, :dx.shape[2], :dx.shape[3]] = dx[:, :, :h, :w_]
+                    dx = full
+            else:
+                dx = conv_fprop(dzq, wq_t, cin, k, k, 2, 0, 1)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            xq = nchw_to_nhwc_bf16(x)
+            if mode == "up":
+                # y[2p+t] += x[p] w[t]  =>  G[t,o,i] = sum_p x[p,i] dz[2p+t,o]: roles swapped, then transposed
+                gw = conv_wgrad(xq, dzq, b, k, k, 2, 0, 1).transpose(2, 3).contiguous()
+            elif mode == "down":
+                gw = conv_wgrad(dzq, xq, b, k, k, 2, 0, dilation)
+            else:
+                gw = conv_wgrad(dzq, xq, b, k, k, 1, pad, dilation)
+            gw = gw[:, :, :cout, :cin]
+            if gw.shape[2] != cout or not gw.is_contiguous():
+                gw = gw.contiguous()
+            dw, ds = weight_style_grad(gw, w4, s, d, wscale, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+            if dw is not None:
+                dw = dw.reshape(weight.shape)
+        return dx, dw, ds, None, None, None
+
+
+def modulated_conv2d(x, weight, s, demodulate=True, mode="same", dilation=1):
+    """x [B,Cin,H,W] fp32, weight [1,Cout,Cin,k,k], s [B,Cin] (already through ``modulation``)."""
+    return ModulatedConv2dFunction.apply(x, weight, s, demodulate, mode, dilation)
