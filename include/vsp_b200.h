@@ -140,8 +140,11 @@ int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void
 /* ---- tcgen05 implicit-GEMM convolution --------------------------------- */
 
 /* Epilogue description shared by the conv entry points. All pointers optional.
- * Order of application: acc * row_scale[b,n] + noise_weight * noise[b,pixel] + bias[n]
- * -> activation * scale -> + residual + residual2. */
+ * Order of application:
+ *   v = acc * row_scale[b,n]
+ *   if pre_act: v = act(v + pre_bias[n]) * scale        (SMART_layer fusion conv + its FusedLeakyReLU)
+ *   v = act(v + noise_weight * noise[b,pixel] + bias[n]) * scale   (NoiseInjection + FusedLeakyReLU; act==0: linear)
+ *   v += residual + residual2 */
 typedef struct vsp_conv_epilogue {
   const float *row_scale; /* [batch, cout]  demodulation coefficient d[b,o]            */
   const float *noise;     /* [batch or 1, full_h, full_w] noise image (NoiseInjection) */
@@ -149,6 +152,8 @@ typedef struct vsp_conv_epilogue {
   float noise_weight;     /* NoiseInjection.weight (host scalar) ...                   */
   const float *noise_weight_dev; /* ... or, if non-NULL, a device scalar read by the kernel (no host sync) */
   const float *bias;      /* [cout] FusedLeakyReLU / ToRGB bias                        */
+  const float *pre_bias;  /* [cout] bias of the first (pre-noise) activation stage     */
+  int pre_act;            /* 0 = no first stage, 3 = leaky relu                        */
   int act;                /* 0 = none, 3 = leaky relu (as fused_bias_act)              */
   float alpha;            /* negative slope                                            */
   float scale;            /* output gain (sqrt 2)                                      */

@@ -341,3 +341,20 @@ def test_modulated_conv_double_backward_runs_and_matches_fp32():
     for g, wv in zip(got, want):
         peak = float(wv.abs().max())
         assert float((g - wv).abs().max()) <= 3e-2 * peak
+
+
+def test_two_stage_epilogue_smart_fusion():
+    """conv -> +b1 -> lrelu*sqrt2 -> +noise -> +b2 -> lrelu*sqrt2 (SMART_layer.forward, models/RestoreNet.py:234-238)."""
+    torch.manual_seed(13)
+    b, c, h = 2, 64, 16
+    x = torch.randn(b, c, h, h, device=DEV)
+    w = torch.randn(c, c, 3, 3, device=DEV) / 24
+    b1, b2 = torch.randn(c, device=DEV), torch.randn(c, device=DEV)
+    noise = torch.randn(b, 1, h, h, device=DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(w)
+    epi = mc.make_epilogue(pre_bias=b1, pre_act=3, noise=noise, noise_weight=0.5, bias=b2, act=3, alpha=0.2, scale=math.sqrt(2))
+    out = mc.conv_fprop(xq, wq, c, 3, 3, 1, 1, 1, epi=epi)
+    y = F.leaky_relu(F.conv2d(bf16r(x), bf16r(w), None, 1, 1) + b1[None, :, None, None], 0.2) * math.sqrt(2)
+    y = F.leaky_relu(y + 0.5 * noise + b2[None, :, None, None], 0.2) * math.sqrt(2)
+    assert_close_tight(out, y)

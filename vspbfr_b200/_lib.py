@@ -105,6 +105,8 @@ class ConvEpilogue(Structure):
         ("noise_weight", c_float),
         ("noise_weight_dev", c_void_p),
         ("bias", c_void_p),
+        ("pre_bias", c_void_p),
+        ("pre_act", c_int),
         ("act", c_int),
         ("alpha", c_float),
         ("scale", c_float),

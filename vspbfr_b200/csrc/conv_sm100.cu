@@ -53,6 +53,8 @@ struct ConvParams {
   float noise_weight;
   const float *noise_weight_dev;
   const float *bias;
+  const float *pre_bias;
+  int pre_act;
   int act;
   float alpha, scale;
   const void *residual;
@@ -66,7 +68,7 @@ struct ConvCfg {
   static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6 * BLOCK_N * 4 /*epilogue vectors*/;
 };
 
 __device__ __forceinline__ float epi_act(float v, int act, float alpha, float scale) {
@@ -87,6 +89,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   uint64_t *tmem_full = empty_bar + C::STAGES;
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *epi_vec = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES + 256);  // 6 * BLOCK_N floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -174,8 +177,17 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // Per-channel vectors (demod, biases) are staged in shared memory once per tile by the 128
+    // epilogue threads (coalesced, issued BEFORE waiting for the accumulator so the latency
+    // hides behind the MMAs) and then read back as 128-bit broadcasts; accumulators leave TMEM
+    // 32 columns at a time.
     const int quad = warp & 3;              // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;       // pixel row inside the tile
+    const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+    float *vec_rs = epi_vec;                // [2][BLOCK_N] demod
+    float *vec_b1 = epi_vec + 2 * BLOCK_N;  // [2][BLOCK_N] pre-activation bias (stage 1)
+    float *vec_b2 = epi_vec + 4 * BLOCK_N;  // [2][BLOCK_N] bias (stage 2)
+    const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -190,62 +202,99 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
       const int fh = oh * p.os + p.oo_h, fw = ow * p.os + p.oo_w;
       const long long pix = (long long)fh * p.full_w + fw;          // within one [full_h, full_w] plane
       const long long plane = (long long)p.full_h * p.full_w;
+      const int nbase = n_i * BLOCK_N;
+
+      // stage the channel vectors of this tile
+      for (int c = et; c < BLOCK_N; c += 128) {
+        const int n = nbase + c;
+        const bool ok = n < p.cout;
+        vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.cout + n) : 1.f;
+        vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + n) : 0.f;
+        vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+      }
       float nz = 0.f;
-      if (p.noise != nullptr && pix_ok)
-        nz = (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) * __ldg(p.noise + b * p.noise_bstride + pix);
+      if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch) {
+        const int n0 = nbase + ch * C::CHUNK;
+        const bool live = pix_ok && n0 < p.cout;
+        const bool fullc = n0 + C::CHUNK <= p.cout;
+        // residual prefetch (independent of the accumulator)
+        float rsd[C::CHUNK];
+#pragma unroll
+        for (int j = 0; j < C::CHUNK; ++j) rsd[j] = 0.f;
+        if (live && (p.residual || p.residual2)) {
+          if (!p.out_nhwc) {
+            const long long off = ((long long)b * p.cout + n0) * plane + pix;
+            const float *r1 = static_cast<const float *>(p.residual);
+            const float *r2 = static_cast<const float *>(p.residual2);
+#pragma unroll
+            for (int j = 0; j < C::CHUNK; ++j)
+              if (fullc || n0 + j < p.cout) {
+                if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
+                if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
+              }
+          } else {
+            const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+            const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
+                                          static_cast<const __nv_bfloat16 *>(p.residual2)};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (!rr[q]) continue;
+              if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+                for (int j = 0; j < C::CHUNK; j += 8) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4 *>(rr[q] + off + j));
+                  const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    rsd[j + 2 * e] += f.x;
+                    rsd[j + 2 * e + 1] += f.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < C::CHUNK; ++j)
+                  if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
+              }
+            }
+          }
+        }
         uint32_t r[C::CHUNK];
         if constexpr (C::CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * 32, r);
         else tmem_ld_32x32b_x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(r));
         tmem_ld_wait();
-        const int n0 = n_i * BLOCK_N + ch * C::CHUNK;
-        if (pix_ok && n0 < p.cout) {
+        if (live) {
+          float v[C::CHUNK];
+          const float4 *srs = reinterpret_cast<const float4 *>(vec_rs + acc * BLOCK_N + ch * C::CHUNK);
+          const float4 *sb1 = reinterpret_cast<const float4 *>(vec_b1 + acc * BLOCK_N + ch * C::CHUNK);
+          const float4 *sb2 = reinterpret_cast<const float4 *>(vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
+#pragma unroll
+          for (int j = 0; j < C::CHUNK; j += 4) {
+            const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
+            const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __uint_as_float(r[j + e]) * aa[e];
+              if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
+              x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
+              v[j + e] = x + rsd[j + e];
+            }
+          }
           if (!p.out_nhwc) {
             float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
-            const float *res = static_cast<const float *>(p.residual);
-            const float *res2 = static_cast<const float *>(p.residual2);
 #pragma unroll
-            for (int j = 0; j < C::CHUNK; ++j) {
-              const int n = n0 + j;
-              if (n < p.cout) {
-                float v = __uint_as_float(r[j]);
-                if (p.row_scale) v *= __ldg(p.row_scale + (long long)b * p.cout + n);
-                v += nz;
-                if (p.bias) v += __ldg(p.bias + n);
-                v = epi_act(v, p.act, p.alpha, p.scale);
-                const long long off = ((long long)b * p.cout + n) * plane + pix;
-                if (res) v += __ldg(res + off);
-                if (res2) v += __ldg(res2 + off);
-                o[(long long)j * plane] = v;
-              }
-            }
+            for (int j = 0; j < C::CHUNK; ++j)
+              if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
           } else {
-            const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + off;
-            const __nv_bfloat16 *res = static_cast<const __nv_bfloat16 *>(p.residual);
-            const __nv_bfloat16 *res2 = static_cast<const __nv_bfloat16 *>(p.residual2);
-            float v[C::CHUNK];
-#pragma unroll
-            for (int j = 0; j < C::CHUNK; ++j) {
-              const int n = n0 + j;
-              float a = __uint_as_float(r[j]);
-              if (n < p.cout) {
-                if (p.row_scale) a *= __ldg(p.row_scale + (long long)b * p.cout + n);
-                a += nz;
-                if (p.bias) a += __ldg(p.bias + n);
-                a = epi_act(a, p.act, p.alpha, p.scale);
-                if (res) a += __bfloat162float(res[off + j]);
-                if (res2) a += __bfloat162float(res2[off + j]);
-              }
-              v[j] = a;
-            }
-            const bool vec_ok = (n0 + C::CHUNK <= p.cout) && (((p.ldo | p.co_off) & 7) == 0);
-            if (vec_ok) {
+            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+            if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
 #pragma unroll
               for (int j = 0; j < C::CHUNK; j += 8) {
                 __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
@@ -357,7 +406,8 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     p.row_scale = epi->row_scale; p.noise_weight = epi->noise_weight; p.bias = epi->bias;
     p.act = epi->act; p.alpha = epi->alpha; p.scale = epi->scale; p.residual = epi->residual;
     p.noise = epi->noise; p.noise_bstride = epi->noise_bstride; p.residual2 = epi->residual2;
-    p.noise_weight_dev = epi->noise_weight_dev;
+    p.noise_weight_dev = epi->noise_weight_dev; p.pre_bias = epi->pre_bias; p.pre_act = epi->pre_act;
+    VSP_REQUIRE(p.pre_act == 0 || p.pre_act == 3, "conv: epilogue pre_act must be 0 or 3");
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
   }
 

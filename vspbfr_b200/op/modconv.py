@@ -89,7 +89,7 @@ def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want
 
 
 def make_epilogue(row_scale=None, noise=None, noise_weight=0.0, noise_weight_dev=None, bias=None, act=0, alpha=0.2,
-                  scale=1.0, residual=None, residual2=None):
+                  scale=1.0, residual=None, residual2=None, pre_bias=None, pre_act=0):
     """Build a ``vsp_conv_epilogue``; returns (struct, keepalive tuple)."""
     e = ConvEpilogue()
     e.row_scale = row_scale.data_ptr() if row_scale is not None else None
@@ -100,9 +100,11 @@ def make_epilogue(row_scale=None, noise=None, noise_weight=0.0, noise_weight_dev
     e.noise_weight_dev = noise_weight_dev.data_ptr() if noise_weight_dev is not None else None
     e.bias = bias.data_ptr() if bias is not None else None
     e.act, e.alpha, e.scale = int(act), float(alpha), float(scale)
+    e.pre_bias = pre_bias.data_ptr() if pre_bias is not None else None
+    e.pre_act = int(pre_act)
     e.residual = residual.data_ptr() if residual is not None else None
     e.residual2 = residual2.data_ptr() if residual2 is not None else None
-    return e, (row_scale, noise, noise_weight_dev, bias, residual, residual2)
+    return e, (row_scale, noise, noise_weight_dev, bias, residual, residual2, pre_bias)
 
 
 def _int_array(vals):
