@@ -69,12 +69,17 @@ int64_t vsp_upfirdn2d_out_size(int64_t in, int k, int up, int down, int pad0, in
 /*
  * Channels-last bf16 variant used inside fused layer chains:
  *   x [n, in_h, in_w, c] bf16 -> y [n, out_h, out_w, c] bf16 (c % 8 == 0).
- * Same arithmetic (fp32 accumulate), same parameter meaning.
+ * Same arithmetic (fp32 accumulate), same parameter meaning.  Optional epilogue `epi`
+ * (struct declared below; noise/bias/act/residual fields only): the StyledConv(upsample)
+ * tail "blur -> NoiseInjection -> FusedLeakyReLU -> + feat + sty_de_feat"
+ * (models/RestoreNet.py:599-603, :1031-1035) in the same pass.
  */
+struct vsp_conv_epilogue;
 int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y,
                             int64_t n, int64_t in_h, int64_t in_w, int64_t c,
                             int kh, int kw, int up_x, int up_y, int down_x, int down_y,
-                            int pad_x0, int pad_x1, int pad_y0, int pad_y1, void *stream);
+                            int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                            const struct vsp_conv_epilogue *epi, void *stream);
 
 /* ---- bias + activation ------------------------------------------------- */
 

@@ -127,7 +127,7 @@ SIGNATURES = {
     "vsp_upfirdn2d_out_size": (c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
     "vsp_upfirdn2d_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                         c_int, c_int, c_int, c_int, c_int, c_int,
-                                        c_int, c_int, c_int, c_int, c_void_p]),
+                                        c_int, c_int, c_int, c_int, POINTER(ConvEpilogue), c_void_p]),
     "vsp_bias_act_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                  c_int, c_int, c_float, c_float, c_void_p]),
     "vsp_bias_act_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,

@@ -345,7 +345,8 @@ int launch_conv(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t co
   }
   CUtensorMap tb;
   {
-    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)cout_pad, (uint64_t)taps_total, (uint64_t)p.groups};
+    // visible rows = cout (a channel slice of a wider packed tensor is legal); strides use cout_pad
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
     uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
                            (uint64_t)p.cin * cout_pad * taps_total * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)BLOCK_N, 1, 1};

@@ -280,10 +280,35 @@ upfirdn2d_generic_kernel(const UfdParams p, long long total) {
 }
 
 // Channels-last bf16 variant: one thread per (output pixel, 8-channel group), 128-bit
-// loads/stores along the contiguous channel axis, fp32 accumulation.
+// loads/stores along the contiguous channel axis, fp32 accumulation, optional epilogue
+// (noise + bias + leaky ReLU, then up to two residual adds — StyledConv(upsample) tail and
+// the decoder skip fusion of models/RestoreNet.py:1031-1035).
+struct NhwcEpi {
+  const float *noise;
+  long long noise_bstride;
+  float noise_weight;
+  const float *noise_weight_dev;
+  const float *bias;
+  int act;
+  float alpha, scale;
+  const uint4 *residual;
+  const uint4 *residual2;
+};
+
+__device__ __forceinline__ void add_bf16x8(float (&acc)[8], const uint4 &v) {
+  const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 upfirdn2d_nhwc_kernel(const uint4 *__restrict__ x, const float *__restrict__ filt, uint4 *__restrict__ y,
-                      const UfdParams p, int cg, long long total) {
+                      const UfdParams p, const NhwcEpi e, int cg, long long total) {
+  const float nw = e.noise ? (e.noise_weight_dev ? __ldg(e.noise_weight_dev) : e.noise_weight) : 0.f;
   for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * kThreads) {
     const int g = (int)(idx % cg);
@@ -317,6 +342,18 @@ upfirdn2d_nhwc_kernel(const uint4 *__restrict__ x, const float *__restrict__ fil
         }
       }
     }
+    if (e.noise != nullptr || e.bias != nullptr || e.act != 0) {
+      const float nz = e.noise ? nw * __ldg(e.noise + b * e.noise_bstride + (long long)oy * p.out_w + ox) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = acc[i] + nz;
+        if (e.bias) v += __ldg(e.bias + g * 8 + i);
+        if (e.act == 3) v = (v > 0.f ? v : v * e.alpha) * e.scale;
+        acc[i] = v;
+      }
+    }
+    if (e.residual) add_bf16x8(acc, __ldg(e.residual + idx));
+    if (e.residual2) add_bf16x8(acc, __ldg(e.residual2 + idx));
     uint4 o;
     __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
 #pragma unroll
@@ -441,7 +478,7 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
 extern "C" int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y, int64_t n, int64_t in_h,
                                        int64_t in_w, int64_t c, int kh, int kw, int up_x, int up_y,
                                        int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
-                                       int pad_y1, void *stream_) {
+                                       int pad_y1, const vsp_conv_epilogue *epi, void *stream_) {
   using namespace vsp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VSP_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d_nhwc: factors must be >= 1");
@@ -464,7 +501,18 @@ extern "C" int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y
   long long blocks = (total + kThreads - 1) / kThreads;
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
+  NhwcEpi e;
+  memset(&e, 0, sizeof(e));
+  if (epi) {
+    VSP_REQUIRE(epi->act == 0 || epi->act == 3, "upfirdn2d_nhwc: epilogue act must be 0 or 3");
+    VSP_REQUIRE(epi->row_scale == nullptr && epi->pre_act == 0, "upfirdn2d_nhwc: row_scale / pre_act are conv-only");
+    e.noise = epi->noise; e.noise_bstride = epi->noise_bstride; e.noise_weight = epi->noise_weight;
+    e.noise_weight_dev = epi->noise_weight_dev; e.bias = epi->bias; e.act = epi->act; e.alpha = epi->alpha;
+    e.scale = epi->scale;
+    e.residual = static_cast<const uint4 *>(epi->residual);
+    e.residual2 = static_cast<const uint4 *>(epi->residual2);
+  }
   upfirdn2d_nhwc_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(
-      static_cast<const uint4 *>(x), filt, static_cast<uint4 *>(y), p, cg, total);
+      static_cast<const uint4 *>(x), filt, static_cast<uint4 *>(y), p, e, cg, total);
   return check_launch("upfirdn2d_nhwc_kernel");
 }

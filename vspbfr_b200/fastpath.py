@@ -1,0 +1,271 @@
+"""Fused channels-last bf16 inference pipeline over the layer modules of ``layers.py``.
+
+Same arithmetic as the reference forwards (models/RestoreNet.py:968-1046,
+e4e/models/stylegan2/model.py:475-552) with the memory traffic removed
+(SURVEY.md §8 f-1): activations stay NHWC bf16 between layers; per-sample style modulation is a
+weight prologue; demodulation, NoiseInjection, bias + leaky-ReLU, the SMART double activation, the
+``out + feat + sty_de_feat`` skip fusion and the ToRGB bias + skip add run in conv / blur epilogues;
+the four dilated SMART branches write channel slices of one buffer (no ``torch.cat``).  The RGB skip
+chain stays fp32 NCHW (3 channels: negligible traffic, keeps the image path at full precision).
+
+No autograd here — use the module ``forward`` methods for training.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import ptr, stream_ptr
+from .layers import LargeConvLayer, SMART_layer, StyledConv, ToRGB
+from .op import modconv as mc
+from .op.upfirdn2d import upfirdn2d_raw
+
+_cache: dict = {}
+
+
+def _cached(owner, tag, tensors, build):
+    """Memoise a derived tensor per module, invalidated when any source tensor is modified in place
+    or re-assigned (weights are static during inference, so this runs once)."""
+    key = (id(owner), tag)
+    ver = tuple((t.data_ptr(), t._version) for t in tensors)
+    hit = _cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = build()
+    _cache[key] = (ver, val)
+    return val
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def _linear(lin, x):
+    """EqualLinear without activation (the per-layer ``modulation``), fp32."""
+    w = _cached(lin, "w_scaled", [lin.weight], lambda: (lin.weight.detach() * lin.scale).contiguous())
+    b = _cached(lin, "b_scaled", [lin.bias], lambda: (lin.bias.detach() * lin.lr_mul).contiguous())
+    return F.linear(x, w, b)
+
+
+def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
+    """NHWC bf16 up-FIR-down with an optional fused epilogue."""
+    n, h, w, c = x.shape
+    kh, kw = kernel.shape
+    lib = _lib.load()
+    oh = lib.vsp_upfirdn2d_out_size(h, kh, up, down, pad[0], pad[1])
+    ow = lib.vsp_upfirdn2d_out_size(w, kw, up, down, pad[0], pad[1])
+    y = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=x.device)
+    e, keep = epi if epi is not None else (None, None)
+    with torch.cuda.device(x.device):
+        rc = lib.vsp_upfirdn2d_nhwc_bf16(ptr(x), ptr(kernel), ptr(y), n, h, w, c, kh, kw, up, up, down, down,
+                                         pad[0], pad[1], pad[0], pad[1],
+                                         ctypes.byref(e) if e is not None else None, stream_ptr())
+    _lib.check(rc, "upfirdn2d_nhwc_bf16")
+    return y
+
+
+def _noise_for(noise, b, h, w, device):
+    """``NoiseInjection`` draws N(0,1) per call when no noise is given (models/RestoreNet.py:564-569)."""
+    if noise is None:
+        return torch.randn(b, 1, h, w, device=device, dtype=torch.float32)
+    return noise.contiguous().float()
+
+
+def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=None):
+    """StyledConv / StyledConv_down: modulated conv -> noise -> bias + lrelu (-> + residuals)."""
+    conv = m.conv
+    b, h, w, _ = x.shape
+    cout, cin, k = conv.out_channel, conv.in_channel, conv.kernel_size
+    s = _linear(conv.modulation, style)
+    wq, d = mc.pack_weights(conv.weight.detach().view(cout, cin, k, k), s, wscale=conv.scale, eps=conv.eps,
+                            want_demod=conv.demodulate)
+    act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
+               noise_weight_dev=m.noise.weight.detach())
+    if conv.upsample:
+        y = mc.conv_transpose_s2(x, wq, cout, k, k, epi=mc.make_epilogue(row_scale=d) if d is not None else None,
+                                 out_nhwc=True)
+        nz = _noise_for(noise, b, 2 * h, 2 * w, x.device)
+        return upfirdn_nhwc(y, conv.blur.kernel, pad=conv.blur.pad,
+                            epi=mc.make_epilogue(noise=nz, residual=residual, residual2=residual2, **act))
+    if conv.downsample:
+        xb = upfirdn_nhwc(x, conv.blur.kernel, pad=conv.blur.pad)
+        nz = _noise_for(noise, b, (xb.shape[1] - k) // 2 + 1, (xb.shape[2] - k) // 2 + 1, x.device)
+        return mc.conv_fprop(xb, wq, cout, k, k, 2, 0, 1, out_nhwc=True,
+                             epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual, residual2=residual2, **act))
+    nz = _noise_for(noise, b, h, w, x.device)
+    return mc.conv_fprop(x, wq, cout, k, k, 1, conv.padding, 1, out_nhwc=True,
+                         epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual, residual2=residual2, **act))
+
+
+def _plain_weights(conv):
+    """Packed bf16 weights of an EqualConv2d (equalised-lr scale folded in), cached."""
+    return _cached(conv, "wq", [conv.weight], lambda: mc.pack_weights(conv.weight.detach(), wscale=conv.scale)[0])
+
+
+def smart_layer(m: SMART_layer, x, style, noise=None):
+    """SMART_layer: 4 dilated modulated branches -> channel slices -> 3x3 fusion conv with the
+    double activation + noise in its epilogue (models/RestoreNet.py:225-244)."""
+    b, h, w, cin = x.shape
+    branches = list(m.ModulatedConv2ds)
+    cq = branches[0].out_channel
+    cout = cq * len(branches)
+    k = branches[0].kernel_size
+    s = _linear(m.modulation, style)
+    wcat = _cached(m, "wcat", [br.weight for br in branches],
+                   lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
+    wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate)
+    buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    for j, br in enumerate(branches):
+        dj = d[:, j * cq:(j + 1) * cq].contiguous() if d is not None else None
+        mc.conv_fprop(x, wq[:, :, j * cq:(j + 1) * cq, :], cq, k, k, 1, br.padding, br.dilation, out=buf, out_nhwc=True,
+                      co_off=j * cq, epi=mc.make_epilogue(row_scale=dj) if dj is not None else None)
+    fconv, fact = m.fusion[0], m.fusion[1]
+    nz = _noise_for(noise, b, h, w, x.device)
+    kw = dict(pre_bias=fact.bias.detach(), pre_act=3, noise=nz, noise_weight_dev=m.noise.weight.detach(),
+              alpha=fact.negative_slope, scale=fact.scale)
+    if m.activate is not None:
+        kw.update(bias=m.activate.bias.detach(), act=3)
+    return mc.conv_fprop(buf, _plain_weights(fconv), cout, 3, 3, 1, fconv.padding, 1, out_nhwc=True,
+                         epi=mc.make_epilogue(**kw))
+
+
+def large_conv_layer(m: LargeConvLayer, x):
+    """LargeConvLayer (un-modulated): dilated convs -> slices -> 1x1 fusion + two activations."""
+    assert not m.downsample, "downsampling LargeConvLayer is not used by the networks"
+    b, h, w, cin = x.shape
+    convs = list(m.dilated_convs)
+    cq = convs[0].weight.shape[0]
+    cout = cq * len(convs)
+    k = convs[0].weight.shape[2]
+    if k == 1:
+        # dilation is meaningless for 1x1: the four branches are ONE conv with concatenated weights
+        wq = _cached(m, "wq1x1", [c.weight for c in convs], lambda: _pack_padded(
+            torch.cat([c.weight.detach() for c in convs], 0), convs[0].scale, cin))
+        buf = mc.conv_fprop(x, wq, cout, 1, 1, 1, 0, 1, out_nhwc=True)
+    else:
+        buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+        for j, c in enumerate(convs):
+            mc.conv_fprop(x, _plain_weights(c), cq, k, k, 1, c.padding, c.dilation, out=buf, out_nhwc=True, co_off=j * cq)
+    fconv, fact = m.fusion[0], m.fusion[1]
+    kw = dict(pre_bias=fact.bias.detach(), pre_act=3, alpha=fact.negative_slope, scale=fact.scale)
+    if m.activate is not None:
+        kw.update(bias=m.activate.bias.detach() if m.activate.bias is not None else None, act=3)
+    return mc.conv_fprop(buf, _plain_weights(fconv), cout, 1, 1, 1, 0, 1, out_nhwc=True, epi=mc.make_epilogue(**kw))
+
+
+def _pack_padded(weight, wscale, cin_pad):
+    """Pack [Cout,Cin,kh,kw] to bf16 with the input-channel axis padded to the activation's width."""
+    cout, cin, kh, kw = weight.shape
+    wq, _ = mc.pack_weights(weight, wscale=wscale)
+    if wq.shape[3] == cin_pad:
+        return wq
+    out = torch.zeros((1, kh * kw, cout, cin_pad), dtype=torch.bfloat16, device=weight.device)
+    out[..., :wq.shape[3]] = wq
+    return out
+
+
+def to_rgb(m: ToRGB, x, style, skip=None):
+    """ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip; fp32 NCHW in/out for RGB."""
+    conv = m.conv
+    s = _linear(conv.modulation, style)
+    wq, _ = mc.pack_weights(conv.weight.detach().view(3, conv.in_channel, 1, 1), s, wscale=conv.scale)
+    res = None
+    if skip is not None:
+        f = m.upsample.factor
+        res = upfirdn2d_raw(skip, m.upsample.kernel, (f, f), (1, 1), (m.upsample.pad[0], m.upsample.pad[1]) * 2)
+    bias = _cached(m, "bias3", [m.bias], lambda: m.bias.detach().reshape(3).contiguous())
+    return mc.conv_fprop(x, wq, 3, 1, 1, 1, 0, 1, epi=mc.make_epilogue(bias=bias, residual=res))
+
+
+def _as_nhwc(t):
+    """Accept the decoder features either as NHWC bf16 (fast path) or NCHW fp32 (reference layout)."""
+    if t.dtype == torch.bfloat16:
+        return t
+    return mc.nchw_to_nhwc_bf16(t)
+
+
+@torch.no_grad()
+def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_index=None, truncation=1,
+                        truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
+    """``Restoration_net.forward`` (models/RestoreNet.py:968-1046) as a fused pipeline.
+    images [B,3,S,S] fp32 -> restored [B,3,S,S] fp32."""
+    b = images.shape[0]
+    latent = net.prepare_latent(pre_styles, noise_styles, inject_index, truncation, truncation_latent, input_is_latent)
+    if noise is None:
+        noise = ([None] * net.num_layers if randomize_noise
+                 else [getattr(net.noises, f"noise_{i}") for i in range(net.num_layers)])
+    lat_rev = torch.flip(latent, dims=[1])
+    noise_rev = noise[::-1]
+
+    out = large_conv_layer(net.down_from_big, mc.nchw_to_nhwc_bf16(images, c_pad=8))
+    features = []
+    enc = net.encoder_convs
+    for ii in range(0, len(enc), 2):
+        out = smart_layer(enc[ii], out, lat_rev[:, ii], noise_rev[ii])
+        features.append(out)
+        out = styled_conv(enc[ii + 1], out, lat_rev[:, ii], noise_rev[ii + 1])
+    out = large_conv_layer(net.final_layer, out)                           # [B,4,4,C]
+    flat = out.permute(0, 3, 1, 2).reshape(b, -1).float()                  # reference flattens NCHW
+    x_global = net.final_linear[0](flat)                                   # Dropout2d is the identity in eval
+    early = net.final_transfer(x_global).view(b, -1, 4, 4).permute(0, 2, 3, 1)
+    features.append((out.float() + early).to(torch.bfloat16).contiguous())
+    features = features[::-1]
+
+    def sty(i):
+        return torch.cat([latent[:, i], x_global], dim=1)
+
+    out = smart_layer(net.conv1, features[0], sty(0), noise[0])
+    skip = to_rgb(net.to_rgb1, out, sty(1))
+    i = 1
+    for up, smart, n_up, n_smart, rgb in zip(net.convs[::2], net.convs[1::2], noise[1::2], noise[2::2], net.to_rgbs):
+        level = (i + 1) // 2
+        out = styled_conv(up, out, sty(i), n_up, residual=features[level], residual2=_as_nhwc(de_feats[level]))
+        out = smart_layer(smart, out, sty(i + 1), n_smart)
+        skip = to_rgb(rgb, out, sty(i + 2), skip)
+        i += 2
+    return skip
+
+
+@torch.no_grad()
+def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_latent=None, input_is_latent=False,
+                      noise=None, randomize_noise=True, return_features=True, features_nchw=False):
+    """Style decoder ``Generator.forward`` (e4e/models/stylegan2/model.py:475-552) fused.
+    Returns (image fp32 NCHW, features) — features NHWC bf16, or NCHW fp32 when ``features_nchw``."""
+    latent = gen.prepare_latent(styles, inject_index, truncation, truncation_latent, input_is_latent)
+    b = latent.shape[0]
+    if noise is None:
+        noise = ([None] * gen.num_layers if randomize_noise
+                 else [getattr(gen.noises, f"noise_{i}") for i in range(gen.num_layers)])
+    const = _cached(gen.input, "nhwc", [gen.input.input], lambda: mc.nchw_to_nhwc_bf16(gen.input.input.detach()))
+    out = styled_conv(gen.conv1, const.expand(b, -1, -1, -1).contiguous(), latent[:, 0], noise[0])
+    skip = to_rgb(gen.to_rgb1, out, latent[:, 1])
+    feats = [out] if return_features else []
+    i = 1
+    for up, conv, n_up, n_conv, rgb in zip(gen.convs[::2], gen.convs[1::2], noise[1::2], noise[2::2], gen.to_rgbs):
+        out = styled_conv(up, out, latent[:, i], n_up)
+        if return_features:
+            feats.append(out)
+        out = styled_conv(conv, out, latent[:, i + 1], n_conv)
+        skip = to_rgb(rgb, out, latent[:, i + 2], skip)
+        i += 2
+    if return_features and features_nchw:
+        feats = [mc.nhwc_bf16_to_nchw(f) for f in feats]
+    return skip, (feats if return_features else None)
+
+
+@torch.no_grad()
+def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent=16):
+    """The hot path of one restoration batch (restoration_test.py:130-131): style decoder features from
+    the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512)."""
+    if noise_styles is None:
+        noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
+    image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True)
+    feats = feats[:out_n_latent]
+    restored = restoration_forward(net, low_imgs, feats, codes, noise_styles)
+    size = low_imgs.shape[-1]
+    if image.shape[-1] != size:
+        image = F.adaptive_avg_pool2d(image, (size, size))      # face_pool, e4e/models/psp.py:245-246
+    return restored, image

@@ -115,11 +115,22 @@ def conv_out_size(n, k, stride, pad, dil):
     return (n + 2 * pad - dil * (k - 1) - 1) // stride + 1
 
 
+def _rows_per_tap(wq):
+    """Row pitch of a packed weight tensor [G,taps,n,k] — also valid for a channel-slice VIEW of it."""
+    assert wq.stride(3) == 1 and wq.stride(2) == wq.shape[3], "packed weights must be dense in (n, k)"
+    if wq.shape[1] > 1:
+        return wq.stride(1) // wq.stride(2)
+    if wq.shape[0] > 1:
+        return wq.stride(0) // wq.stride(2)
+    return wq.shape[2]
+
+
 def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=None, out_nhwc=False, co_off=0):
     """out = conv(x_nhwc, wq) (+ epilogue).  x_nhwc [B,H,W,Cin_pad] bf16, wq [G,taps,cout_pad,Cin_pad] bf16."""
     b, h, w, cin = x_nhwc.shape
-    g, taps, cout_pad, k_pad = wq.shape
+    g, taps, _, k_pad = wq.shape
     assert taps == kh * kw and k_pad == cin, (wq.shape, x_nhwc.shape, kh, kw)
+    cout_pad = _rows_per_tap(wq)
     oh, ow = conv_out_size(h, kh, stride, pad, dil), conv_out_size(w, kw, stride, pad, dil)
     if out is None:
         if out_nhwc:
@@ -142,8 +153,9 @@ def conv_gather(x_nhwc, wq, cout, tap_w, tap_dy, tap_dx, stride, out_hw, full_hw
                 out=None, out_nhwc=False, co_off=0):
     """General tap-list convolution (input gradients, parity classes); see vsp_conv2d_gather_bf16."""
     b, h, w, cin = x_nhwc.shape
-    g, taps_total, cout_pad, k_pad = wq.shape
+    g, taps_total, _, k_pad = wq.shape
     assert k_pad == cin
+    cout_pad = _rows_per_tap(wq)
     oh, ow = out_hw
     fh, fw = full_hw or out_hw
     if out is None:
@@ -166,8 +178,9 @@ def conv_gather(x_nhwc, wq, cout, tap_w, tap_dy, tap_dx, stride, out_hw, full_hw
 def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
     """Stride-2, padding-0 transposed convolution -> extent ((H-1)*2+kh, (W-1)*2+kw)."""
     b, h, w, cin = x_nhwc.shape
-    g, taps, cout_pad, k_pad = wq.shape
+    g, taps, _, k_pad = wq.shape
     assert taps == kh * kw and k_pad == cin
+    cout_pad = _rows_per_tap(wq)
     fh, fw = (h - 1) * 2 + kh, (w - 1) * 2 + kw
     if out_nhwc:
         out = torch.empty((b, fh, fw, _round_up(cout, 8)), dtype=torch.bfloat16, device=x_nhwc.device)
