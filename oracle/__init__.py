@@ -20,3 +20,6 @@ __all__ = [
     "bias_act_ref", "fused_leaky_relu_ref", "fused_leaky_relu_grads_ref",
     "modulated_conv2d_ref", "conv2d_ref",
 ]
+from .network_ref import generator_ref, restoration_ref, restore_faces_ref  # noqa: E402
+
+__all__ += ["generator_ref", "restoration_ref", "restore_faces_ref"]

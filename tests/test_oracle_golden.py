@@ -104,3 +104,22 @@ def test_modconv_oracle_matches_reference(name):
     np.testing.assert_allclose(gx.numpy(), MOD[f"{name}.gx"], rtol=1e-4, atol=2e-5)
     np.testing.assert_allclose(gs.numpy(), MOD[f"{name}.gstyle"], rtol=1e-3, atol=1e-4)
     np.testing.assert_allclose(gw.numpy(), MOD[f"{name}.gw"], rtol=1e-3, atol=1e-4)
+
+
+def test_network_oracle_matches_reference():
+    """Functional CPU oracle of decoder + Restoration_net vs the real reference's outputs (size 16)."""
+    from vspbfr_b200.restorenet import Restoration_net
+    from vspbfr_b200.stylegan2 import Generator
+
+    net_g = load_golden("networks")
+    size = int(net_g["size"])
+    torch.manual_seed(2024)
+    net = Restoration_net(size, 512, 2, channel_multiplier=2)
+    dec = Generator(size, 512, 2, channel_multiplier=2)
+    low, codes, z = (torch.from_numpy(net_g[k]) for k in ("low", "codes", "z"))
+    img, feats = oracle.generator_ref(dec.state_dict(), codes, size)
+    np.testing.assert_allclose(img.numpy(), net_g["decoder_image"], rtol=1e-3, atol=2e-4)
+    for i, f in enumerate(feats):
+        np.testing.assert_allclose(f.numpy(), net_g[f"decoder_feat{i}"], rtol=1e-3, atol=2e-4)
+    restored = oracle.restoration_ref(net.state_dict(), low, feats, codes, z, size, 2)
+    np.testing.assert_allclose(restored.numpy(), net_g["restored"], rtol=1e-3, atol=5e-4)

@@ -23,6 +23,45 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+class KernelProfiler:
+    """Optional per-launch accounting used by bench.py for the roofline numbers: CUDA events around
+    every tcgen05 conv launch on the launching stream plus the launch's ALGORITHMIC flops
+    (2 * pixels * Cout * Cin * taps).  Off (None) by default: no overhead on the product path."""
+
+    def __init__(self):
+        self.records = []
+
+    def wrap(self, name, flops, fn):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn()
+        e.record()
+        self.records.append((name, float(flops), s, e))
+        return out
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, flops, s, e in self.records:
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += flops
+            a[2] += s.elapsed_time(e) * 1e-3
+        return {k: {"launches": v[0], "flops": v[1], "seconds": v[2]} for k, v in agg.items()}
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
+
+
+def _prof(name, flops, fn):
+    return fn() if _profiler is None else _profiler.wrap(name, flops, fn)
+
+
 # ----------------------------------------------------------------------------------------------
 # thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------
@@ -142,9 +181,9 @@ def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=N
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
     with torch.cuda.device(x_nhwc.device):
-        rc = _lib.load().vsp_conv2d_fprop_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw,
-                                               stride, pad, dil, int(out_nhwc), ldo, co_off,
-                                               ctypes.byref(e) if e is not None else None, stream_ptr())
+        rc = _prof("conv_fprop", 2.0 * b * oh * ow * cout * cin * kh * kw, lambda: _lib.load().vsp_conv2d_fprop_bf16(
+            ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, stride, pad, dil, int(out_nhwc),
+            ldo, co_off, ctypes.byref(e) if e is not None else None, stream_ptr()))
     _lib.check(rc, "conv2d_fprop_bf16")
     return out
 
@@ -193,9 +232,10 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
     with torch.cuda.device(x_nhwc.device):
-        rc = _lib.load().vsp_conv_transpose2d_s2_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad,
-                                                      kh, kw, int(out_nhwc), ldo, 0,
-                                                      ctypes.byref(e) if e is not None else None, stream_ptr())
+        rc = _prof("conv_transpose_s2", 2.0 * b * h * w * cout * cin * kh * kw,
+                   lambda: _lib.load().vsp_conv_transpose2d_s2_bf16(
+                       ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, int(out_nhwc), ldo, 0,
+                       ctypes.byref(e) if e is not None else None, stream_ptr()))
     _lib.check(rc, "conv_transpose2d_s2_bf16")
     return out
 
