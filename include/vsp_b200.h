@@ -136,11 +136,16 @@ int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y,
  *                    tap offsets of vsp_conv2d_gather_bf16, the tap index t' = t is kept)
  * `s` may be NULL (plain EqualConv2d: s == 1, batch == 1 group shared by all
  * samples).  n is padded to n_pad rows and k to k_pad columns with zeros.
+ * `wsq` (optional, [cout, cin] from vsp_weight_sumsq_f32) turns the demodulation sum into
+ * sum_i s^2 * wsq — the host caches it while the weights are static (inference).
  */
 int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void *wq,
                               int64_t batch, int64_t cout, int64_t cin, int taps,
                               float wscale, float eps, int transpose, int fold_demod,
-                              int64_t n_pad, int64_t k_pad, void *stream);
+                              int64_t n_pad, int64_t k_pad, const float *wsq, void *stream);
+
+/* wsq[o,i] = sum_t w[o,i,t]^2 (style-independent part of the demodulation sum). */
+int vsp_weight_sumsq_f32(const float *w, float *wsq, int64_t cout, int64_t cin, int taps, void *stream);
 
 /* ---- tcgen05 implicit-GEMM convolution --------------------------------- */
 

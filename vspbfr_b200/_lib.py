@@ -137,7 +137,8 @@ SIGNATURES = {
     "vsp_nchw_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vsp_modulate_weights_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int,
-                                          c_float, c_float, c_int, c_int, c_int64, c_int64, c_void_p]),
+                                          c_float, c_float, c_int, c_int, c_int64, c_int64, c_void_p, c_void_p]),
+    "vsp_weight_sumsq_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "vsp_conv2d_fprop_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int,

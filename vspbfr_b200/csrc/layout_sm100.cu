@@ -114,6 +114,36 @@ demod_kernel(const float *__restrict__ w, const float *__restrict__ s, float *__
   if (lane == 0) demod[warp] = rsqrtf(acc + eps);
 }
 
+// ---- wsq[o,i] = sum_t W[o,i,t]^2 (style independent: cached by the host while weights are static)
+__global__ void __launch_bounds__(kThreads)
+weight_sumsq_kernel(const float *__restrict__ w, float *__restrict__ wsq, long long n, int taps) {
+  const long long e = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (e >= n) return;
+  float acc = 0.f;
+  for (int t = 0; t < taps; ++t) {
+    const float v = w[e * taps + t];
+    acc = fmaf(v, v, acc);
+  }
+  wsq[e] = acc;
+}
+
+// ---- demod[b,o] = rsqrt(wscale^2 * sum_i s[b,i]^2 * wsq[o,i] + eps): one warp per (b,o)
+__global__ void __launch_bounds__(kThreads)
+demod_from_wsq_kernel(const float *__restrict__ wsq, const float *__restrict__ s, float *__restrict__ demod,
+                      long long batch, long long cout, long long cin, float wscale, float eps) {
+  const long long warp = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * cout) return;
+  const long long b = warp / cout, o = warp % cout;
+  float acc = 0.f;
+  for (long long i = lane; i < cin; i += 32) {
+    const float sv = s ? __ldg(s + b * cin + i) : 1.f;
+    acc = fmaf(sv * sv, __ldg(wsq + o * cin + i), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) demod[warp] = rsqrtf(wscale * wscale * acc + eps);
+}
+
 // ---- pack modulated weights to bf16 [b][tap'][n_pad][k_pad]; one thread per (n', k')
 __global__ void __launch_bounds__(kThreads)
 pack_weights_kernel(const float *__restrict__ w, const float *__restrict__ s,
@@ -262,7 +292,7 @@ extern "C" int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void 
 extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void *wq,
                                          int64_t batch, int64_t cout, int64_t cin, int taps,
                                          float wscale, float eps, int transpose, int fold_demod,
-                                         int64_t n_pad, int64_t k_pad, void *stream_) {
+                                         int64_t n_pad, int64_t k_pad, const float *wsq, void *stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VSP_REQUIRE(batch >= 1 && cout >= 1 && cin >= 1 && taps >= 1, "modulate_weights: bad geometry");
   VSP_REQUIRE(w != nullptr, "modulate_weights: null weight");
@@ -270,9 +300,15 @@ extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *
   VSP_REQUIRE(batch <= 65535, "modulate_weights: batch too large");
   if (demod) {
     const long long warps = batch * cout;
-    demod_kernel<<<(unsigned)ceil_div64(warps * 32, kThreads), kThreads, 0, stream>>>(w, s, demod, batch, cout, cin,
-                                                                                      taps, wscale, eps);
-    if (int rc = check_launch("demod_kernel")) return rc;
+    if (wsq) {
+      demod_from_wsq_kernel<<<(unsigned)ceil_div64(warps * 32, kThreads), kThreads, 0, stream>>>(wsq, s, demod, batch,
+                                                                                                 cout, cin, wscale, eps);
+      if (int rc = check_launch("demod_from_wsq_kernel")) return rc;
+    } else {
+      demod_kernel<<<(unsigned)ceil_div64(warps * 32, kThreads), kThreads, 0, stream>>>(w, s, demod, batch, cout, cin,
+                                                                                        taps, wscale, eps);
+      if (int rc = check_launch("demod_kernel")) return rc;
+    }
   }
   if (wq) {
     const int64_t n_real = transpose ? cin : cout, k_real = transpose ? cout : cin;
@@ -284,6 +320,13 @@ extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *
     if (int rc = check_launch("pack_weights_kernel")) return rc;
   }
   return 0;
+}
+
+extern "C" int vsp_weight_sumsq_f32(const float *w, float *wsq, int64_t cout, int64_t cin, int taps, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(w && wsq && cout >= 1 && cin >= 1 && taps >= 1, "weight_sumsq: bad arguments");
+  weight_sumsq_kernel<<<(unsigned)ceil_div64(cout * cin, kThreads), kThreads, 0, stream>>>(w, wsq, cout * cin, taps);
+  return check_launch("weight_sumsq_kernel");
 }
 
 extern "C" int vsp_modconv_weight_style_grad(const float *gw, const float *w, const float *s,

@@ -80,8 +80,9 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     b, h, w, _ = x.shape
     cout, cin, k = conv.out_channel, conv.in_channel, conv.kernel_size
     s = _linear(conv.modulation, style)
-    wq, d = mc.pack_weights(conv.weight.detach().view(cout, cin, k, k), s, wscale=conv.scale, eps=conv.eps,
-                            want_demod=conv.demodulate)
+    w4 = conv.weight.detach().view(cout, cin, k, k)
+    wsq = _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(w4)) if conv.demodulate else None
+    wq, d = mc.pack_weights(w4, s, wscale=conv.scale, eps=conv.eps, want_demod=conv.demodulate, wsq=wsq)
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
                noise_weight_dev=m.noise.weight.detach())
     if conv.upsample:
@@ -116,7 +117,9 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     s = _linear(m.modulation, style)
     wcat = _cached(m, "wcat", [br.weight for br in branches],
                    lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
-    wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate)
+    wsq = _cached(m, "wsq", [br.weight for br in branches], lambda: mc.weight_sumsq(wcat)) if branches[0].demodulate else None
+    wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate,
+                            wsq=wsq)
     buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
     for j, br in enumerate(branches):
         dj = d[:, j * cq:(j + 1) * cq].contiguous() if d is not None else None

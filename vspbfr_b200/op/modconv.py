@@ -103,8 +103,19 @@ def nchw_to_bf16(x, scale_nc=None):
     return y
 
 
+def weight_sumsq(weight):
+    """wsq[o,i] = sum over taps of W^2 — the style-independent half of the demodulation sum."""
+    cout, cin, kh, kw = weight.shape
+    weight = weight.contiguous()
+    wsq = torch.empty((cout, cin), dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        rc = _lib.load().vsp_weight_sumsq_f32(ptr(weight), ptr(wsq), cout, cin, kh * kw, stream_ptr())
+    _lib.check(rc, "weight_sumsq_f32")
+    return wsq
+
+
 def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want_demod=False, fold_demod=False,
-                 batch=None):
+                 batch=None, wsq=None):
     """weight [Cout,Cin,kh,kw] fp32 (+ style [B,Cin]) -> (wq bf16 [G,taps,n_pad,k_pad], demod [G,Cout] | None).
 
     G = B when a style is given (per-sample modulated weights), else 1.
@@ -122,7 +133,7 @@ def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want
     with torch.cuda.device(weight.device):
         rc = _lib.load().vsp_modulate_weights_bf16(ptr(weight), ptr(style), ptr(demod), ptr(wq), g, cout, cin, taps,
                                                    wscale, eps, int(transpose), int(fold_demod), n_pad, k_pad,
-                                                   stream_ptr())
+                                                   ptr(wsq), stream_ptr())
     _lib.check(rc, "modulate_weights_bf16")
     return wq, demod
 
