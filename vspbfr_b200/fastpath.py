@@ -183,6 +183,18 @@ def to_rgb(m: ToRGB, x, style, skip=None):
     return mc.conv_fprop(x, wq, 3, 1, 1, 1, 0, 1, epi=mc.make_epilogue(bias=bias, residual=res))
 
 
+def _mapped_latent(mapping, n_latent, styles, inject_index, truncation, truncation_latent, input_is_latent):
+    """Style MLP + truncation + broadcast/mixing to [B, n_latent, D] (models/RestoreNet.py:982-1011);
+    written against attributes the reference's own modules also have, so it accepts either."""
+    from .restorenet import assemble_latent
+
+    if not input_is_latent:
+        styles = [mapping(s) for s in styles]
+    if truncation < 1:
+        styles = [truncation_latent + truncation * (s - truncation_latent) for s in styles]
+    return assemble_latent(styles, n_latent, inject_index)
+
+
 def _as_nhwc(t):
     """Accept the decoder features either as NHWC bf16 (fast path) or NCHW fp32 (reference layout)."""
     if t.dtype == torch.bfloat16:
@@ -196,7 +208,9 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     """``Restoration_net.forward`` (models/RestoreNet.py:968-1046) as a fused pipeline.
     images [B,3,S,S] fp32 -> restored [B,3,S,S] fp32."""
     b = images.shape[0]
-    latent = net.prepare_latent(pre_styles, noise_styles, inject_index, truncation, truncation_latent, input_is_latent)
+    noise_latent = _mapped_latent(net.style, net.n_latent, noise_styles, inject_index, truncation, truncation_latent,
+                                  input_is_latent)
+    latent = torch.cat([pre_styles[:, :noise_latent.shape[1], :], noise_latent], dim=-1)
     if noise is None:
         noise = ([None] * net.num_layers if randomize_noise
                  else [getattr(net.noises, f"noise_{i}") for i in range(net.num_layers)])
@@ -237,7 +251,8 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
                       noise=None, randomize_noise=True, return_features=True, features_nchw=False):
     """Style decoder ``Generator.forward`` (e4e/models/stylegan2/model.py:475-552) fused.
     Returns (image fp32 NCHW, features) — features NHWC bf16, or NCHW fp32 when ``features_nchw``."""
-    latent = gen.prepare_latent(styles, inject_index, truncation, truncation_latent, input_is_latent)
+    latent = _mapped_latent(gen.style, gen.n_latent, styles, inject_index, truncation, truncation_latent,
+                            input_is_latent)
     b = latent.shape[0]
     if noise is None:
         noise = ([None] * gen.num_layers if randomize_noise
