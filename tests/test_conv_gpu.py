@@ -358,3 +358,39 @@ def test_two_stage_epilogue_smart_fusion():
     y = F.leaky_relu(F.conv2d(bf16r(x), bf16r(w), None, 1, 1) + b1[None, :, None, None], 0.2) * math.sqrt(2)
     y = F.leaky_relu(y + 0.5 * noise + b2[None, :, None, None], 0.2) * math.sqrt(2)
     assert_close_tight(out, y)
+
+
+HALO_CASES = [
+    # b, cin, cout, h, w, dil   (stride-1 3x3 'same' convs on wide images -> row-halo kernel)
+    (1, 64, 64, 8, 128, 1),
+    (2, 64, 16, 6, 128, 2),
+    (1, 64, 16, 20, 256, 4),
+    (1, 64, 16, 20, 128, 8),
+    (2, 32, 32, 5, 256, 1),
+    (1, 128, 128, 6, 128, 1),
+    (1, 128, 32, 10, 256, 2),
+    (1, 256, 256, 4, 128, 1),
+    (1, 256, 64, 12, 128, 8),
+    (1, 64, 64, 5, 200, 1),
+    (1, 64, 48, 3, 130, 4),
+    (3, 64, 64, 3, 128, 1),
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,dil", HALO_CASES)
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_rowhalo_conv(b, cin, cout, h, w, dil, per_sample):
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + w + dil)
+    x = torch.randn(b, cin, h, w, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    if per_sample:
+        s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
+        wq, _ = mc.pack_weights(wt, s)
+        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wt * s[i][None, :, None, None]), None, 1, dil, dil)
+                          for i in range(b)])
+    else:
+        wq, _ = mc.pack_weights(wt)
+        want = F.conv2d(bf16r(x), bf16r(wt), None, 1, dil, dil)
+    out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, dil, dil)
+    assert_close_tight(out, want)

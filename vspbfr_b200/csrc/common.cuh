@@ -190,6 +190,9 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(1) << 16;                          // LBO (unused for swizzled K-major)
   d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;      // SBO [32,46)
   d |= static_cast<uint64_t>(1) << 46;                          // descriptor version (sm_100)
+  // base offset [49,52) stays 0 even for operands that start on a row that is not a multiple of 8
+  // (row-shifted halo views): measured on B200, the 128B swizzle XOR is taken from the ABSOLUTE smem
+  // address bits, exactly as TMA wrote it, so a start address shifted by k*128 B just works.
   d |= layout << 61;                                            // swizzle mode [61,64)
   return d;
 }

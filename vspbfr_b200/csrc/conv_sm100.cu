@@ -21,6 +21,8 @@
 // residual -> global).  Persistent: one CTA per SM walks the tile list.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace vsp {
 namespace {
 
@@ -41,6 +43,7 @@ struct ConvParams {
   int tw, th, tiles_w, tiles_h, tiles_n;
   long long total_tiles;
   int kc;                  // channel blocks per tap = ceil(cin / 64)
+  int halo_d, halo_w;      // row-halo kernel: dilation and padded halo row length (pixels)
   // output addressing: logical (oh, ow) -> (oh*os + oo_h, ow*os + oo_w) inside [full_h, full_w]
   void *out;
   int out_nhwc;
@@ -74,6 +77,158 @@ struct ConvCfg {
 __device__ __forceinline__ float epi_act(float v, int act, float alpha, float scale) {
   if (act == 3) v = (v > 0.f ? v : v * alpha) * scale;
   return v;
+}
+
+// Epilogue role (warps 2..5 of either kernel): TMEM -> registers -> fused epilogue -> global.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_vec, uint64_t *tmem_full,
+                                              uint64_t *tmem_empty, uint32_t tmem_base, int warp, int lane) {
+  using C = ConvCfg<BLOCK_N>;
+  // ===================== epilogue (warps 2..5) =====================
+  // Per-channel vectors (demod, biases) are staged in shared memory once per tile by the 128
+  // epilogue threads (coalesced, issued BEFORE waiting for the accumulator so the latency
+  // hides behind the MMAs) and then read back as 128-bit broadcasts; accumulators leave TMEM
+  // 32 columns at a time.
+  const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+  const int row = quad * 32 + lane;       // pixel row inside the tile
+  const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+  float *vec_rs = epi_vec;                // [2][BLOCK_N] demod
+  float *vec_b1 = epi_vec + 2 * BLOCK_N;  // [2][BLOCK_N] pre-activation bias (stage 1)
+  float *vec_b2 = epi_vec + 4 * BLOCK_N;  // [2][BLOCK_N] bias (stage 2)
+  const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    long long t = tile;
+    const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+    const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+    const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
+    const int b = (int)t;
+    const int oh = h_i * p.th + row / p.tw;
+    const int ow = w_i * p.tw + row % p.tw;
+    const bool pix_ok = oh < p.out_h && ow < p.out_w;
+    const int fh = oh * p.os + p.oo_h, fw = ow * p.os + p.oo_w;
+    const long long pix = (long long)fh * p.full_w + fw;          // within one [full_h, full_w] plane
+    const long long plane = (long long)p.full_h * p.full_w;
+    const int nbase = n_i * BLOCK_N;
+
+    // stage the channel vectors of this tile
+    for (int c = et; c < BLOCK_N; c += 128) {
+      const int n = nbase + c;
+      const bool ok = n < p.cout;
+      vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.cout + n) : 1.f;
+      vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + n) : 0.f;
+      vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+    }
+    float nz = 0.f;
+    if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+    for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch) {
+      const int n0 = nbase + ch * C::CHUNK;
+      const bool live = pix_ok && n0 < p.cout;
+      const bool fullc = n0 + C::CHUNK <= p.cout;
+      // residual prefetch (independent of the accumulator)
+      float rsd[C::CHUNK];
+#pragma unroll
+      for (int j = 0; j < C::CHUNK; ++j) rsd[j] = 0.f;
+      if (live && (p.residual || p.residual2)) {
+        if (!p.out_nhwc) {
+          const long long off = ((long long)b * p.cout + n0) * plane + pix;
+          const float *r1 = static_cast<const float *>(p.residual);
+          const float *r2 = static_cast<const float *>(p.residual2);
+#pragma unroll
+          for (int j = 0; j < C::CHUNK; ++j)
+            if (fullc || n0 + j < p.cout) {
+              if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
+              if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
+            }
+        } else {
+          const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+          const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
+                                        static_cast<const __nv_bfloat16 *>(p.residual2)};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (!rr[q]) continue;
+            if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+              for (int j = 0; j < C::CHUNK; j += 8) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(rr[q] + off + j));
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h2[e]);
+                  rsd[j + 2 * e] += f.x;
+                  rsd[j + 2 * e + 1] += f.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < C::CHUNK; ++j)
+                if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
+            }
+          }
+        }
+      }
+      uint32_t r[C::CHUNK];
+      if constexpr (C::CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * 32, r);
+      else tmem_ld_32x32b_x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(r));
+      tmem_ld_wait();
+      if (live) {
+        float v[C::CHUNK];
+        const float4 *srs = reinterpret_cast<const float4 *>(vec_rs + acc * BLOCK_N + ch * C::CHUNK);
+        const float4 *sb1 = reinterpret_cast<const float4 *>(vec_b1 + acc * BLOCK_N + ch * C::CHUNK);
+        const float4 *sb2 = reinterpret_cast<const float4 *>(vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
+#pragma unroll
+        for (int j = 0; j < C::CHUNK; j += 4) {
+          const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
+          const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(r[j + e]) * aa[e];
+            if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
+            x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
+            v[j + e] = x + rsd[j + e];
+          }
+        }
+        if (!p.out_nhwc) {
+          float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
+#pragma unroll
+          for (int j = 0; j < C::CHUNK; ++j)
+            if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
+        } else {
+          __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+          if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+            for (int j = 0; j < C::CHUNK; j += 8) {
+              __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 q1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 q2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 q3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t *>(&q0);
+              u.y = *reinterpret_cast<uint32_t *>(&q1);
+              u.z = *reinterpret_cast<uint32_t *>(&q2);
+              u.w = *reinterpret_cast<uint32_t *>(&q3);
+              *reinterpret_cast<uint4 *>(o + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < C::CHUNK; ++j)
+              if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
 }
 
 template <int BLOCK_N>
@@ -176,151 +331,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    // Per-channel vectors (demod, biases) are staged in shared memory once per tile by the 128
-    // epilogue threads (coalesced, issued BEFORE waiting for the accumulator so the latency
-    // hides behind the MMAs) and then read back as 128-bit broadcasts; accumulators leave TMEM
-    // 32 columns at a time.
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;       // pixel row inside the tile
-    const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
-    float *vec_rs = epi_vec;                // [2][BLOCK_N] demod
-    float *vec_b1 = epi_vec + 2 * BLOCK_N;  // [2][BLOCK_N] pre-activation bias (stage 1)
-    float *vec_b2 = epi_vec + 4 * BLOCK_N;  // [2][BLOCK_N] bias (stage 2)
-    const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      long long t = tile;
-      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
-      const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
-      const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
-      const int b = (int)t;
-      const int oh = h_i * p.th + row / p.tw;
-      const int ow = w_i * p.tw + row % p.tw;
-      const bool pix_ok = oh < p.out_h && ow < p.out_w;
-      const int fh = oh * p.os + p.oo_h, fw = ow * p.os + p.oo_w;
-      const long long pix = (long long)fh * p.full_w + fw;          // within one [full_h, full_w] plane
-      const long long plane = (long long)p.full_h * p.full_w;
-      const int nbase = n_i * BLOCK_N;
-
-      // stage the channel vectors of this tile
-      for (int c = et; c < BLOCK_N; c += 128) {
-        const int n = nbase + c;
-        const bool ok = n < p.cout;
-        vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.cout + n) : 1.f;
-        vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + n) : 0.f;
-        vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
-      }
-      float nz = 0.f;
-      if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch) {
-        const int n0 = nbase + ch * C::CHUNK;
-        const bool live = pix_ok && n0 < p.cout;
-        const bool fullc = n0 + C::CHUNK <= p.cout;
-        // residual prefetch (independent of the accumulator)
-        float rsd[C::CHUNK];
-#pragma unroll
-        for (int j = 0; j < C::CHUNK; ++j) rsd[j] = 0.f;
-        if (live && (p.residual || p.residual2)) {
-          if (!p.out_nhwc) {
-            const long long off = ((long long)b * p.cout + n0) * plane + pix;
-            const float *r1 = static_cast<const float *>(p.residual);
-            const float *r2 = static_cast<const float *>(p.residual2);
-#pragma unroll
-            for (int j = 0; j < C::CHUNK; ++j)
-              if (fullc || n0 + j < p.cout) {
-                if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
-                if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
-              }
-          } else {
-            const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-            const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
-                                          static_cast<const __nv_bfloat16 *>(p.residual2)};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              if (!rr[q]) continue;
-              if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
-#pragma unroll
-                for (int j = 0; j < C::CHUNK; j += 8) {
-                  const uint4 u = __ldg(reinterpret_cast<const uint4 *>(rr[q] + off + j));
-                  const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h2[e]);
-                    rsd[j + 2 * e] += f.x;
-                    rsd[j + 2 * e + 1] += f.y;
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < C::CHUNK; ++j)
-                  if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
-              }
-            }
-          }
-        }
-        uint32_t r[C::CHUNK];
-        if constexpr (C::CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * 32, r);
-        else tmem_ld_32x32b_x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(r));
-        tmem_ld_wait();
-        if (live) {
-          float v[C::CHUNK];
-          const float4 *srs = reinterpret_cast<const float4 *>(vec_rs + acc * BLOCK_N + ch * C::CHUNK);
-          const float4 *sb1 = reinterpret_cast<const float4 *>(vec_b1 + acc * BLOCK_N + ch * C::CHUNK);
-          const float4 *sb2 = reinterpret_cast<const float4 *>(vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
-#pragma unroll
-          for (int j = 0; j < C::CHUNK; j += 4) {
-            const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
-            const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x = __uint_as_float(r[j + e]) * aa[e];
-              if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
-              x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
-              v[j + e] = x + rsd[j + e];
-            }
-          }
-          if (!p.out_nhwc) {
-            float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
-#pragma unroll
-            for (int j = 0; j < C::CHUNK; ++j)
-              if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
-          } else {
-            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-            if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
-#pragma unroll
-              for (int j = 0; j < C::CHUNK; j += 8) {
-                __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 q1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 q2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 q3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t *>(&q0);
-                u.y = *reinterpret_cast<uint32_t *>(&q1);
-                u.z = *reinterpret_cast<uint32_t *>(&q2);
-                u.w = *reinterpret_cast<uint32_t *>(&q3);
-                *reinterpret_cast<uint4 *>(o + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < C::CHUNK; ++j)
-                if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -329,6 +340,228 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-halo variant for stride-1 3x3 (dilated) convolutions on wide images (out_w >= 128).
+// The plain implicit GEMM re-reads every input pixel once per tap (9x through L2), which makes the
+// C <= 128 layers at 128^2..1024^2 L2-bound.  Here a tile is 128 consecutive pixels of ONE output row
+// and the three input rows it needs (128 + 2*dil pixels each, x 64 channels) are TMA-loaded ONCE per
+// channel block; the nine taps are nine row-shifted UMMA descriptors into that halo (start address
+// + (kh*halo_w + kw*dil) * 128 B; the swizzle XOR is absolute-address based, base offset stays 0).
+// Weights: RESIDENT_B keeps all nine [N x 64] tap tiles in smem across the tiles of a sample (Cin <= 64);
+// otherwise they stream through their own mbarrier ring, decoupled from the halo ring.
+template <int BLOCK_N, bool RESIDENT_B>
+struct HaloCfg {
+  static constexpr int HALO_W_MAX = 144;                           // 128 + 2*8
+  static constexpr int A_STAGE_BYTES = 3 * HALO_W_MAX * 128;       // 55296, multiple of 1024
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_SLOTS = RESIDENT_B ? 9 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? 6 : 9));
+  static constexpr int B_TOTAL = B_SLOTS * B_BYTES;
+  static constexpr int DATA_BYTES = A_STAGES * A_STAGE_BYTES + B_TOTAL;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512 + 6 * BLOCK_N * 4;
+  static_assert(SMEM_BYTES <= 232448, "halo kernel exceeds shared memory");
+};
+
+template <int BLOCK_N, bool RESIDENT_B>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_rowhalo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b) {
+  using C = ConvCfg<BLOCK_N>;
+  using H = HaloCfg<BLOCK_N, RESIDENT_B>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char *a_buf = smem;
+  unsigned char *b_buf = smem + H::A_STAGES * H::A_STAGE_BYTES;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + H::DATA_BYTES);
+  uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 13;
+  uint64_t *tmem_full = bars + 22, *tmem_empty = bars + 24;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+  float *epi_vec = reinterpret_cast<float *>(smem + H::DATA_BYTES + 512);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    for (int i = 0; i < 9; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int d = p.halo_d, hw = p.halo_w;
+  const uint32_t a_row_bytes = (uint32_t)hw * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, res_ph = 0;
+      long long cur_key = -1;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        long long t = tile;
+        const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+        const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+        const int oh = (int)(t % p.tiles_h); t /= p.tiles_h;
+        const int b = (int)t;
+        const int g = p.groups == 1 ? 0 : b;
+        if (RESIDENT_B) {
+          const long long key = (long long)g * p.tiles_n + n_i;
+          if (key != cur_key) {
+            mbar_wait(&b_empty[0], res_ph ^ 1);          // every MMA that read the old weights has retired
+            mbar_arrive_expect_tx(&b_full[0], 9 * H::B_BYTES);
+            for (int tap = 0; tap < 9; ++tap)
+              tma_load_4d(b_buf + tap * H::B_BYTES, &tmap_b, &b_full[0], 0, n_i * BLOCK_N, p.tap_w[tap], g);
+            cur_key = key;
+            res_ph ^= 1;
+          }
+        }
+        for (int c = 0; c < p.kc; ++c) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          unsigned char *sa = a_buf + as * H::A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&a_full[as], 3 * a_row_bytes);
+          for (int kh = 0; kh < 3; ++kh)
+            tma_load_4d(sa + kh * a_row_bytes, &tmap_a, &a_full[as], c * kBlockK, w_i * kBlockM - d, oh + (kh - 1) * d, b);
+          if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
+          if (!RESIDENT_B) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], H::B_BYTES);
+              tma_load_4d(b_buf + bs * H::B_BYTES, &tmap_b, &b_full[bs], c * kBlockK, n_i * BLOCK_N, p.tap_w[tap], g);
+              if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0, res_ph = 0;
+      long long cur_key = -1;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        if (RESIDENT_B) {
+          const int n_i = (int)(tile % p.tiles_n);
+          const int b = (int)(tile / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
+          const long long key = (long long)(p.groups == 1 ? 0 : b) * p.tiles_n + n_i;
+          if (key != cur_key) {
+            mbar_wait(&b_full[0], res_ph);
+            res_ph ^= 1;
+            cur_key = key;
+          }
+        }
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int c = 0; c < p.kc; ++c) {
+          mbar_wait(&a_full[as], aph);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(a_buf + as * H::A_STAGE_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap - kh * 3;
+            uint32_t b_base;
+            if (RESIDENT_B) {
+              b_base = smem_u32(b_buf + tap * H::B_BYTES);
+            } else {
+              mbar_wait(&b_full[bs], bph);
+              tcgen05_fence_after();
+              b_base = smem_u32(b_buf + bs * H::B_BYTES);
+            }
+            const uint64_t adesc = umma_smem_desc(a_base + (uint32_t)kh * a_row_bytes + (uint32_t)(kw * d) * 128u, 128);
+            const uint64_t bdesc = umma_smem_desc(b_base, 128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                           (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if (!RESIDENT_B) {
+              umma_commit(&b_empty[bs]);
+              if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (RESIDENT_B) {
+          const long long nt = tile + gridDim.x;
+          bool release = nt >= p.total_tiles;
+          if (!release) {
+            const int n_i2 = (int)(nt % p.tiles_n);
+            const int b2 = (int)(nt / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
+            release = ((long long)(p.groups == 1 ? 0 : b2) * p.tiles_n + n_i2) != cur_key;
+          }
+          if (release) umma_commit(&b_empty[0]);   // weights may be overwritten once these MMAs retire
+        }
+      }
+    }
+  } else {
+    epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, bool RESIDENT_B>
+int launch_halo(ConvParams &p, const void *x, int64_t batch, int64_t in_h, int64_t in_w, const void *wq,
+                int64_t cout_pad, int taps_total, cudaStream_t stream) {
+  using H = HaloCfg<BLOCK_N, RESIDENT_B>;
+  auto kern = conv_rowhalo_kernel<BLOCK_N, RESIDENT_B>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, H::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)batch};
+    uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * in_w * 2, (uint64_t)p.cin * in_w * in_h * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.halo_w, 1, 1};
+    if (int rc = encode_tma(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
+    uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
+                           (uint64_t)p.cin * cout_pad * taps_total * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)BLOCK_N, 1, 1};
+    if (int rc = encode_tma(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, wq, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  p.tiles_n = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  p.total_tiles = (long long)p.batch * p.tiles_h * p.tiles_w * p.tiles_n;
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kern<<<(unsigned)grid, kNumThreads, H::SMEM_BYTES, stream>>>(p, ta, tb);
+  return check_launch("conv_rowhalo_kernel");
 }
 
 template <int BLOCK_N>
@@ -410,6 +643,32 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     p.noise_weight_dev = epi->noise_weight_dev; p.pre_bias = epi->pre_bias; p.pre_act = epi->pre_act;
     VSP_REQUIRE(p.pre_act == 0 || p.pre_act == 3, "conv: epilogue pre_act must be 0 or 3");
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
+  }
+
+  // Row-halo path: stride-1 3x3 (dilated) "same" convolution on a wide image, plain output mapping
+  {
+    static const bool no_halo = getenv("VSP_NO_HALO") != nullptr;
+    bool grid3 = !no_halo && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h;
+    int dd = grid3 ? tap_dx[8] : 0;   // tap (kh,kw) offset must be ((kh-1)*d, (kw-1)*d)
+    grid3 = grid3 && dd >= 1 && dd <= 8;
+    for (int t = 0; grid3 && t < 9; ++t)
+      grid3 = tap_dy[t] == (t / 3 - 1) * dd && tap_dx[t] == (t % 3 - 1) * dd;
+    if (grid3) {
+      p.tw = kBlockM; p.th = 1;
+      p.tiles_w = ((int)out_w + kBlockM - 1) / kBlockM;
+      p.tiles_h = (int)out_h;
+      p.halo_d = dd;
+      p.halo_w = (kBlockM + 2 * dd + 7) & ~7;
+      const bool resident = p.kc == 1;
+      if (cout > 128) return launch_halo<256, false>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream);
+      if (cout > 64) return launch_halo<128, false>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream);
+      if (cout > 32) return resident ? launch_halo<64, true>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream)
+                                     : launch_halo<64, false>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream);
+      if (cout > 16) return resident ? launch_halo<32, true>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream)
+                                     : launch_halo<32, false>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream);
+      return resident ? launch_halo<16, true>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream)
+                      : launch_halo<16, false>(p, x, batch, in_h, in_w, wq, cout_pad, taps_total, stream);
+    }
   }
 
   // A operand: NHWC bf16 activations as a 4-D tensor (c, w, h, b); the box is one tap-shifted
