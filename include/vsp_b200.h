@@ -226,6 +226,16 @@ int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void *out,
                                  const vsp_conv_epilogue *epi, void *stream);
 
 /*
+ * ToRGB (models/RestoreNet.py:647-666): 1x1 modulated convolution to 3 channels, no demodulation,
+ *   out[b,o,p] = sum_c x[b,p,c] * wscale * w[o,c] * s[b,c] + bias[o] + skip[b,o,p]
+ * x [batch, hw, c] bf16 NHWC (c % 8 == 0), w [3, c], s [batch, c] (NULL = 1), bias [3] / skip
+ * [batch, 3, hw] fp32 optional, out [batch, 3, hw] fp32 NCHW.  Memory-bound SIMT kernel.
+ */
+int vsp_torgb_nhwc_bf16(const void *x, const float *w, const float *s, const float *bias,
+                        const float *skip, float *out, int64_t batch, int64_t hw, int64_t c,
+                        float wscale, void *stream);
+
+/*
  * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):
  *   gw[g, t, o, i] = sum_{p in sample(s) of group g} dy[b,p,o] * x[b, p*stride + t*dil - pad, i]
  * Replaces aten::cudnn_convolution_backward_weight, op/conv2d_gradfix.py:177-199.

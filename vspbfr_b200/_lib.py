@@ -28,6 +28,7 @@ SOURCES = [
     "layout_sm100.cu",
     "conv_sm100.cu",
     "wgrad_sm100.cu",
+    "torgb_sm100.cu",
 ]
 
 NVCC_FLAGS = [
@@ -151,6 +152,8 @@ SIGNATURES = {
     "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_torgb_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),

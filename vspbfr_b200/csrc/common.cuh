@@ -49,6 +49,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (elect.sync). Producer / MMA roles run their loops on the WHOLE
+// warp (warp-uniform control flow keeps tile counters, coordinates and descriptors in uniform
+// registers) and only the issuing instructions sit under this predicate; issuing them from inside an
+// `if (lane == 0)` region instead makes ptxas wrap every UTMALDG / UTCHMMA in an ELECT + R2UR loop
+// (measured: ~100 cycles of issue overhead per MMA, which dominated every N <= 64 layer).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() {
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

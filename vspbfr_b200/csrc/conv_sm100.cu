@@ -246,7 +246,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
   float *epi_vec = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES + 256);  // 6 * BLOCK_N floats
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -355,9 +355,10 @@ template <int BLOCK_N, bool RESIDENT_B>
 struct HaloCfg {
   static constexpr int HALO_W_MAX = 144;                           // 128 + 2*8
   static constexpr int A_STAGE_BYTES = 3 * HALO_W_MAX * 128;       // 55296, multiple of 1024
-  static constexpr int A_STAGES = 2;
   static constexpr int B_BYTES = BLOCK_N * 128;
-  static constexpr int B_SLOTS = RESIDENT_B ? 9 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 128 ? 6 : 9));
+  static constexpr int B_SLOTS = RESIDENT_B ? 9 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 64 ? 6 : 9));
+  // three halo stages wherever shared memory allows (the loads are latency bound: bytes in flight matter)
+  static constexpr int A_STAGES = (3 * A_STAGE_BYTES + B_SLOTS * B_BYTES + 1024 + 512 + 6 * BLOCK_N * 4 <= 232448) ? 3 : 2;
   static constexpr int B_TOTAL = B_SLOTS * B_BYTES;
   static constexpr int DATA_BYTES = A_STAGES * A_STAGE_BYTES + B_TOTAL;
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512 + 6 * BLOCK_N * 4;
@@ -376,20 +377,22 @@ conv_rowhalo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   unsigned char *a_buf = smem;
   unsigned char *b_buf = smem + H::A_STAGES * H::A_STAGE_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + H::DATA_BYTES);
-  uint64_t *a_full = bars, *a_empty = bars + 2, *b_full = bars + 4, *b_empty = bars + 13;
-  uint64_t *tmem_full = bars + 22, *tmem_empty = bars + 24;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 26);
+  uint64_t *a_full = bars, *a_empty = bars + 3, *b_full = bars + 6, *b_empty = bars + 15;
+  uint64_t *tmem_full = bars + 24, *tmem_empty = bars + 26;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
   float *epi_vec = reinterpret_cast<float *>(smem + H::DATA_BYTES + 512);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
@@ -683,11 +686,28 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
                             CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
-  if (cout > 128) return launch_conv<256>(p, ta, wq, cout_pad, taps_total, stream);
-  if (cout > 64) return launch_conv<128>(p, ta, wq, cout_pad, taps_total, stream);
-  if (cout > 32) return launch_conv<64>(p, ta, wq, cout_pad, taps_total, stream);
-  if (cout > 16) return launch_conv<32>(p, ta, wq, cout_pad, taps_total, stream);
-  return launch_conv<16>(p, ta, wq, cout_pad, taps_total, stream);
+  // BLOCK_N: widest tile that still fills the machine. Cost model per k-block ~ (256 + 2*BLOCK_N) cycles
+  // (measured: the mainloop is bound by ~64 B/clk/SM of L2->smem traffic: 16 KB of A + 128*BLOCK_N B of B),
+  // times k-blocks, times waves over the SMs.
+  int best_bn = 16;
+  {
+    double best = 1e300;
+    const long long m_tiles = (long long)p.batch * p.tiles_h * p.tiles_w;
+    for (int bn = 256; bn >= 16; bn >>= 1) {
+      if (bn > 16 && bn >= 2 * cout) continue;               // more than half of the tile would be padding
+      const long long tiles = m_tiles * ((cout + bn - 1) / bn);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const double cost = (double)waves * ((double)p.ntaps * p.kc * (256.0 + 2.0 * bn) + 600.0 + 8.0 * bn);
+      if (cost < best) { best = cost; best_bn = bn; }
+    }
+  }
+  switch (best_bn) {
+    case 256: return launch_conv<256>(p, ta, wq, cout_pad, taps_total, stream);
+    case 128: return launch_conv<128>(p, ta, wq, cout_pad, taps_total, stream);
+    case 64: return launch_conv<64>(p, ta, wq, cout_pad, taps_total, stream);
+    case 32: return launch_conv<32>(p, ta, wq, cout_pad, taps_total, stream);
+    default: return launch_conv<16>(p, ta, wq, cout_pad, taps_total, stream);
+  }
 }
 
 }  // namespace vsp

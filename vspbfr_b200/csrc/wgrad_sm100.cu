@@ -76,7 +76,7 @@ wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmap_dy,
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {

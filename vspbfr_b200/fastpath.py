@@ -171,16 +171,34 @@ def _pack_padded(weight, wscale, cin_pad):
 
 
 def to_rgb(m: ToRGB, x, style, skip=None):
-    """ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip; fp32 NCHW in/out for RGB."""
+    """ToRGB: 1x1 modulated conv (no demod) + bias + FIR-upsampled skip; fp32 NCHW in/out for RGB.
+    N = 3 makes this a memory-bound read of the feature map: dedicated SIMT kernel, modulation applied
+    to the weights in shared memory (no weight prologue launch)."""
     conv = m.conv
+    b, h, w, c = x.shape
     s = _linear(conv.modulation, style)
-    wq, _ = mc.pack_weights(conv.weight.detach().view(3, conv.in_channel, 1, 1), s, wscale=conv.scale)
     res = None
     if skip is not None:
         f = m.upsample.factor
         res = upfirdn2d_raw(skip, m.upsample.kernel, (f, f), (1, 1), (m.upsample.pad[0], m.upsample.pad[1]) * 2)
     bias = _cached(m, "bias3", [m.bias], lambda: m.bias.detach().reshape(3).contiguous())
-    return mc.conv_fprop(x, wq, 3, 1, 1, 1, 0, 1, epi=mc.make_epilogue(bias=bias, residual=res))
+    w3 = _cached(m, "w3", [conv.weight], lambda: _pad_cols(conv.weight.detach().reshape(3, conv.in_channel), c))
+    if c != conv.in_channel:
+        s = F.pad(s, (0, c - conv.in_channel))
+    out = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().vsp_torgb_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(res), ptr(out),
+                                             b, h * w, c, conv.scale, stream_ptr())
+    _lib.check(rc, "torgb_nhwc_bf16")
+    return out
+
+
+def _pad_cols(w, c):
+    if w.shape[1] == c:
+        return w.contiguous()
+    out = torch.zeros((w.shape[0], c), dtype=w.dtype, device=w.device)
+    out[:, :w.shape[1]] = w
+    return out
 
 
 def _mapped_latent(mapping, n_latent, styles, inject_index, truncation, truncation_latent, input_is_latent):
