@@ -274,46 +274,47 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   const int num_kb = p.ntaps * p.kc;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long t = tile;
-        const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
-        const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
-        const int b = (int)t;
-        const int g = p.groups == 1 ? 0 : b;
-        const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.kc;
-          const int c0 = (kb - tap * p.kc) * kBlockK;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long t = tile;
+      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+      const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
+      const int b = (int)t;
+      const int g = p.groups == 1 ? 0 : b;
+      const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.kc;
+        const int c0 = (kb - tap * p.kc) * kBlockK;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           unsigned char *sa = smem + stage * C::STAGE_BYTES;
           unsigned char *sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, iw0 + p.tap_dx[tap], ih0 + p.tap_dy[tap], b);
           tma_load_4d(sb, &tmap_b, &full_bar[stage], c0, n_i * BLOCK_N, p.tap_w[tap], g);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (same scheme) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = umma_smem_desc(sa, 128);
           const uint64_t bdesc = umma_smem_desc(sa + kABytes, 128);
@@ -324,11 +325,12 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
                          (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);
@@ -415,108 +417,131 @@ conv_rowhalo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
   const uint32_t a_row_bytes = (uint32_t)hw * 128u;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0, res_ph = 0;
-      long long cur_key = -1;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long t = tile;
-        const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
-        const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
-        const int oh = (int)(t % p.tiles_h); t /= p.tiles_h;
-        const int b = (int)t;
-        const int g = p.groups == 1 ? 0 : b;
-        if (RESIDENT_B) {
-          const long long key = (long long)g * p.tiles_n + n_i;
-          if (key != cur_key) {
-            mbar_wait(&b_empty[0], res_ph ^ 1);          // every MMA that read the old weights has retired
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0, res_ph = 0;
+    long long cur_key = -1;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long t = tile;
+      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+      const int oh = (int)(t % p.tiles_h); t /= p.tiles_h;
+      const int b = (int)t;
+      const int g = p.groups == 1 ? 0 : b;
+      if (RESIDENT_B) {
+        const long long key = (long long)g * p.tiles_n + n_i;
+        if (key != cur_key) {
+          mbar_wait(&b_empty[0], res_ph ^ 1);          // every MMA that read the old weights has retired
+          if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[0], 9 * H::B_BYTES);
             for (int tap = 0; tap < 9; ++tap)
               tma_load_4d(b_buf + tap * H::B_BYTES, &tmap_b, &b_full[0], 0, n_i * BLOCK_N, p.tap_w[tap], g);
-            cur_key = key;
-            res_ph ^= 1;
           }
+          __syncwarp();
+          cur_key = key;
+          res_ph ^= 1;
         }
-        for (int c = 0; c < p.kc; ++c) {
-          mbar_wait(&a_empty[as], aph ^ 1);
+      }
+      for (int c = 0; c < p.kc; ++c) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
           unsigned char *sa = a_buf + as * H::A_STAGE_BYTES;
           mbar_arrive_expect_tx(&a_full[as], 3 * a_row_bytes);
           for (int kh = 0; kh < 3; ++kh)
             tma_load_4d(sa + kh * a_row_bytes, &tmap_a, &a_full[as], c * kBlockK, w_i * kBlockM - d, oh + (kh - 1) * d, b);
-          if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
-          if (!RESIDENT_B) {
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
+        }
+        __syncwarp();
+        if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
+        if (!RESIDENT_B) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(&b_full[bs], H::B_BYTES);
               tma_load_4d(b_buf + bs * H::B_BYTES, &tmap_b, &b_full[bs], c * kBlockK, n_i * BLOCK_N, p.tap_w[tap], g);
-              if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
             }
+            __syncwarp();
+            if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-      int as = 0, bs = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, acc_phase = 0, res_ph = 0;
-      long long cur_key = -1;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        if (RESIDENT_B) {
-          const int n_i = (int)(tile % p.tiles_n);
-          const int b = (int)(tile / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
-          const long long key = (long long)(p.groups == 1 ? 0 : b) * p.tiles_n + n_i;
-          if (key != cur_key) {
-            mbar_wait(&b_full[0], res_ph);
-            res_ph ^= 1;
-            cur_key = key;
-          }
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, acc_phase = 0, res_ph = 0;
+    long long cur_key = -1;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (RESIDENT_B) {
+        const int n_i = (int)(tile % p.tiles_n);
+        const int b = (int)(tile / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
+        const long long key = (long long)(p.groups == 1 ? 0 : b) * p.tiles_n + n_i;
+        if (key != cur_key) {
+          mbar_wait(&b_full[0], res_ph);
+          res_ph ^= 1;
+          cur_key = key;
         }
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      }
+      bool release = false;
+      if (RESIDENT_B) {
+        const long long nt = tile + gridDim.x;
+        release = nt >= p.total_tiles;
+        if (!release) {
+          const int n_i2 = (int)(nt % p.tiles_n);
+          const int b2 = (int)(nt / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
+          release = ((long long)(p.groups == 1 ? 0 : b2) * p.tiles_n + n_i2) != cur_key;
+        }
+      }
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int c = 0; c < p.kc; ++c) {
+        mbar_wait(&a_full[as], aph);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int c = 0; c < p.kc; ++c) {
-          mbar_wait(&a_full[as], aph);
-          tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(a_buf + as * H::A_STAGE_BYTES);
+        const uint32_t a_base = smem_u32(a_buf + as * H::A_STAGE_BYTES);
+        if (RESIDENT_B) {
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const uint64_t adesc = umma_smem_desc(a_base + (uint32_t)kh * a_row_bytes + (uint32_t)(kw * d) * 128u, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(b_buf + tap * H::B_BYTES), 128);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                             (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&a_empty[as]);
+            if (c == p.kc - 1) {
+              umma_commit(&tmem_full[acc]);
+              if (release) umma_commit(&b_empty[0]);   // weights may be overwritten once these MMAs retire
+            }
+          }
+          __syncwarp();
+        } else {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const int kh = tap / 3, kw = tap - kh * 3;
-            uint32_t b_base;
-            if (RESIDENT_B) {
-              b_base = smem_u32(b_buf + tap * H::B_BYTES);
-            } else {
-              mbar_wait(&b_full[bs], bph);
-              tcgen05_fence_after();
-              b_base = smem_u32(b_buf + bs * H::B_BYTES);
-            }
-            const uint64_t adesc = umma_smem_desc(a_base + (uint32_t)kh * a_row_bytes + (uint32_t)(kw * d) * 128u, 128);
-            const uint64_t bdesc = umma_smem_desc(b_base, 128);
+            mbar_wait(&b_full[bs], bph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint64_t adesc = umma_smem_desc(a_base + (uint32_t)kh * a_row_bytes + (uint32_t)(kw * d) * 128u, 128);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(b_buf + bs * H::B_BYTES), 128);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                           (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            if (!RESIDENT_B) {
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                             (c > 0 || tap > 0 || k > 0) ? 1u : 0u);
               umma_commit(&b_empty[bs]);
-              if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
+              if (tap == 8) {
+                umma_commit(&a_empty[as]);
+                if (c == p.kc - 1) umma_commit(&tmem_full[acc]);
+              }
             }
+            __syncwarp();
+            if (++bs == H::B_SLOTS) { bs = 0; bph ^= 1; }
           }
-          umma_commit(&a_empty[as]);
-          if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (RESIDENT_B) {
-          const long long nt = tile + gridDim.x;
-          bool release = nt >= p.total_tiles;
-          if (!release) {
-            const int n_i2 = (int)(nt % p.tiles_n);
-            const int b2 = (int)(nt / ((long long)p.tiles_n * p.tiles_w * p.tiles_h));
-            release = ((long long)(p.groups == 1 ? 0 : b2) * p.tiles_n + n_i2) != cur_key;
-          }
-          if (release) umma_commit(&b_empty[0]);   // weights may be overwritten once these MMAs retire
-        }
+        if (++as == H::A_STAGES) { as = 0; aph ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);

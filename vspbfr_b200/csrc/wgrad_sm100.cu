@@ -107,23 +107,24 @@ wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmap_dy,
   const int kb_per = (kb_total + p.ksplit - 1) / p.ksplit;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        long long t = tile;
-        const int ks = (int)(t % p.ksplit); t /= p.ksplit;
-        const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
-        const int m_i = (int)(t % p.tiles_m); t /= p.tiles_m;
-        const int tap = (int)(t % p.ntaps); t /= p.ntaps;
-        const int g = (int)t;
-        const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, kb_total);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          int r = kb;
-          const int wb = r % p.kb_w; r /= p.kb_w;
-          const int hb = r % p.kb_h; r /= p.kb_h;
-          const int b = p.groups == 1 ? r : g;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // whole warp walks the loop; one elected lane issues (see elect_one in common.cuh)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      long long t = tile;
+      const int ks = (int)(t % p.ksplit); t /= p.ksplit;
+      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int m_i = (int)(t % p.tiles_m); t /= p.tiles_m;
+      const int tap = (int)(t % p.ntaps); t /= p.ntaps;
+      const int g = (int)t;
+      const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int r = kb;
+        const int wb = r % p.kb_w; r /= p.kb_w;
+        const int hb = r % p.kb_h; r /= p.kb_h;
+        const int b = p.groups == 1 ? r : g;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           unsigned char *sa = smem + stage * C::STAGE_BYTES;
           unsigned char *sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
@@ -135,26 +136,27 @@ wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmap_dy,
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(sb + j * kBoxBytes, &tmap_x, &full_bar[stage], n_i * BLOCK_N + 64 * j,
                         ow0 * p.stride + p.tap_dx[tap], oh0 * p.stride + p.tap_dy[tap], b);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_mn(kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ks = (int)(tile % p.ksplit);
-        const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, kb_total);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int ks = (int)(tile % p.ksplit);
+      const int kb0 = ks * kb_per, kb1 = min(kb0 + kb_per, kb_total);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint64_t adesc = umma_desc_mn(sa);
           const uint64_t bdesc = umma_desc_mn(sa + C::A_BYTES);
@@ -165,11 +167,13 @@ wgrad_kernel(const WgradParams p, const __grid_constant__ CUtensorMap tmap_dy,
                          (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int quad = warp & 3;

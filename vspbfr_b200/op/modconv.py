@@ -30,14 +30,21 @@ class KernelProfiler:
 
     def __init__(self):
         self.records = []
+        self.details = []
 
-    def wrap(self, name, flops, fn):
+    def wrap(self, name, flops, fn, detail="", nbytes=0.0):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         out = fn()
         e.record()
         self.records.append((name, float(flops), s, e))
+        self.details.append((detail, float(nbytes)))
         return out
+
+    def table(self):
+        """Per-launch rows (name, detail, flops, bytes, seconds) in launch order."""
+        torch.cuda.synchronize()
+        return [(n, d, f, nb, s.elapsed_time(e) * 1e-3) for (n, f, s, e), (d, nb) in zip(self.records, self.details)]
 
     def summary(self):
         torch.cuda.synchronize()
@@ -58,8 +65,8 @@ def set_profiler(p):
     _profiler = p
 
 
-def _prof(name, flops, fn):
-    return fn() if _profiler is None else _profiler.wrap(name, flops, fn)
+def _prof(name, flops, fn, detail="", nbytes=0.0):
+    return fn() if _profiler is None else _profiler.wrap(name, flops, fn, detail, nbytes)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -194,7 +201,9 @@ def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=N
     with torch.cuda.device(x_nhwc.device):
         rc = _prof("conv_fprop", 2.0 * b * oh * ow * cout * cin * kh * kw, lambda: _lib.load().vsp_conv2d_fprop_bf16(
             ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, stride, pad, dil, int(out_nhwc),
-            ldo, co_off, ctypes.byref(e) if e is not None else None, stream_ptr()))
+            ldo, co_off, ctypes.byref(e) if e is not None else None, stream_ptr()),
+            detail=f"b{b} {cin}->{cout} k{kh} s{stride} d{dil} {h}x{w} g{g}",
+            nbytes=2.0 * b * (h * w * cin + oh * ow * cout * (2 if not out_nhwc else 1)))
     _lib.check(rc, "conv2d_fprop_bf16")
     return out
 
@@ -246,7 +255,9 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
         rc = _prof("conv_transpose_s2", 2.0 * b * h * w * cout * cin * kh * kw,
                    lambda: _lib.load().vsp_conv_transpose2d_s2_bf16(
                        ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, int(out_nhwc), ldo, 0,
-                       ctypes.byref(e) if e is not None else None, stream_ptr()))
+                       ctypes.byref(e) if e is not None else None, stream_ptr()),
+                   detail=f"b{b} {cin}->{cout} k{kh} up2 {h}x{w} g{g}",
+                   nbytes=2.0 * b * (h * w * cin + (2 * h + 1) * (2 * w + 1) * cout))
     _lib.check(rc, "conv_transpose2d_s2_bf16")
     return out
 
