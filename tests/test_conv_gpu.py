@@ -394,3 +394,78 @@ def test_rowhalo_conv(b, cin, cout, h, w, dil, per_sample):
         want = F.conv2d(bf16r(x), bf16r(wt), None, 1, dil, dil)
     out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, dil, dil)
     assert_close_tight(out, want)
+
+
+RING_CASES = [
+    # b, cin, cout, h, w, k, dil   (wide shallow stride-1 layers -> row-ring kernel: rolling row slots, R rows per hand-off)
+    (2, 64, 64, 37, 128, 3, 1),      # resident weights, R=4 with a remainder step
+    (1, 32, 32, 64, 256, 3, 1),      # K-skip (Cin < 64), two strips
+    (2, 64, 16, 24, 128, 3, 2),      # dilated chains
+    (1, 64, 16, 32, 256, 3, 4),
+    (1, 64, 16, 48, 128, 3, 8),
+    (1, 128, 32, 20, 128, 3, 1),     # kc = 2, resident
+    (1, 128, 32, 32, 128, 3, 4),
+    (1, 128, 128, 21, 128, 3, 1),    # kc = 2, streamed weights, R=2
+    (2, 64, 128, 19, 128, 3, 1),     # N = 128
+    (1, 64, 48, 9, 200, 3, 1),       # ragged width and channels
+    (2, 8, 64, 40, 128, 1, 1),       # 1x1, Cin = 8 (first LargeConvLayer)
+    (1, 64, 64, 33, 256, 1, 1),      # 1x1
+    (1, 128, 24, 17, 130, 1, 1),     # 1x1, kc = 2
+    (4, 64, 64, 300, 128, 3, 1),     # many units per CTA: ring wrap, weight reload per sample
+]
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w,k,dil", RING_CASES)
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_ring_conv(b, cin, cout, h, w, k, dil, per_sample):
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + w + dil + h)
+    x = torch.randn(b, cin, h, w, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(DEV)
+    pad = dil * (k // 2)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    if per_sample:
+        s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
+        wq, _ = mc.pack_weights(wt, s)
+        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wt * s[i][None, :, None, None]), None, 1, pad, dil)
+                          for i in range(b)])
+    else:
+        wq, _ = mc.pack_weights(wt)
+        want = F.conv2d(bf16r(x), bf16r(wt), None, 1, pad, dil)
+    if wq.shape[3] != xq.shape[3]:   # Cin padded to 8 on the activation side
+        wq = F.pad(wq, (0, xq.shape[3] - wq.shape[3]))
+    out = mc.conv_fprop(xq, wq, cout, k, k, 1, pad, dil)
+    assert_close_tight(out, want)
+
+
+def test_ring_conv_epilogue_nhwc_slices():
+    """Row-ring kernel with the full fused epilogue, NHWC bf16 output at a channel offset (SMART branch layout)
+    and the two-stage activation + noise + residuals (SMART fusion / StyledConv tails)."""
+    torch.manual_seed(21)
+    b, cin, cout, h, w = 2, 64, 64, 26, 256
+    x = torch.randn(b, cin, h, w, device=DEV)
+    wt = torch.randn(cout, cin, 3, 3, device=DEV) / 24
+    noise = torch.randn(b, 1, h, w, device=DEV)
+    b1, b2 = torch.randn(cout, device=DEV), torch.randn(cout, device=DEV)
+    rs = torch.rand(b, cout, device=DEV) + 0.5
+    res = torch.randn(b, cout, h, w, device=DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(wt)
+    nw = torch.tensor([0.41], device=DEV)
+    resq = mc.nchw_to_nhwc_bf16(res)
+    epi = mc.make_epilogue(row_scale=rs, pre_bias=b1, pre_act=3, noise=noise, noise_weight_dev=nw, bias=b2, act=3, alpha=0.2,
+                           scale=math.sqrt(2), residual=resq)
+    out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, 1, 1, epi=epi, out_nhwc=True)
+    y = F.leaky_relu(F.conv2d(bf16r(x), bf16r(wt), None, 1, 1) * rs[:, :, None, None] + b1[None, :, None, None], 0.2) * math.sqrt(2)
+    y = F.leaky_relu(y + 0.41 * noise + b2[None, :, None, None], 0.2) * math.sqrt(2) + bf16r(res)
+    assert_close_tight(out.permute(0, 3, 1, 2).float(), y, tol=1e-2)
+    # four dilated 16-channel branches into slices of one 64-channel buffer
+    buf = torch.zeros(b, h - 2, w, 64, dtype=torch.bfloat16, device=DEV)
+    xs = x[:, :, :h - 2].contiguous()
+    xsq = mc.nchw_to_nhwc_bf16(xs)
+    for j, dil in enumerate((1, 2, 4, 8)):
+        wj = wt[16 * j:16 * j + 16].contiguous()
+        wqj, _ = mc.pack_weights(wj)
+        epi = mc.make_epilogue(row_scale=rs[:, 16 * j:16 * j + 16].contiguous())
+        mc.conv_fprop(xsq, wqj, 16, 3, 3, 1, dil, dil, epi=epi, out=buf, out_nhwc=True, co_off=16 * j)
+        want = F.conv2d(bf16r(xs), bf16r(wj), None, 1, dil, dil) * rs[:, 16 * j:16 * j + 16, None, None]
+        assert_close_tight(buf[..., 16 * j:16 * j + 16].permute(0, 3, 1, 2).float(), want, tol=1e-2)

@@ -27,6 +27,7 @@ SOURCES = [
     "bias_act_sm100.cu",
     "layout_sm100.cu",
     "conv_sm100.cu",
+    "conv_ring_sm100.cu",
     "wgrad_sm100.cu",
     "torgb_sm100.cu",
 ]
@@ -71,9 +72,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         for src in _sources():
             obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
             objs.append(obj)
+            hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+            hdrs.append(os.path.join(INCLUDE, "vsp_b200.h"))
             if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
-                    and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "common.cuh"))
-                    and os.path.getmtime(obj) > os.path.getmtime(os.path.join(INCLUDE, "vsp_b200.h"))):
+                    and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in hdrs)):
                 continue
             cmd = [nvcc, *compile_flags, "-c", src, "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -1,0 +1,160 @@
+// conv_common.cuh — pieces shared by the tcgen05 convolution kernels (conv_sm100.cu, conv_ring_sm100.cu):
+// launch parameters, tile constants and the fused epilogue applied to one chunk of accumulator columns.
+#pragma once
+#include "common.cuh"
+
+namespace vsp {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kNumThreads = 192;         // 6 warps
+constexpr int kMaxTaps = 16;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+struct ConvParams {
+  int batch, groups;
+  int cin, cout;
+  int out_h, out_w;        // logical output extent of this launch
+  int stride;
+  int ntaps;
+  int tap_w[kMaxTaps], tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+  int tw, th, tiles_w, tiles_h, tiles_n;
+  long long total_tiles;
+  int kc;                  // channel blocks per tap = ceil(cin / 64)
+  int halo_d, halo_w;      // row-halo / row-ring kernels: dilation and padded halo row length (pixels)
+  // row-ring kernel: R output rows per accumulator hand-off, S row slots, segments of L rows per chain
+  int rr_R, rr_S, rr_L, rr_segs, rr_chains, rr_strips, rr_nb;
+  // output addressing: logical (oh, ow) -> (oh*os + oo_h, ow*os + oo_w) inside [full_h, full_w]
+  void *out;
+  int out_nhwc;
+  int full_h, full_w, os, oo_h, oo_w;
+  long long ldo, co_off;
+  // epilogue
+  const float *row_scale;
+  const float *noise;
+  long long noise_bstride;
+  float noise_weight;
+  const float *noise_weight_dev;
+  const float *bias;
+  const float *pre_bias;
+  int pre_act;
+  int act;
+  float alpha, scale;
+  const void *residual;
+  const void *residual2;
+};
+
+__device__ __forceinline__ float epi_act(float v, int act, float alpha, float scale) {
+  if (act == 3) v = (v > 0.f ? v : v * alpha) * scale;
+  return v;
+}
+
+// Fused epilogue of CHUNK accumulator columns (output channels n0 .. n0+CHUNK-1) of one pixel:
+// TMEM -> registers -> demod, [bias1 + lrelu], noise + bias + lrelu, residuals -> global.
+// `vrs`/`vb1`/`vb2` point at this chunk's slice of the per-channel vectors staged in shared memory.
+template <int CHUNK>
+__device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
+                                          long long plane, bool pix_ok, float nz, const float *vrs,
+                                          const float *vb1, const float *vb2) {
+  const bool live = pix_ok && n0 < p.cout;
+  const bool fullc = n0 + CHUNK <= p.cout;
+  // residual prefetch (independent of the accumulator)
+  float rsd[CHUNK];
+#pragma unroll
+  for (int j = 0; j < CHUNK; ++j) rsd[j] = 0.f;
+  if (live && (p.residual || p.residual2)) {
+    if (!p.out_nhwc) {
+      const long long off = ((long long)b * p.cout + n0) * plane + pix;
+      const float *r1 = static_cast<const float *>(p.residual);
+      const float *r2 = static_cast<const float *>(p.residual2);
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        if (fullc || n0 + j < p.cout) {
+          if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
+          if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
+        }
+    } else {
+      const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+      const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
+                                    static_cast<const __nv_bfloat16 *>(p.residual2)};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!rr[q]) continue;
+        if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; j += 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(rr[q] + off + j));
+            const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h2[e]);
+              rsd[j + 2 * e] += f.x;
+              rsd[j + 2 * e + 1] += f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j)
+            if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
+        }
+      }
+    }
+  }
+  uint32_t r[CHUNK];
+  if constexpr (CHUNK == 32) tmem_ld_32x32b_x32(taddr, r);
+  else tmem_ld_32x32b_x16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
+  tmem_ld_wait();
+  if (live) {
+    float v[CHUNK];
+    const float4 *srs = reinterpret_cast<const float4 *>(vrs);
+    const float4 *sb1 = reinterpret_cast<const float4 *>(vb1);
+    const float4 *sb2 = reinterpret_cast<const float4 *>(vb2);
+#pragma unroll
+    for (int j = 0; j < CHUNK; j += 4) {
+      const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
+      const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = __uint_as_float(r[j + e]) * aa[e];
+        if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
+        x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
+        v[j + e] = x + rsd[j + e];
+      }
+    }
+    if (!p.out_nhwc) {
+      float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
+    } else {
+      __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+      if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 8) {
+          __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+          __nv_bfloat162 q1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+          __nv_bfloat162 q2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+          __nv_bfloat162 q3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t *>(&q0);
+          u.y = *reinterpret_cast<uint32_t *>(&q1);
+          u.z = *reinterpret_cast<uint32_t *>(&q2);
+          u.w = *reinterpret_cast<uint32_t *>(&q3);
+          *reinterpret_cast<uint4 *>(o + j) = u;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j)
+          if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
+
+// conv_ring_sm100.cu: returns -1 when the shape is not eligible (caller falls through to the other kernels),
+// 0 on success, >0 on error.  `p` must already carry cin/cout/extent/output/epilogue fields.
+int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t in_h, int64_t in_w,
+                         int64_t cout_pad, int taps_total, int dil, cudaStream_t stream);
+
+}  // namespace vsp

@@ -19,50 +19,12 @@
 // tile i overlaps the MMAs of tile i+1).  Warp roles: warp0 = TMA producer, warp1 = MMA
 // issuer (one elected lane), warps2-5 = epilogue (tcgen05.ld -> demod/noise/bias/lrelu/
 // residual -> global).  Persistent: one CTA per SM walks the tile list.
-#include "common.cuh"
+#include "conv_common.cuh"
 
 #include <stdlib.h>
 
 namespace vsp {
 namespace {
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 192;         // 6 warps
-constexpr int kMaxTaps = 16;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-
-struct ConvParams {
-  int batch, groups;
-  int cin, cout;
-  int out_h, out_w;        // logical output extent of this launch
-  int stride;
-  int ntaps;
-  int tap_w[kMaxTaps], tap_dy[kMaxTaps], tap_dx[kMaxTaps];
-  int tw, th, tiles_w, tiles_h, tiles_n;
-  long long total_tiles;
-  int kc;                  // channel blocks per tap = ceil(cin / 64)
-  int halo_d, halo_w;      // row-halo kernel: dilation and padded halo row length (pixels)
-  // output addressing: logical (oh, ow) -> (oh*os + oo_h, ow*os + oo_w) inside [full_h, full_w]
-  void *out;
-  int out_nhwc;
-  int full_h, full_w, os, oo_h, oo_w;
-  long long ldo, co_off;
-  // epilogue
-  const float *row_scale;
-  const float *noise;
-  long long noise_bstride;
-  float noise_weight;
-  const float *noise_weight_dev;
-  const float *bias;
-  const float *pre_bias;
-  int pre_act;
-  int act;
-  float alpha, scale;
-  const void *residual;
-  const void *residual2;
-};
 
 template <int BLOCK_N>
 struct ConvCfg {
@@ -74,17 +36,11 @@ struct ConvCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6 * BLOCK_N * 4 /*epilogue vectors*/;
 };
 
-__device__ __forceinline__ float epi_act(float v, int act, float alpha, float scale) {
-  if (act == 3) v = (v > 0.f ? v : v * alpha) * scale;
-  return v;
-}
-
 // Epilogue role (warps 2..5 of either kernel): TMEM -> registers -> fused epilogue -> global.
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_vec, uint64_t *tmem_full,
                                               uint64_t *tmem_empty, uint32_t tmem_base, int warp, int lane) {
   using C = ConvCfg<BLOCK_N>;
-  // ===================== epilogue (warps 2..5) =====================
   // Per-channel vectors (demod, biases) are staged in shared memory once per tile by the 128
   // epilogue threads (coalesced, issued BEFORE waiting for the accumulator so the latency
   // hides behind the MMAs) and then read back as 128-bit broadcasts; accumulators leave TMEM
@@ -128,102 +84,10 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-    for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch) {
-      const int n0 = nbase + ch * C::CHUNK;
-      const bool live = pix_ok && n0 < p.cout;
-      const bool fullc = n0 + C::CHUNK <= p.cout;
-      // residual prefetch (independent of the accumulator)
-      float rsd[C::CHUNK];
-#pragma unroll
-      for (int j = 0; j < C::CHUNK; ++j) rsd[j] = 0.f;
-      if (live && (p.residual || p.residual2)) {
-        if (!p.out_nhwc) {
-          const long long off = ((long long)b * p.cout + n0) * plane + pix;
-          const float *r1 = static_cast<const float *>(p.residual);
-          const float *r2 = static_cast<const float *>(p.residual2);
-#pragma unroll
-          for (int j = 0; j < C::CHUNK; ++j)
-            if (fullc || n0 + j < p.cout) {
-              if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
-              if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
-            }
-        } else {
-          const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-          const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
-                                        static_cast<const __nv_bfloat16 *>(p.residual2)};
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (!rr[q]) continue;
-            if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
-#pragma unroll
-              for (int j = 0; j < C::CHUNK; j += 8) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(rr[q] + off + j));
-                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h2[e]);
-                  rsd[j + 2 * e] += f.x;
-                  rsd[j + 2 * e + 1] += f.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < C::CHUNK; ++j)
-                if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
-            }
-          }
-        }
-      }
-      uint32_t r[C::CHUNK];
-      if constexpr (C::CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * 32, r);
-      else tmem_ld_32x32b_x16(taddr + ch * 16, reinterpret_cast<uint32_t(&)[16]>(r));
-      tmem_ld_wait();
-      if (live) {
-        float v[C::CHUNK];
-        const float4 *srs = reinterpret_cast<const float4 *>(vec_rs + acc * BLOCK_N + ch * C::CHUNK);
-        const float4 *sb1 = reinterpret_cast<const float4 *>(vec_b1 + acc * BLOCK_N + ch * C::CHUNK);
-        const float4 *sb2 = reinterpret_cast<const float4 *>(vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
-#pragma unroll
-        for (int j = 0; j < C::CHUNK; j += 4) {
-          const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
-          const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = __uint_as_float(r[j + e]) * aa[e];
-            if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
-            x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
-            v[j + e] = x + rsd[j + e];
-          }
-        }
-        if (!p.out_nhwc) {
-          float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
-#pragma unroll
-          for (int j = 0; j < C::CHUNK; ++j)
-            if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
-        } else {
-          __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-          if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
-#pragma unroll
-            for (int j = 0; j < C::CHUNK; j += 8) {
-              __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 q1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 q2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 q3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t *>(&q0);
-              u.y = *reinterpret_cast<uint32_t *>(&q1);
-              u.z = *reinterpret_cast<uint32_t *>(&q2);
-              u.w = *reinterpret_cast<uint32_t *>(&q3);
-              *reinterpret_cast<uint4 *>(o + j) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < C::CHUNK; ++j)
-              if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-      }
-    }
+    for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch)
+      epi_chunk<C::CHUNK>(p, taddr + ch * C::CHUNK, nbase + ch * C::CHUNK, b, pix, plane, pix_ok, nz,
+                          vec_rs + acc * BLOCK_N + ch * C::CHUNK, vec_b1 + acc * BLOCK_N + ch * C::CHUNK,
+                          vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -671,6 +535,12 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     p.noise_weight_dev = epi->noise_weight_dev; p.pre_bias = epi->pre_bias; p.pre_act = epi->pre_act;
     VSP_REQUIRE(p.pre_act == 0 || p.pre_act == 3, "conv: epilogue pre_act must be 0 or 3");
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
+  }
+
+  // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers
+  {
+    const int rc = conv_ring_try_launch(p, x, wq, in_h, in_w, cout_pad, taps_total, ntaps == 9 ? tap_dx[8] : 1, stream);
+    if (rc >= 0) return rc;
   }
 
   // Row-halo path: stride-1 3x3 (dilated) "same" convolution on a wide image, plain output mapping
