@@ -417,7 +417,8 @@ RING_CASES = [
 
 @pytest.mark.parametrize("b,cin,cout,h,w,k,dil", RING_CASES)
 @pytest.mark.parametrize("per_sample", [False, True])
-def test_ring_conv(b, cin, cout, h, w, k, dil, per_sample):
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_ring_conv(b, cin, cout, h, w, k, dil, per_sample, nhwc):
     g = torch.Generator(device="cpu").manual_seed(cin + cout + w + dil + h)
     x = torch.randn(b, cin, h, w, generator=g).to(DEV)
     wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(DEV)
@@ -433,8 +434,13 @@ def test_ring_conv(b, cin, cout, h, w, k, dil, per_sample):
         want = F.conv2d(bf16r(x), bf16r(wt), None, 1, pad, dil)
     if wq.shape[3] != xq.shape[3]:   # Cin padded to 8 on the activation side
         wq = F.pad(wq, (0, xq.shape[3] - wq.shape[3]))
-    out = mc.conv_fprop(xq, wq, cout, k, k, 1, pad, dil)
-    assert_close_tight(out, want)
+    if nhwc:   # staged epilogue: swizzled shared-memory tile + TMA store
+        out = mc.conv_fprop(xq, wq, cout, k, k, 1, pad, dil, out_nhwc=True)
+        assert_close_tight(out[..., :cout].permute(0, 3, 1, 2).float(), want, tol=1e-2)
+        assert float(out[..., cout:].abs().max() if out.shape[3] > cout else 0.0) == 0.0
+    else:
+        out = mc.conv_fprop(xq, wq, cout, k, k, 1, pad, dil)
+        assert_close_tight(out, want)
 
 
 def test_ring_conv_epilogue_nhwc_slices():

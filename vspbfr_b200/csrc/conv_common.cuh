@@ -24,7 +24,7 @@ struct ConvParams {
   int kc;                  // channel blocks per tap = ceil(cin / 64)
   int halo_d, halo_w;      // row-halo / row-ring kernels: dilation and padded halo row length (pixels)
   // row-ring kernel: R output rows per accumulator hand-off, S row slots, segments of L rows per chain
-  int rr_R, rr_S, rr_L, rr_segs, rr_chains, rr_strips, rr_nb;
+  int rr_R, rr_S, rr_L, rr_segs, rr_chains, rr_strips, rr_nb, rr_staged;
   // output addressing: logical (oh, ow) -> (oh*os + oo_h, ow*os + oo_w) inside [full_h, full_w]
   void *out;
   int out_nhwc;
@@ -50,13 +50,14 @@ __device__ __forceinline__ float epi_act(float v, int act, float alpha, float sc
   return v;
 }
 
-// Fused epilogue of CHUNK accumulator columns (output channels n0 .. n0+CHUNK-1) of one pixel:
-// TMEM -> registers -> demod, [bias1 + lrelu], noise + bias + lrelu, residuals -> global.
-// `vrs`/`vb1`/`vb2` point at this chunk's slice of the per-channel vectors staged in shared memory.
+// Fused epilogue arithmetic of CHUNK accumulator columns (output channels n0 .. n0+CHUNK-1) of one pixel:
+// TMEM -> registers -> demod, [bias1 + lrelu], noise + bias + lrelu, residuals.  Results in v[] (zeros when the
+// pixel / chunk is outside the output).  `vrs`/`vb1`/`vb2` point at this chunk's slice of the per-channel
+// vectors staged in shared memory.  The tcgen05.ld is executed unconditionally (warp-collective).
 template <int CHUNK>
-__device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
-                                          long long plane, bool pix_ok, float nz, const float *vrs,
-                                          const float *vb1, const float *vb2) {
+__device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
+                                            long long plane, bool pix_ok, float nz, const float *vrs,
+                                            const float *vb1, const float *vb2, float (&v)[CHUNK]) {
   const bool live = pix_ok && n0 < p.cout;
   const bool fullc = n0 + CHUNK <= p.cout;
   // residual prefetch (independent of the accumulator)
@@ -105,51 +106,67 @@ __device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, i
   if constexpr (CHUNK == 32) tmem_ld_32x32b_x32(taddr, r);
   else tmem_ld_32x32b_x16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
   tmem_ld_wait();
-  if (live) {
-    float v[CHUNK];
-    const float4 *srs = reinterpret_cast<const float4 *>(vrs);
-    const float4 *sb1 = reinterpret_cast<const float4 *>(vb1);
-    const float4 *sb2 = reinterpret_cast<const float4 *>(vb2);
+  const float4 *srs = reinterpret_cast<const float4 *>(vrs);
+  const float4 *sb1 = reinterpret_cast<const float4 *>(vb1);
+  const float4 *sb2 = reinterpret_cast<const float4 *>(vb2);
 #pragma unroll
-    for (int j = 0; j < CHUNK; j += 4) {
-      const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
-      const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+  for (int j = 0; j < CHUNK; j += 4) {
+    const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
+    const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float x = __uint_as_float(r[j + e]) * aa[e];
-        if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
-        x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
-        v[j + e] = x + rsd[j + e];
-      }
-    }
-    if (!p.out_nhwc) {
-      float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
-#pragma unroll
-      for (int j = 0; j < CHUNK; ++j)
-        if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
-    } else {
-      __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
-      if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
-#pragma unroll
-        for (int j = 0; j < CHUNK; j += 8) {
-          __nv_bfloat162 q0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-          __nv_bfloat162 q1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-          __nv_bfloat162 q2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-          __nv_bfloat162 q3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t *>(&q0);
-          u.y = *reinterpret_cast<uint32_t *>(&q1);
-          u.z = *reinterpret_cast<uint32_t *>(&q2);
-          u.w = *reinterpret_cast<uint32_t *>(&q3);
-          *reinterpret_cast<uint4 *>(o + j) = u;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < CHUNK; ++j)
-          if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
-      }
+    for (int e = 0; e < 4; ++e) {
+      float x = __uint_as_float(r[j + e]) * aa[e];
+      if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
+      x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
+      v[j + e] = live ? x + rsd[j + e] : 0.f;
     }
   }
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float *v) {
+  __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 q1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 q3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t *>(&q0);
+  u.y = *reinterpret_cast<uint32_t *>(&q1);
+  u.z = *reinterpret_cast<uint32_t *>(&q2);
+  u.w = *reinterpret_cast<uint32_t *>(&q3);
+  return u;
+}
+
+// Direct per-thread stores of one computed chunk: NCHW fp32 (coalesced across the warp's pixels) or NHWC bf16.
+template <int CHUNK>
+__device__ __forceinline__ void epi_store_direct(const ConvParams &p, int n0, int b, long long pix, long long plane,
+                                                 bool pix_ok, const float (&v)[CHUNK]) {
+  if (!(pix_ok && n0 < p.cout)) return;
+  const bool fullc = n0 + CHUNK <= p.cout;
+  if (!p.out_nhwc) {
+    float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
+#pragma unroll
+    for (int j = 0; j < CHUNK; ++j)
+      if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
+  } else {
+    __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+    if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CHUNK; j += 8) *reinterpret_cast<uint4 *>(o + j) = pack8_bf16(&v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CHUNK; ++j)
+        if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+template <int CHUNK>
+__device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
+                                          long long plane, bool pix_ok, float nz, const float *vrs,
+                                          const float *vb1, const float *vb2) {
+  float v[CHUNK];
+  epi_compute<CHUNK>(p, taddr, n0, b, pix, plane, pix_ok, nz, vrs, vb1, vb2, v);
+  epi_store_direct<CHUNK>(p, n0, b, pix, plane, pix_ok, v);
 }
 
 // conv_ring_sm100.cu: returns -1 when the shape is not eligible (caller falls through to the other kernels),
