@@ -226,6 +226,21 @@ int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void *out,
                                  const vsp_conv_epilogue *epi, void *stream);
 
 /*
+ * Fused up-convolution: stride-2 transposed 3x3 convolution followed by the 4x4 FIR blur (pad 1,1), i.e.
+ * ModulatedConv2d(upsample=True) of models/RestoreNet.py:522-535 (conv_transpose2d -> Blur), as ONE dense 3x3
+ * convolution on the low-resolution grid with 4*cout GEMM columns (the composite 6x6 stride-2 kernel split into
+ * its four output-parity classes) and a pixel-shuffle epilogue: column n = (pa*2+pb)*cout + o is written to
+ * out[b, 2*oh+pa, 2*ow+pb, co_off+o].  No (2H+1)^2 intermediate, no separate blur pass.
+ *   x   [batch, in_h, in_w, cin] bf16 NHWC
+ *   wq  [groups, 9, 4*cout, cin] bf16: vsp_modulate_weights_bf16 applied to the class-split composite weights
+ *   out [batch, 2*in_h, 2*in_w, ldo] bf16 NHWC (ldo % 8 == 0); epilogue vectors are indexed by the real channel o
+ */
+int vsp_conv2d_up2_fused_bf16(const void *x, const void *wq, void *out,
+                              int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                              int64_t cin, int64_t cout, int64_t ldo, int64_t co_off,
+                              const vsp_conv_epilogue *epi, void *stream);
+
+/*
  * ToRGB (models/RestoreNet.py:647-666): 1x1 modulated convolution to 3 channels, no demodulation,
  *   out[b,o,p] = sum_c x[b,p,c] * wscale * w[o,c] * s[b,c] + bias[o] + skip[b,o,p]
  * x [batch, hw, c] bf16 NHWC (c % 8 == 0), w [3, c], s [batch, c] (NULL = 1), bias [3] / skip

@@ -475,3 +475,53 @@ def test_ring_conv_epilogue_nhwc_slices():
         mc.conv_fprop(xsq, wqj, 16, 3, 3, 1, dil, dil, epi=epi, out=buf, out_nhwc=True, co_off=16 * j)
         want = F.conv2d(bf16r(xs), bf16r(wj), None, 1, dil, dil) * rs[:, 16 * j:16 * j + 16, None, None]
         assert_close_tight(buf[..., 16 * j:16 * j + 16].permute(0, 3, 1, 2).float(), want, tol=1e-2)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w_", [(2, 64, 32, 32, 32), (1, 128, 64, 16, 64), (2, 64, 64, 8, 160), (1, 256, 128, 32, 32),
+                                             (3, 64, 32, 5, 96)])
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_up2_fused_matches_transposed_conv_then_blur(b, cin, cout, h, w_, per_sample):
+    """Fused up-conv (composite 6x6 stride-2 kernel as a dense 3x3 conv with a pixel-shuffle epilogue) against the
+    reference formulation: conv_transpose2d(stride 2) -> upfirdn2d blur pad (1,1), with noise + bias + lrelu and two
+    residuals in the epilogue (the StyledConv(up) tail of the restoration decoder)."""
+    from oracle import upfirdn2d_ref
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + h + w_)
+    x = torch.randn(b, cin, h, w_, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    k4 = (torch.outer(k1, k1) / 64 * 4).to(DEV)
+    s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV) if per_sample else None
+    noise = torch.randn(b, 1, 2 * h, 2 * w_, generator=g).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    rs = (torch.rand(b, cout, generator=g) + 0.5).to(DEV)
+    res = torch.randn(b, cout, 2 * h, 2 * w_, generator=g).to(DEV)
+    res2 = torch.randn(b, cout, 2 * h, 2 * w_, generator=g).to(DEV)
+    w3 = mc.compose_up2_weights(wt, k4)
+    wq, _ = mc.pack_weights(w3, s)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    epi = mc.make_epilogue(row_scale=rs, noise=noise, noise_weight=0.3, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2),
+                           residual=mc.nchw_to_nhwc_bf16(res), residual2=mc.nchw_to_nhwc_bf16(res2))
+    out = mc.conv_up2_fused(xq, wq, cout, epi=epi)
+    assert out.shape == (b, 2 * h, 2 * w_, cout)
+    # reference: per-sample transposed conv (fp32 on bf16-rounded activations), then the FIR blur via the CPU oracle
+    ys = []
+    for i in range(b):
+        wi = wt * s[i][None, :, None, None] if per_sample else wt
+        ys.append(F.conv_transpose2d(bf16r(x[i:i + 1]), wi.transpose(0, 1), stride=2))
+    y = torch.cat(ys)
+    yb = torch.from_numpy(upfirdn2d_ref(y.cpu().numpy(), k4.cpu().numpy(), 1, 1, (1, 1))).to(DEV)
+    want = F.leaky_relu(yb * rs[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    want = want + bf16r(res) + bf16r(res2)
+    got = out.permute(0, 3, 1, 2).float()
+    # tight check of the kernel itself: fp32 conv with the bf16-rounded composite weights + pixel shuffle
+    zs = []
+    for i in range(b):
+        wi = bf16r(w3 * s[i][None, :, None, None]) if per_sample else bf16r(w3)
+        zs.append(F.pixel_shuffle(F.conv2d(bf16r(x[i:i + 1]), wi, None, 1, 1)
+                                  .view(1, 4, cout, h, w_).transpose(1, 2).reshape(1, cout * 4, h, w_), 2))
+    z = torch.cat(zs)
+    want_t = F.leaky_relu(z * rs[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    assert_close_tight(got, want_t + bf16r(res) + bf16r(res2), tol=1e-2)
+    # composite weights are rounded to bf16 once (instead of the 3x3 weights): compare at the bf16 tolerance
+    assert_close_tight(got, want, tol=2e-2)
+    assert psnr(got, want) > 45.0

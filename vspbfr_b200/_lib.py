@@ -154,6 +154,8 @@ SIGNATURES = {
     "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_conv2d_up2_fused_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                          c_int64, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
     "vsp_torgb_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,

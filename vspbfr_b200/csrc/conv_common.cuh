@@ -30,6 +30,10 @@ struct ConvParams {
   int out_nhwc;
   int full_h, full_w, os, oo_h, oo_w;
   long long ldo, co_off;
+  // pixel-shuffle epilogue (fused up-conv): GEMM column n = class * shuffle_cout + channel, class = (pa, pb) in
+  // row-major order, written to (2*oh + pa, 2*ow + pb); 0 = off
+  int shuffle_cout;
+  int staged;              // conv_fprop_kernel: epilogue through swizzled shared memory + TMA stores
   // epilogue
   const float *row_scale;
   const float *noise;
@@ -44,6 +48,19 @@ struct ConvParams {
   const void *residual;
   const void *residual2;
 };
+
+__device__ __forceinline__ uint4 pack8_bf16(const float *v) {
+  __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 q1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 q3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t *>(&q0);
+  u.y = *reinterpret_cast<uint32_t *>(&q1);
+  u.z = *reinterpret_cast<uint32_t *>(&q2);
+  u.w = *reinterpret_cast<uint32_t *>(&q3);
+  return u;
+}
 
 __device__ __forceinline__ float epi_act(float v, int act, float alpha, float scale) {
   if (act == 3) v = (v > 0.f ? v : v * alpha) * scale;
@@ -123,19 +140,6 @@ __device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr,
   }
 }
 
-__device__ __forceinline__ uint4 pack8_bf16(const float *v) {
-  __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]);
-  __nv_bfloat162 q1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]);
-  __nv_bfloat162 q3 = __floats2bfloat162_rn(v[6], v[7]);
-  uint4 u;
-  u.x = *reinterpret_cast<uint32_t *>(&q0);
-  u.y = *reinterpret_cast<uint32_t *>(&q1);
-  u.z = *reinterpret_cast<uint32_t *>(&q2);
-  u.w = *reinterpret_cast<uint32_t *>(&q3);
-  return u;
-}
-
 // Direct per-thread stores of one computed chunk: NCHW fp32 (coalesced across the warp's pixels) or NHWC bf16.
 template <int CHUNK>
 __device__ __forceinline__ void epi_store_direct(const ConvParams &p, int n0, int b, long long pix, long long plane,
@@ -159,6 +163,50 @@ __device__ __forceinline__ void epi_store_direct(const ConvParams &p, int n0, in
     }
   }
 }
+
+// Lean staged epilogue arithmetic for 8 channels: demod, [bias1 + lrelu], noise + bias + lrelu, branch-free
+// (a disabled stage has alpha = scale = 1: max(t, t) = t).  lrelu(t) * s == max(t * s, t * s * a) for 0 <= a <= 1, s > 0.
+__device__ __forceinline__ void epi_lean8f(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
+                                           float nz, float m1, float m1a, float m2, float m2a, float (&v)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = reinterpret_cast<const float4 *>(vrs)[h];
+    const float4 c1 = reinterpret_cast<const float4 *>(vb1)[h];
+    const float4 c2 = reinterpret_cast<const float4 *>(vb2)[h];
+    const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], b1[e]);
+      const float y = fmaxf(t * m1, t * m1a);
+      const float t2 = y + (nz + b2[e]);
+      v[4 * h + e] = fmaxf(t2 * m2, t2 * m2a);
+    }
+  }
+}
+__device__ __forceinline__ uint4 epi_lean8(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
+                                           float nz, float m1, float m1a, float m2, float m2a) {
+  float v[8];
+  epi_lean8f(r, vrs, vb1, vb2, nz, m1, m1a, m2, m2a, v);
+  return pack8_bf16(v);
+}
+
+// v[0..7] += a + b (packed bf16 residuals)
+__device__ __forceinline__ void add2_bf16x8(float (&v)[8], const uint4 &a, const uint4 &b) {
+  const __nv_bfloat162 *ha = reinterpret_cast<const __nv_bfloat162 *>(&a);
+  const __nv_bfloat162 *hb = reinterpret_cast<const __nv_bfloat162 *>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
+    v[2 * i] += fa.x + fb.x;
+    v[2 * i + 1] += fa.y + fb.y;
+  }
+}
+
+// Output tensor maps of the staged (shared memory -> TMA store) epilogue: one per output parity class
+// (plain convs use m[0]; a stride-2 class launch uses its own; the pixel-shuffle epilogue uses all four).
+struct OutMaps {
+  CUtensorMap m[4];
+};
 
 template <int CHUNK>
 __device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,

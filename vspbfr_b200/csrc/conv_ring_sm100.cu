@@ -49,28 +49,6 @@ __device__ __forceinline__ RingUnit ring_decode(const ConvParams &p, long long u
   return r;
 }
 
-// Lean staged epilogue arithmetic for 8 channels: demod, [bias1 + lrelu], noise + bias + lrelu, branch-free
-// (a disabled stage has alpha = scale = 1: max(t, t) = t).  lrelu(t) * s == max(t * s, t * s * a) for 0 <= a <= 1, s > 0.
-__device__ __forceinline__ uint4 epi_lean8(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
-                                           float nz, float m1, float m1a, float m2, float m2a) {
-  float v[8];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float4 a = reinterpret_cast<const float4 *>(vrs)[h];
-    const float4 c1 = reinterpret_cast<const float4 *>(vb1)[h];
-    const float4 c2 = reinterpret_cast<const float4 *>(vb2)[h];
-    const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], b1[e]);
-      const float y = fmaxf(t * m1, t * m1a);
-      const float t2 = y + (nz + b2[e]);
-      v[4 * h + e] = fmaxf(t2 * m2, t2 * m2a);
-    }
-  }
-  return pack8_bf16(v);
-}
-
 template <int BLOCK_N, int TAPS, bool STAGED>
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,

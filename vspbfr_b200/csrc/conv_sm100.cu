@@ -33,7 +33,10 @@ struct ConvCfg {
   static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;
+  static constexpr int SBUF_BYTES = 32 * CHUNK * 2;          // staged epilogue: 32 pixels x CHUNK channels bf16
+  static constexpr int OSTAGE_BYTES = 4 * 2 * SBUF_BYTES;     // two buffers per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6 * BLOCK_N * 4 /*epilogue vectors*/;
+  static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + OSTAGE_BYTES + 1024;
 };
 
 // Epilogue role (warps 2..5 of either kernel): TMEM -> registers -> fused epilogue -> global.
@@ -95,10 +98,119 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
   }
 }
 
+// Staged epilogue role: same arithmetic (branch-free form), but each warp stages its 32 pixels x CHUNK channels in
+// swizzled shared memory and writes them with one TMA store (full lines instead of 16-byte pieces at pixel
+// pitch).  Handles the parity-class output mappings (one tensor map per class) and the pixel-shuffle mapping of
+// the fused up-convolution.  Requires tw >= 32 (a warp's pixels lie in one output row).
 template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const OutMaps &maps, float *epi_vec,
+                                                     unsigned char *o_buf, uint64_t *tmem_full, uint64_t *tmem_empty,
+                                                     uint32_t tmem_base, int warp, int lane) {
+  using C = ConvCfg<BLOCK_N>;
+  constexpr int CHUNK = C::CHUNK;
+  constexpr int ROW_BYTES = CHUNK * 2;
+  const int quad = warp & 3;
+  const int row = quad * 32 + lane;
+  const int et = threadIdx.x - 64;
+  float *vec_rs = epi_vec, *vec_b1 = epi_vec + 2 * BLOCK_N, *vec_b2 = epi_vec + 4 * BLOCK_N;
+  const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
+  const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
+  const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
+  const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+  unsigned char *stage = o_buf + quad * 2 * C::SBUF_BYTES;
+  const long long plane = (long long)p.full_h * p.full_w;
+  const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+  const __nv_bfloat16 *res1 = static_cast<const __nv_bfloat16 *>(p.residual);
+  const __nv_bfloat16 *res2 = static_cast<const __nv_bfloat16 *>(p.residual2);
+  int acc = 0;
+  uint32_t acc_phase = 0, sbuf = 0;
+  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    long long t = tile;
+    const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+    const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+    const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
+    const int b = (int)t;
+    const int oh = h_i * p.th + row / p.tw;
+    const int ow = w_i * p.tw + row % p.tw;
+    const bool pix_ok = oh < p.out_h && ow < p.out_w;
+    const int oh_w = h_i * p.th + (quad * 32) / p.tw, ow_w = w_i * p.tw + (quad * 32) % p.tw;   // warp's first pixel
+    const int nbase = n_i * BLOCK_N;
+    for (int c = et; c < BLOCK_N; c += 128) {
+      const int n = nbase + c;
+      const int cr = p.shuffle_cout ? n % p.shuffle_cout : n;
+      const bool ok = n < p.cout;
+      vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * creal + cr) : 1.f;
+      vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f;
+      vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + cr) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+    constexpr int NCH = BLOCK_N / CHUNK;
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int n0 = nbase + ch * CHUNK;
+      if (n0 >= p.cout) {            // warp-uniform: nothing to write for the padded tail of the channel tile
+        if (ch == NCH - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        continue;
+      }
+      const int cls = p.shuffle_cout ? n0 / p.shuffle_cout : 0;
+      const int c0 = p.shuffle_cout ? n0 % p.shuffle_cout : n0;
+      const int fh = oh * p.os + p.oo_h + (cls >> 1), fw = ow * p.os + p.oo_w + (cls & 1);
+      const long long pix = (long long)fh * p.full_w + fw;
+      float nz = 0.f;
+      if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
+      uint4 rs1[CHUNK / 8], rs2[CHUNK / 8];
+      const long long roff = ((long long)b * plane + pix) * p.ldo + p.co_off + c0;
+#pragma unroll
+      for (int i = 0; i < CHUNK / 8; ++i) {
+        rs1[i] = (res1 && pix_ok) ? __ldg(reinterpret_cast<const uint4 *>(res1 + roff) + i) : make_uint4(0u, 0u, 0u, 0u);
+        rs2[i] = (res2 && pix_ok) ? __ldg(reinterpret_cast<const uint4 *>(res2 + roff) + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      uint32_t r[CHUNK];
+      if constexpr (CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * CHUNK, r);
+      else tmem_ld_32x32b_x16(taddr + ch * CHUNK, reinterpret_cast<uint32_t(&)[16]>(r));
+      tmem_ld_wait();
+      if (ch == NCH - 1) {           // accumulators are in registers: the MMA warp may reuse this stage
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      unsigned char *buf = stage + (sbuf & 1) * C::SBUF_BYTES;
+      ++sbuf;
+      if (lane == 0) bulk_wait_group_read<1>();
+      __syncwarp();
+      const float *vrs = vec_rs + acc * BLOCK_N + ch * CHUNK, *vb1 = vec_b1 + acc * BLOCK_N + ch * CHUNK,
+                  *vb2 = vec_b2 + acc * BLOCK_N + ch * CHUNK;
+#pragma unroll
+      for (int i = 0; i < CHUNK / 8; ++i) {
+        float v[8];
+        epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz, m1, m1a, m2, m2a, v);
+        if (res1 || res2) add2_bf16x8(v, rs1[i], rs2[i]);
+        *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&maps.m[cls], buf, (int)p.co_off + c0, ow_w, oh_w, b);
+        bulk_commit_group();
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (lane == 0) bulk_wait_group<0>();
+}
+
+template <int BLOCK_N, bool STAGED>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
-                  const __grid_constant__ CUtensorMap tmap_b) {
+                  const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ OutMaps omaps) {
   using C = ConvCfg<BLOCK_N>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
@@ -109,6 +221,8 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
   float *epi_vec = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES + 256);  // 6 * BLOCK_N floats
+  unsigned char *o_buf = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(epi_vec + 6 * BLOCK_N) + 1023) & ~uintptr_t(1023));   // STAGED only
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -197,7 +311,10 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);
+    if constexpr (STAGED)
+      epilogue_role_staged<BLOCK_N>(p, omaps, epi_vec, o_buf, tmem_full, tmem_empty, tmem_base, warp, lane);
+    else
+      epilogue_role<BLOCK_N>(p, epi_vec, tmem_full, tmem_empty, tmem_base, warp, lane);
   }
 
   tcgen05_fence_before();
@@ -456,16 +573,17 @@ int launch_halo(ConvParams &p, const void *x, int64_t batch, int64_t in_h, int64
   return check_launch("conv_rowhalo_kernel");
 }
 
-template <int BLOCK_N>
-int launch_conv(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
-                cudaStream_t stream) {
+template <int BLOCK_N, bool STAGED>
+int launch_conv_impl(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
+                     cudaStream_t stream) {
   using C = ConvCfg<BLOCK_N>;
-  auto kern = conv_fprop_kernel<BLOCK_N>;
+  auto kern = conv_fprop_kernel<BLOCK_N, STAGED>;
+  constexpr int SMEM = STAGED ? C::SMEM_BYTES_STAGED : C::SMEM_BYTES;
   static bool attr_done[64] = {false};
   int dev = 0;
   VSP_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   CUtensorMap tb;
@@ -479,11 +597,38 @@ int launch_conv(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t co
                             CU_TENSOR_MAP_SWIZZLE_128B))
       return rc;
   }
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  if (STAGED) {
+    // one map per output parity class: base shifted to the class origin, pixel strides scaled by `os`
+    const int ncls = p.shuffle_cout ? 4 : 1;
+    const int os = p.os;
+    const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+    for (int cls = 0; cls < ncls; ++cls) {
+      const int oh0 = p.oo_h + (cls >> 1), ow0 = p.oo_w + (cls & 1);
+      const __nv_bfloat16 *base = static_cast<const __nv_bfloat16 *>(p.out) + ((long long)oh0 * p.full_w + ow0) * p.ldo;
+      uint64_t dims[4] = {(uint64_t)(p.co_off + creal), (uint64_t)((p.full_w - ow0 + os - 1) / os),
+                          (uint64_t)((p.full_h - oh0 + os - 1) / os), (uint64_t)p.batch};
+      uint64_t strides[4] = {0, (uint64_t)p.ldo * 2 * os, (uint64_t)p.ldo * p.full_w * 2 * os,
+                             (uint64_t)p.ldo * p.full_w * p.full_h * 2};
+      uint32_t box[4] = {(uint32_t)C::CHUNK, 32, 1, 1};
+      if (int rc = encode_tma(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, nullptr,
+                              C::CHUNK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
+        return rc;
+    }
+  }
   p.tiles_n = (p.cout + BLOCK_N - 1) / BLOCK_N;
   p.total_tiles = (long long)p.batch * p.tiles_h * p.tiles_w * p.tiles_n;
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kern<<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(p, ta, tb);
+  kern<<<(unsigned)grid, kNumThreads, SMEM, stream>>>(p, ta, tb, om);
   return check_launch("conv_fprop_kernel");
+}
+
+template <int BLOCK_N>
+int launch_conv(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
+                cudaStream_t stream) {
+  return p.staged ? launch_conv_impl<BLOCK_N, true>(p, ta, wq, cout_pad, taps_total, stream)
+                  : launch_conv_impl<BLOCK_N, false>(p, ta, wq, cout_pad, taps_total, stream);
 }
 
 inline int next_pow2(int v) {
@@ -500,7 +645,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
                        int ntaps, const int *tap_w, const int *tap_dy, const int *tap_dx, int stride,
                        int64_t out_h, int64_t out_w, void *out, int out_nhwc, int64_t full_h,
                        int64_t full_w, int os, int oo_h, int oo_w, int64_t ldo, int64_t co_off,
-                       const vsp_conv_epilogue *epi, cudaStream_t stream) {
+                       const vsp_conv_epilogue *epi, cudaStream_t stream, int shuffle_cout = 0) {
   VSP_REQUIRE(batch >= 1 && (groups == 1 || groups == batch), "conv: groups must be 1 or batch");
   VSP_REQUIRE(cin >= 8 && cin % 8 == 0, "conv: cin must be a multiple of 8 (pad NHWC channels), got %lld", (long long)cin);
   VSP_REQUIRE(cout >= 1 && cout_pad >= cout, "conv: bad cout");
@@ -526,6 +671,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   p.tiles_h = ((int)out_h + p.th - 1) / p.th;
   p.kc = ((int)cin + kBlockK - 1) / kBlockK;
   p.out = out; p.out_nhwc = out_nhwc;
+  p.shuffle_cout = shuffle_cout;
   p.full_h = (int)full_h; p.full_w = (int)full_w; p.os = os; p.oo_h = oo_h; p.oo_w = oo_w;
   p.ldo = ldo; p.co_off = co_off;
   if (epi) {
@@ -535,6 +681,18 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     p.noise_weight_dev = epi->noise_weight_dev; p.pre_bias = epi->pre_bias; p.pre_act = epi->pre_act;
     VSP_REQUIRE(p.pre_act == 0 || p.pre_act == 3, "conv: epilogue pre_act must be 0 or 3");
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
+  }
+
+  // staged epilogue (swizzled shared memory + TMA stores) for NHWC bf16 outputs whose warps cover one output row
+  {
+    static const bool no_staged = getenv("VSP_NO_STAGED") != nullptr;
+    const float al = p.alpha, sc = p.scale;
+    p.staged = (!no_staged && out_nhwc && (ldo % 8) == 0 && (co_off % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                p.tw >= 32 && al >= 0.f && al <= 1.f && (sc > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
+    if (shuffle_cout) {
+      VSP_REQUIRE(p.staged && os == 2 && oo_h == 0 && oo_w == 0 && shuffle_cout % 32 == 0 && cout == 4 * shuffle_cout,
+                  "conv: pixel-shuffle epilogue needs an NHWC bf16 output (ldo %% 8 == 0), width >= 32, Cout %% 32 == 0");
+    }
   }
 
   // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers
@@ -677,4 +835,21 @@ extern "C" int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void 
         return rc;
     }
   return 0;
+}
+
+extern "C" int vsp_conv2d_up2_fused_bf16(const void *x, const void *wq, void *out, int64_t batch, int64_t groups,
+                                         int64_t in_h, int64_t in_w, int64_t cin, int64_t cout, int64_t ldo,
+                                         int64_t co_off, const vsp_conv_epilogue *epi, void *stream_) {
+  using namespace vsp;
+  VSP_REQUIRE(cout >= 32 && cout % 32 == 0, "conv2d_up2_fused: Cout must be a multiple of 32");
+  int tw_[9], dy[9], dx[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      tw_[i * 3 + j] = i * 3 + j;
+      dy[i * 3 + j] = i - 1;
+      dx[i * 3 + j] = j - 1;
+    }
+  return conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, 4 * cout, 4 * cout, 9, 9, tw_, dy, dx, 1, in_h, in_w,
+                            out, 1, 2 * in_h, 2 * in_w, 2, 0, 0, ldo, co_off, epi, static_cast<cudaStream_t>(stream_),
+                            (int)cout);
 }

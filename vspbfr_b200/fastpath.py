@@ -13,6 +13,7 @@ No autograd here — use the module ``forward`` methods for training.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 from torch.nn import functional as F
@@ -24,6 +25,9 @@ from .op import modconv as mc
 from .op.upfirdn2d import upfirdn2d_raw
 
 _cache: dict = {}
+# ModulatedConv2d(upsample=True) layers with Cin up to this run as the fused up-convolution (4x the transposed
+# conv's FLOPs, but no (2H+1)^2 intermediate and no blur pass): a win wherever the layer is bandwidth-bound
+_UP_FUSED_MAX_CIN = int(os.environ.get("VSP_UP_FUSED_MAX_CIN", "256"))
 
 
 def _cached(owner, tag, tensors, build):
@@ -82,9 +86,19 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     s = _linear(conv.modulation, style)
     w4 = conv.weight.detach().view(cout, cin, k, k)
     wsq = _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(w4)) if conv.demodulate else None
-    wq, d = mc.pack_weights(w4, s, wscale=conv.scale, eps=conv.eps, want_demod=conv.demodulate, wsq=wsq)
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
                noise_weight_dev=m.noise.weight.detach())
+    if conv.upsample and k == 3 and cin <= _UP_FUSED_MAX_CIN and cout % 32 == 0 and w >= 32:
+        # transposed conv + blur as ONE dense conv with the composite weights and a pixel-shuffle epilogue
+        w3 = _cached(conv, "w_up2", [conv.weight, conv.blur.kernel], lambda: mc.compose_up2_weights(w4, conv.blur.kernel))
+        wq3, _ = mc.pack_weights(w3, s, wscale=conv.scale)
+        d = None
+        if conv.demodulate:
+            d = torch.rsqrt((conv.scale * conv.scale) * ((s * s) @ wsq.t()) + conv.eps)
+        nz = _noise_for(noise, b, 2 * h, 2 * w, x.device)
+        return mc.conv_up2_fused(x, wq3, cout, epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual,
+                                                                     residual2=residual2, **act))
+    wq, d = mc.pack_weights(w4, s, wscale=conv.scale, eps=conv.eps, want_demod=conv.demodulate, wsq=wsq)
     if conv.upsample:
         y = mc.conv_transpose_s2(x, wq, cout, k, k, epi=mc.make_epilogue(row_scale=d) if d is not None else None,
                                  out_nhwc=True)

@@ -262,6 +262,47 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
     return out
 
 
+def compose_up2_weights(weight, blur_kernel):
+    """Composite weights of `conv_transpose2d(stride=2, 3x3)` followed by `Blur(4x4, pad=(1,1))`
+    (models/RestoreNet.py:522-535), split into the four output-parity classes of the 6x6 stride-2 kernel.
+
+    weight [Cout, Cin, 3, 3] (ModulatedConv2d.weight[0]), blur_kernel [4, 4] (already x upsample_factor^2)
+    -> [4*Cout, Cin, 3, 3] with row (pa*2+pb)*Cout + o and tap (dy+1, dx+1) on the low-res grid:
+    out[2A+pa, 2B+pb] = sum_{dy,dx} x[A+dy, B+dx] * W6[pa - 2*dy + 2, pb - 2*dx + 2],  W6 = weight (*) blur (full conv).
+    """
+    cout, cin, kh, kw = weight.shape
+    assert kh == 3 and kw == 3 and tuple(blur_kernel.shape) == (4, 4)
+    w6 = torch.nn.functional.conv2d(weight.reshape(cout * cin, 1, 3, 3).double(),
+                                    torch.flip(blur_kernel, [0, 1]).reshape(1, 1, 4, 4).double(), padding=3)
+    w6 = w6.reshape(cout, cin, 6, 6)
+    out = torch.empty((4, cout, cin, 3, 3), dtype=torch.float64, device=weight.device)
+    for pa in range(2):
+        for pb in range(2):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    out[pa * 2 + pb, :, :, dy + 1, dx + 1] = w6[:, :, pa - 2 * dy + 2, pb - 2 * dx + 2]
+    return out.reshape(4 * cout, cin, 3, 3).float().contiguous()
+
+
+def conv_up2_fused(x_nhwc, wq, cout, epi=None, out=None, co_off=0):
+    """Fused transposed-conv + blur (see vsp_conv2d_up2_fused_bf16): x [B,H,W,Cin] -> [B,2H,2W,ldo] NHWC bf16."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps, rows, k_pad = wq.shape
+    assert taps == 9 and k_pad == cin and rows == 4 * cout, (wq.shape, cout)
+    if out is None:
+        out = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    e, keep = epi if epi is not None else (None, None)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _prof("conv_up2_fused", 2.0 * b * h * w * 4 * cout * cin * 9,
+                   lambda: _lib.load().vsp_conv2d_up2_fused_bf16(
+                       ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, out.shape[3], co_off,
+                       ctypes.byref(e) if e is not None else None, stream_ptr()),
+                   detail=f"b{b} {cin}->{cout} up2-fused {h}x{w} g{g}",
+                   nbytes=2.0 * b * (h * w * cin + 4 * h * w * cout))
+    _lib.check(rc, "conv2d_up2_fused_bf16")
+    return out
+
+
 def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
     """gw[g,t,o,i] = sum_p dy[b,p,o] x[b, p*stride + t*dil - pad, i] (tap-major); groups == batch or 1.
     dy_nhwc [B,OH,OW,Cout_pad] bf16, x_nhwc [B,H,W,Cin_pad] bf16 -> [groups, kh*kw, Cout_pad, Cin_pad] fp32."""
