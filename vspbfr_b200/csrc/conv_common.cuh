@@ -8,7 +8,7 @@ namespace vsp {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;              // bf16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumThreads = 192;         // 6 warps
+constexpr int kNumThreads = 320;         // 10 warps: TMA producer, MMA issuer, 8 epilogue (two per TMEM lane quadrant)
 constexpr int kMaxTaps = 16;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 

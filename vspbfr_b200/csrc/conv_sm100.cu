@@ -30,13 +30,15 @@ template <int BLOCK_N>
 struct ConvCfg {
   static constexpr int B_BYTES = BLOCK_N * kBlockK * 2;
   static constexpr int STAGE_BYTES = kABytes + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 5 : (BLOCK_N >= 64 ? 7 : 8));
   static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   static constexpr int CHUNK = BLOCK_N < 32 ? BLOCK_N : 32;
   static constexpr int SBUF_BYTES = 32 * CHUNK * 2;          // staged epilogue: 32 pixels x CHUNK channels bf16
-  static constexpr int OSTAGE_BYTES = 4 * 2 * SBUF_BYTES;     // two buffers per epilogue warp
+  static constexpr int NBUF = BLOCK_N >= 256 ? 1 : 2;         // staging buffers per epilogue warp (smem budget)
+  static constexpr int OSTAGE_BYTES = 8 * NBUF * SBUF_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6 * BLOCK_N * 4 /*epilogue vectors*/;
   static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + OSTAGE_BYTES + 1024;
+  static_assert(SMEM_BYTES_STAGED <= 232448, "conv_fprop_kernel exceeds shared memory");
 };
 
 // Epilogue role (warps 2..5 of either kernel): TMEM -> registers -> fused epilogue -> global.
@@ -49,8 +51,9 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
   // hides behind the MMAs) and then read back as 128-bit broadcasts; accumulators leave TMEM
   // 32 columns at a time.
   const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+  const int wg = (warp - 2) >> 2;         // the two warps of a quadrant alternate accumulator chunks
   const int row = quad * 32 + lane;       // pixel row inside the tile
-  const int et = threadIdx.x - 64;        // 0..127 among the epilogue threads
+  const int et = threadIdx.x - 64;        // 0..255 among the epilogue threads
   float *vec_rs = epi_vec;                // [2][BLOCK_N] demod
   float *vec_b1 = epi_vec + 2 * BLOCK_N;  // [2][BLOCK_N] pre-activation bias (stage 1)
   float *vec_b2 = epi_vec + 4 * BLOCK_N;  // [2][BLOCK_N] bias (stage 2)
@@ -72,7 +75,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
     const int nbase = n_i * BLOCK_N;
 
     // stage the channel vectors of this tile
-    for (int c = et; c < BLOCK_N; c += 128) {
+    for (int c = et; c < BLOCK_N; c += 256) {
       const int n = nbase + c;
       const bool ok = n < p.cout;
       vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.cout + n) : 1.f;
@@ -81,13 +84,13 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
     }
     float nz = 0.f;
     if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 
     mbar_wait(&tmem_full[acc], acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-    for (int ch = 0; ch < BLOCK_N / C::CHUNK; ++ch)
+    for (int ch = wg; ch < BLOCK_N / C::CHUNK; ch += 2)
       epi_chunk<C::CHUNK>(p, taddr + ch * C::CHUNK, nbase + ch * C::CHUNK, b, pix, plane, pix_ok, nz,
                           vec_rs + acc * BLOCK_N + ch * C::CHUNK, vec_b1 + acc * BLOCK_N + ch * C::CHUNK,
                           vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
@@ -110,6 +113,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   constexpr int CHUNK = C::CHUNK;
   constexpr int ROW_BYTES = CHUNK * 2;
   const int quad = warp & 3;
+  const int wg = (warp - 2) >> 2;         // the two warps of a quadrant alternate accumulator chunks
   const int row = quad * 32 + lane;
   const int et = threadIdx.x - 64;
   float *vec_rs = epi_vec, *vec_b1 = epi_vec + 2 * BLOCK_N, *vec_b2 = epi_vec + 4 * BLOCK_N;
@@ -117,7 +121,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
   const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
   const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
-  unsigned char *stage = o_buf + quad * 2 * C::SBUF_BYTES;
+  unsigned char *stage = o_buf + (warp - 2) * C::NBUF * C::SBUF_BYTES;
   const long long plane = (long long)p.full_h * p.full_w;
   const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
   const __nv_bfloat16 *res1 = static_cast<const __nv_bfloat16 *>(p.residual);
@@ -135,7 +139,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
     const bool pix_ok = oh < p.out_h && ow < p.out_w;
     const int oh_w = h_i * p.th + (quad * 32) / p.tw, ow_w = w_i * p.tw + (quad * 32) % p.tw;   // warp's first pixel
     const int nbase = n_i * BLOCK_N;
-    for (int c = et; c < BLOCK_N; c += 128) {
+    for (int c = et; c < BLOCK_N; c += 256) {
       const int n = nbase + c;
       const int cr = p.shuffle_cout ? n % p.shuffle_cout : n;
       const bool ok = n < p.cout;
@@ -143,17 +147,60 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
       vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f;
       vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + cr) : 0.f;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue warps only
+    // noise of this thread's pixel in every output class of the tile, fetched before the accumulator wait
+    float nzc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.noise != nullptr && pix_ok) {
+      const float *nb = p.noise + b * p.noise_bstride;
+      if (p.shuffle_cout) {
+        const int c_lo = nbase / p.shuffle_cout, c_hi = min(3, (nbase + BLOCK_N - 1) / p.shuffle_cout);
+#pragma unroll
+        for (int cls = 0; cls < 4; ++cls)
+          if (cls >= c_lo && cls <= c_hi)
+            nzc[cls] = nw * __ldg(nb + (long long)(oh * 2 + (cls >> 1)) * p.full_w + ow * 2 + (cls & 1));
+      } else {
+        nzc[0] = nw * __ldg(nb + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
+
+    constexpr int NCH = BLOCK_N / CHUNK;
+    constexpr int PIECES = CHUNK / 8;                 // 16-byte pieces per pixel of a chunk
+    constexpr int PPR = 32 / PIECES;                  // pixels covered by one warp-wide 128-bit request
+    const bool has_res = res1 != nullptr || res2 != nullptr;
+    // residuals: warp-cooperative loads (lane -> piece lane % PIECES of pixel lane / PIECES: whole sectors per
+    // request), prefetched one chunk ahead and transposed to pixel-per-lane through the staging buffer
+    uint4 pr1[PIECES], pr2[PIECES];
+    auto load_res = [&](int ch) {
+      const int n0 = nbase + ch * CHUNK;
+      const int cls = p.shuffle_cout ? n0 / p.shuffle_cout : 0;
+      const int c0 = p.shuffle_cout ? n0 % p.shuffle_cout : n0;
+      const int fh = oh_w * p.os + p.oo_h + (cls >> 1);
+#pragma unroll
+      for (int i = 0; i < PIECES; ++i) {
+        const int px = i * PPR + lane / PIECES;
+        const int fw = (ow_w + px) * p.os + p.oo_w + (cls & 1);
+        const bool ok = n0 < p.cout && oh_w < p.out_h && ow_w + px < p.out_w;
+        const long long off = (((long long)b * p.full_h + fh) * p.full_w + fw) * p.ldo + p.co_off + c0 + (lane % PIECES) * 8;
+        pr1[i] = (res1 && ok) ? __ldg(reinterpret_cast<const uint4 *>(res1 + off)) : make_uint4(0u, 0u, 0u, 0u);
+        pr2[i] = (res2 && ok) ? __ldg(reinterpret_cast<const uint4 *>(res2 + off)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    if (has_res && wg < NCH) load_res(wg);
 
     mbar_wait(&tmem_full[acc], acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-    constexpr int NCH = BLOCK_N / CHUNK;
+    if (wg >= NCH) {                 // single-chunk tiles: the second warp of the quadrant has nothing to read
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
 #pragma unroll 1
-    for (int ch = 0; ch < NCH; ++ch) {
+    for (int ch = wg; ch < NCH; ch += 2) {
       const int n0 = nbase + ch * CHUNK;
+      const bool last_ch = ch + 2 >= NCH;
       if (n0 >= p.cout) {            // warp-uniform: nothing to write for the padded tail of the channel tile
-        if (ch == NCH - 1) {
+        if (last_ch) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -162,37 +209,54 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
       }
       const int cls = p.shuffle_cout ? n0 / p.shuffle_cout : 0;
       const int c0 = p.shuffle_cout ? n0 % p.shuffle_cout : n0;
-      const int fh = oh * p.os + p.oo_h + (cls >> 1), fw = ow * p.os + p.oo_w + (cls & 1);
-      const long long pix = (long long)fh * p.full_w + fw;
-      float nz = 0.f;
-      if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
-      uint4 rs1[CHUNK / 8], rs2[CHUNK / 8];
-      const long long roff = ((long long)b * plane + pix) * p.ldo + p.co_off + c0;
+      float nz = nzc[0];
 #pragma unroll
-      for (int i = 0; i < CHUNK / 8; ++i) {
-        rs1[i] = (res1 && pix_ok) ? __ldg(reinterpret_cast<const uint4 *>(res1 + roff) + i) : make_uint4(0u, 0u, 0u, 0u);
-        rs2[i] = (res2 && pix_ok) ? __ldg(reinterpret_cast<const uint4 *>(res2 + roff) + i) : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int q = 1; q < 4; ++q) nz = cls == q ? nzc[q] : nz;
       uint32_t r[CHUNK];
       if constexpr (CHUNK == 32) tmem_ld_32x32b_x32(taddr + ch * CHUNK, r);
       else tmem_ld_32x32b_x16(taddr + ch * CHUNK, reinterpret_cast<uint32_t(&)[16]>(r));
       tmem_ld_wait();
-      if (ch == NCH - 1) {           // accumulators are in registers: the MMA warp may reuse this stage
+      if (last_ch) {                 // accumulators are in registers: the MMA warp may reuse this stage
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       }
-      unsigned char *buf = stage + (sbuf & 1) * C::SBUF_BYTES;
+      unsigned char *buf = stage + (C::NBUF == 2 ? (sbuf & 1) : 0) * C::SBUF_BYTES;
       ++sbuf;
-      if (lane == 0) bulk_wait_group_read<1>();
+      if (lane == 0) bulk_wait_group_read<C::NBUF - 1>();
       __syncwarp();
+      uint4 own1[PIECES], own2[PIECES];
+      if (has_res) {
+        // transpose the prefetched pieces: [pixel][piece] in the (swizzled) staging tile, then read the own row
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+          const int px = i * PPR + lane / PIECES;
+          const int swp = ROW_BYTES == 64 ? ((px >> 1) & 3) : ((px >> 2) & 1);
+          *reinterpret_cast<uint4 *>(buf + px * ROW_BYTES + (((lane % PIECES) ^ swp) << 4)) = pr1[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) own1[i] = *reinterpret_cast<const uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+          const int px = i * PPR + lane / PIECES;
+          const int swp = ROW_BYTES == 64 ? ((px >> 1) & 3) : ((px >> 2) & 1);
+          *reinterpret_cast<uint4 *>(buf + px * ROW_BYTES + (((lane % PIECES) ^ swp) << 4)) = pr2[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) own2[i] = *reinterpret_cast<const uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4));
+        __syncwarp();
+        if (ch + 2 < NCH) load_res(ch + 2);
+      }
       const float *vrs = vec_rs + acc * BLOCK_N + ch * CHUNK, *vb1 = vec_b1 + acc * BLOCK_N + ch * CHUNK,
                   *vb2 = vec_b2 + acc * BLOCK_N + ch * CHUNK;
 #pragma unroll
-      for (int i = 0; i < CHUNK / 8; ++i) {
+      for (int i = 0; i < PIECES; ++i) {
         float v[8];
         epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz, m1, m1a, m2, m2a, v);
-        if (res1 || res2) add2_bf16x8(v, rs1[i], rs2[i]);
+        if (has_res) add2_bf16x8(v, own1[i], own2[i]);
         *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
       }
       fence_proxy_async();
@@ -236,7 +300,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -377,7 +441,7 @@ conv_rowhalo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     for (int i = 0; i < 9; ++i) {
       mbar_init(&b_full[i], 1);
