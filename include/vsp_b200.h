@@ -147,6 +147,24 @@ int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void
 /* wsq[o,i] = sum_t w[o,i,t]^2 (style-independent part of the demodulation sum). */
 int vsp_weight_sumsq_f32(const float *w, float *wsq, int64_t cout, int64_t cin, int taps, void *stream);
 
+/*
+ * Grouped EqualLinear (models/RestoreNet.py:142-176 without activation): every modulation linear of a network
+ * pass in one launch.  Problem j:  y[y_off_j + b*out_dim_j + o] = wscale_j * sum_i w_j[o,i] * x[x_off_j + b*x_bstride + i]
+ *                                                               + bscale_j * bias_j[o]
+ * `descs_dev` / `row_start_dev` live in device memory; row_start[j] = sum of out_dim of problems < j.
+ * w_j must be 16-byte aligned when in_dim % 4 == 0, and x_off_j a multiple of 4 floats.
+ */
+typedef struct vsp_linear_desc {
+  const float *w;     /* [out_dim, in_dim] row-major */
+  const float *bias;  /* [out_dim] or NULL */
+  int64_t x_off;      /* element offset of this problem's style row inside sample 0 of x */
+  int64_t y_off;      /* element offset of this problem's [batch, out_dim] block in y */
+  int32_t in_dim, out_dim;
+  float wscale, bscale;
+} vsp_linear_desc;
+int vsp_grouped_linear_f32(const vsp_linear_desc *descs_dev, const int *row_start_dev, int n_problems,
+                           int total_rows, const float *x, int64_t x_bstride, float *y, int batch, void *stream);
+
 /* ---- tcgen05 implicit-GEMM convolution --------------------------------- */
 
 /* Epilogue description shared by the conv entry points. All pointers optional.

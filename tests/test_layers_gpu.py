@@ -166,3 +166,20 @@ def test_network_backward_runs_and_touches_every_parameter():
     missing = [n for n, p in net.named_parameters() if p.grad is None]
     assert not missing, missing
     assert all(torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+def test_grouped_linear_matches_equal_linear():
+    """ModulationBank (one grouped launch) == the per-layer EqualLinear forwards (models/RestoreNet.py:142-176)."""
+    torch.manual_seed(5)
+    lins = [L.EqualLinear(512, 64, bias_init=1), L.EqualLinear(512, 512, bias_init=1, lr_mul=0.5),
+            L.EqualLinear(512, 3, bias_init=1), L.EqualLinear(512, 130)]
+    lins = [m.to(DEV) for m in lins]
+    for m in lins:
+        m.bias.data.normal_()
+    for batch in (1, 3, 8, 11):
+        styles = torch.randn(batch, 6, 512, device=DEV)
+        bank = fp.ModulationBank([(m, idx) for m, idx in zip(lins, (0, 5, 2, 2))])
+        got = bank(styles)
+        for m, idx in zip(lins, (0, 5, 2, 2)):
+            want = m(styles[:, idx])
+            np.testing.assert_allclose(got[id(m)].cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-5)

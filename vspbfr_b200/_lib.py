@@ -30,6 +30,7 @@ SOURCES = [
     "conv_ring_sm100.cu",
     "wgrad_sm100.cu",
     "torgb_sm100.cu",
+    "linear_sm100.cu",
 ]
 
 NVCC_FLAGS = [
@@ -118,6 +119,21 @@ class ConvEpilogue(Structure):
     ]
 
 
+class LinearDesc(Structure):
+    """Mirror of ``vsp_linear_desc`` (include/vsp_b200.h)."""
+
+    _fields_ = [
+        ("w", c_void_p),
+        ("bias", c_void_p),
+        ("x_off", c_int64),
+        ("y_off", c_int64),
+        ("in_dim", ctypes.c_int32),
+        ("out_dim", ctypes.c_int32),
+        ("wscale", c_float),
+        ("bscale", c_float),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/vsp_b200.h declares.
 SIGNATURES = {
     "vsp_version": (c_int, []),
@@ -154,6 +170,7 @@ SIGNATURES = {
     "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_grouped_linear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "vsp_conv2d_up2_fused_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                           c_int64, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
     "vsp_torgb_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

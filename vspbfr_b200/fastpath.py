@@ -45,6 +45,8 @@ def _cached(owner, tag, tensors, build):
 
 def clear_cache():
     _cache.clear()
+    _bank_cache.clear()
+    _mod_ctx.clear()
 
 
 def _linear(lin, x):
@@ -52,6 +54,74 @@ def _linear(lin, x):
     w = _cached(lin, "w_scaled", [lin.weight], lambda: (lin.weight.detach() * lin.scale).contiguous())
     b = _cached(lin, "b_scaled", [lin.bias], lambda: (lin.bias.detach() * lin.lr_mul).contiguous())
     return F.linear(x, w, b)
+
+
+class ModulationBank:
+    """All style-modulation linears of one network pass as a single grouped launch (vsp_grouped_linear_f32).
+
+    ``entries`` = [(EqualLinear, style_index)]: problem j reads style row ``styles[:, style_index_j]`` of a
+    [B, n, D] style tensor and yields s_j [B, out_dim_j].  The descriptor table is built once and cached on the
+    device while the parameters stay in place."""
+
+    def __init__(self, entries):
+        self.entries = list(entries)
+        self._key = None
+        self._descs = self._rows = None
+        self._offs = []
+        self._total = 0
+
+    def _build(self, device, d_style, batch):
+        key = tuple((lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+                    for lin, _ in self.entries) + (d_style, batch, str(device))
+        if key == self._key:
+            return
+        descs = (_lib.LinearDesc * len(self.entries))()
+        rows, offs, y_off, r = [], [], 0, 0
+        for j, (lin, idx) in enumerate(self.entries):
+            out_dim, in_dim = lin.weight.shape
+            assert in_dim == d_style and lin.weight.is_contiguous() and lin.weight.dtype == torch.float32
+            dsc = descs[j]
+            dsc.w, dsc.bias = lin.weight.data_ptr(), lin.bias.data_ptr()
+            dsc.x_off, dsc.y_off = idx * d_style, y_off
+            dsc.in_dim, dsc.out_dim = in_dim, out_dim
+            dsc.wscale, dsc.bscale = lin.scale, lin.lr_mul
+            rows.append(r)
+            offs.append((y_off, out_dim))
+            r += out_dim
+            y_off += batch * out_dim
+        raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+        self._descs = raw.to(device)
+        self._rows = torch.tensor(rows, dtype=torch.int32, device=device)
+        self._offs, self._total, self._rows_total, self._key = offs, y_off, r, key
+
+    def __call__(self, styles):
+        """styles [B, n, D] fp32 contiguous -> {id(lin): s [B, out_dim]}"""
+        b, n, d = styles.shape
+        styles = styles.contiguous().float()
+        self._build(styles.device, d, b)
+        y = torch.empty(self._total, dtype=torch.float32, device=styles.device)
+        with torch.cuda.device(styles.device):
+            rc = _lib.load().vsp_grouped_linear_f32(ptr(self._descs), ptr(self._rows), len(self.entries), self._rows_total,
+                                                    ptr(styles), n * d, ptr(y), b, stream_ptr())
+        _lib.check(rc, "grouped_linear_f32")
+        return {id(lin): y[o:o + b * od].view(b, od) for (lin, _), (o, od) in zip(self.entries, self._offs)}
+
+
+_mod_ctx: dict = {}
+_bank_cache: dict = {}
+
+
+def _banks_for(owner, build):
+    hit = _bank_cache.get(id(owner))
+    if hit is None:
+        hit = _bank_cache[id(owner)] = build()
+    return hit
+
+
+def _modulation(lin, style):
+    """s = modulation(style): from the pass's ModulationBank when one is active, else a plain linear."""
+    hit = _mod_ctx.get(id(lin))
+    return hit if hit is not None else _linear(lin, style)
 
 
 def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
@@ -71,10 +141,34 @@ def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
     return y
 
 
+class _NoisePool:
+    """N(0,1) noise images of a whole pass from ONE generator launch: layers take consecutive slices of a pool
+    sized by the previous pass (shapes are static during inference)."""
+
+    def __init__(self):
+        self.buf, self.off, self.used, self.want = None, 0, 0, 0
+
+    def begin(self, device):
+        self.want = max(self.want, self.used)
+        self.used = self.off = 0
+        self.buf = torch.randn(self.want, device=device, dtype=torch.float32) if self.want else None
+
+    def take(self, n, device):
+        self.used += n
+        if self.buf is None or self.off + n > self.buf.numel() or self.buf.device != device:
+            return torch.randn(n, device=device, dtype=torch.float32)
+        out = self.buf[self.off:self.off + n]
+        self.off += n
+        return out
+
+
+_noise_pool = _NoisePool()
+
+
 def _noise_for(noise, b, h, w, device):
     """``NoiseInjection`` draws N(0,1) per call when no noise is given (models/RestoreNet.py:564-569)."""
     if noise is None:
-        return torch.randn(b, 1, h, w, device=device, dtype=torch.float32)
+        return _noise_pool.take(b * h * w, device).view(b, 1, h, w)
     return noise.contiguous().float()
 
 
@@ -83,7 +177,7 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     conv = m.conv
     b, h, w, _ = x.shape
     cout, cin, k = conv.out_channel, conv.in_channel, conv.kernel_size
-    s = _linear(conv.modulation, style)
+    s = _modulation(conv.modulation, style)
     w4 = conv.weight.detach().view(cout, cin, k, k)
     wsq = _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(w4)) if conv.demodulate else None
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
@@ -128,7 +222,7 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     cq = branches[0].out_channel
     cout = cq * len(branches)
     k = branches[0].kernel_size
-    s = _linear(m.modulation, style)
+    s = _modulation(m.modulation, style)
     wcat = _cached(m, "wcat", [br.weight for br in branches],
                    lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
     wsq = _cached(m, "wsq", [br.weight for br in branches], lambda: mc.weight_sumsq(wcat)) if branches[0].demodulate else None
@@ -190,7 +284,7 @@ def to_rgb(m: ToRGB, x, style, skip=None):
     to the weights in shared memory (no weight prologue launch)."""
     conv = m.conv
     b, h, w, c = x.shape
-    s = _linear(conv.modulation, style)
+    s = _modulation(conv.modulation, style)
     res = None
     if skip is not None:
         f = m.upsample.factor
@@ -249,9 +343,16 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     lat_rev = torch.flip(latent, dims=[1])
     noise_rev = noise[::-1]
 
+    enc = net.encoder_convs
+    banks = _banks_for(net, lambda: (
+        ModulationBank([(enc[ii + j].modulation if j == 0 else enc[ii + j].conv.modulation, ii)
+                        for ii in range(0, len(enc), 2) for j in (0, 1)]),
+        ModulationBank([(net.conv1.modulation, 0), (net.to_rgb1.conv.modulation, 1)] +
+                       [(m, 1 + 2 * q + j) for q, (up, smart, rgb) in enumerate(zip(net.convs[::2], net.convs[1::2], net.to_rgbs))
+                        for j, m in enumerate((up.conv.modulation, smart.modulation, rgb.conv.modulation))])))
+    _mod_ctx.update(banks[0](lat_rev))
     out = large_conv_layer(net.down_from_big, mc.nchw_to_nhwc_bf16(images, c_pad=8))
     features = []
-    enc = net.encoder_convs
     for ii in range(0, len(enc), 2):
         out = smart_layer(enc[ii], out, lat_rev[:, ii], noise_rev[ii])
         features.append(out)
@@ -263,8 +364,12 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     features.append((out.float() + early).to(torch.bfloat16).contiguous())
     features = features[::-1]
 
+    n_sty = 2 * len(net.to_rgbs) + 2
+    stys = torch.cat([latent[:, :n_sty], x_global[:, None, :].expand(-1, n_sty, -1)], dim=2)   # [B, n, 2048]
+    _mod_ctx.update(banks[1](stys))
+
     def sty(i):
-        return torch.cat([latent[:, i], x_global], dim=1)
+        return stys[:, i]
 
     out = smart_layer(net.conv1, features[0], sty(0), noise[0])
     skip = to_rgb(net.to_rgb1, out, sty(1))
@@ -275,6 +380,7 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
         out = smart_layer(smart, out, sty(i + 1), n_smart)
         skip = to_rgb(rgb, out, sty(i + 2), skip)
         i += 2
+    _mod_ctx.clear()
     return skip
 
 
@@ -289,6 +395,11 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
     if noise is None:
         noise = ([None] * gen.num_layers if randomize_noise
                  else [getattr(gen.noises, f"noise_{i}") for i in range(gen.num_layers)])
+    bank = _banks_for(gen, lambda: (ModulationBank(
+        [(gen.conv1.conv.modulation, 0), (gen.to_rgb1.conv.modulation, 1)] +
+        [(m.conv.modulation, 1 + 2 * q + j) for q, trio in enumerate(zip(gen.convs[::2], gen.convs[1::2], gen.to_rgbs))
+         for j, m in enumerate(trio)]),))[0]
+    _mod_ctx.update(bank(latent))
     const = _cached(gen.input, "nhwc", [gen.input.input], lambda: mc.nchw_to_nhwc_bf16(gen.input.input.detach()))
     out = styled_conv(gen.conv1, const.expand(b, -1, -1, -1).contiguous(), latent[:, 0], noise[0])
     skip = to_rgb(gen.to_rgb1, out, latent[:, 1])
@@ -301,6 +412,7 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
         out = styled_conv(conv, out, latent[:, i + 1], n_conv)
         skip = to_rgb(rgb, out, latent[:, i + 2], skip)
         i += 2
+    _mod_ctx.clear()
     if return_features and features_nchw:
         feats = [mc.nhwc_bf16_to_nchw(f) for f in feats]
     return skip, (feats if return_features else None)
@@ -312,6 +424,7 @@ def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent
     the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512)."""
     if noise_styles is None:
         noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
+    _noise_pool.begin(low_imgs.device)
     image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True)
     feats = feats[:out_n_latent]
     restored = restoration_forward(net, low_imgs, feats, codes, noise_styles)
