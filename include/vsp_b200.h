@@ -119,6 +119,11 @@ int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y,
 int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
                               int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
 
+/* y[b,p,c] = bf16(x[b,p,c] * s[b,c]) on an NHWC bf16 activation [batch, hw, c] (c % 8 == 0, s [batch, c] fp32):
+ * the input-modulated form of ModulatedConv2d (models/RestoreNet.py:481-508, `fused=False`), used where the
+ * activation is smaller than the per-sample weights so the convolution can run on shared, cached weights. */
+int vsp_scale_nhwc_bf16(const void *x, const float *s, void *y, int64_t batch, int64_t hw, int64_t c, void *stream);
+
 /* NCHW fp32 -> NCHW bf16, optionally scaled per (n, c) plane. */
 int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y,
                          int64_t planes, int64_t hw, void *stream);
@@ -257,6 +262,18 @@ int vsp_conv2d_up2_fused_bf16(const void *x, const void *wq, void *out,
                               int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
                               int64_t cin, int64_t cout, int64_t ldo, int64_t co_off,
                               const vsp_conv_epilogue *epi, void *stream);
+
+/*
+ * The four dilated branches of a SMART_layer (models/RestoreNet.py:196-209,229-233: Dilated_ModulatedConv2d x4 ->
+ * torch.cat) as ONE launch: branch j is a 3x3 stride-1 convolution with dilation = padding = dils[j] producing
+ * channels [j*cout/n, (j+1)*cout/n) of the output (channel tile = branch; no torch.cat, one wave of tiles).
+ *   wq [groups, 9, cout, cin]: the branches' weights concatenated along the output-channel axis.
+ */
+int vsp_conv2d_branches_bf16(const void *x, const void *wq, void *out,
+                             int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                             int64_t cin, int64_t cout, int n_branches, const int *dils,
+                             int out_nhwc_bf16, int64_t ldo, int64_t co_off,
+                             const vsp_conv_epilogue *epi, void *stream);
 
 /*
  * ToRGB (models/RestoreNet.py:647-666): 1x1 modulated convolution to 3 channels, no demodulation,

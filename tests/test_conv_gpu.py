@@ -525,3 +525,67 @@ def test_up2_fused_matches_transposed_conv_then_blur(b, cin, cout, h, w_, per_sa
     # composite weights are rounded to bf16 once (instead of the 3x3 weights): compare at the bf16 tolerance
     assert_close_tight(got, want, tol=2e-2)
     assert psnr(got, want) > 45.0
+
+
+@pytest.mark.parametrize("b,cin,cq,h,w_", [(8, 512, 128, 4, 4), (3, 512, 128, 8, 8), (2, 128, 32, 16, 16), (2, 64, 16, 32, 32),
+                                           (2, 256, 64, 64, 64), (5, 64, 64, 4, 8)])
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_conv_branches_one_launch(b, cin, cq, h, w_, per_sample):
+    """Four dilated branches (SMART_layer) as one launch == four separate dilated convs written to channel slices;
+    shared weights stack several small samples into one 128-row tile, with the per-sample demod in the epilogue."""
+    g = torch.Generator(device="cpu").manual_seed(cin + cq + h)
+    dils = (1, 2, 4, 8)
+    x = torch.randn(b, cin, h, w_, generator=g).to(DEV)
+    wt = (torch.randn(4 * cq, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+    rs = (torch.rand(b, 4 * cq, generator=g) + 0.5).to(DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    if per_sample:
+        s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
+        wq, _ = mc.pack_weights(wt, s)
+    else:
+        wq, _ = mc.pack_weights(wt)
+    out = mc.conv_branches(xq, wq, 4 * cq, dils, epi=mc.make_epilogue(row_scale=rs))
+    for j, dil in enumerate(dils):
+        wj = wt[j * cq:(j + 1) * cq]
+        if per_sample:
+            want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wj * s[i][None, :, None, None]), None, 1, dil, dil)
+                              for i in range(b)])
+        else:
+            want = F.conv2d(bf16r(x), bf16r(wj), None, 1, dil, dil)
+        want = want * rs[:, j * cq:(j + 1) * cq, None, None]
+        assert_close_tight(out[..., j * cq:(j + 1) * cq].permute(0, 3, 1, 2).float(), want, tol=1e-2)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,w_", [(8, 512, 512, 4, 4), (3, 128, 64, 8, 8), (2, 64, 32, 16, 16), (5, 64, 32, 4, 8)])
+def test_up2_fused_lowres_shared_weights(b, cin, cout, h, w_):
+    """Fused up-conv below 32 pixels wide: stacked tiles + pixel-shuffle through the direct epilogue, input-modulated
+    (x * s with shared weights) == per-sample weights."""
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + h)
+    x = torch.randn(b, cin, h, w_, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+    k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+    k4 = (torch.outer(k1, k1) / 64 * 4).to(DEV)
+    s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
+    noise = torch.randn(b, 1, 2 * h, 2 * w_, generator=g).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    wsq = mc.weight_sumsq(wt)
+    d = mc.demod_from_wsq(s, wsq, 1.0)
+    d_ref = torch.rsqrt(((wt[None] * s[:, None, :, None, None]) ** 2).sum(dim=(2, 3, 4)) + 1e-8)
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref.cpu().numpy(), rtol=1e-4)
+    w3 = mc.compose_up2_weights(wt, k4)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    xs = mc.scale_nhwc(xq, s)
+    np.testing.assert_allclose(xs.float().cpu().numpy(), (xq.float() * s[:, None, None, :]).to(torch.bfloat16).float().cpu().numpy())
+    wq, _ = mc.pack_weights(w3)
+    epi = mc.make_epilogue(row_scale=d, noise=noise, noise_weight=0.3, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2))
+    out = mc.conv_up2_fused(xs, wq, cout, epi=epi)
+    z = F.pixel_shuffle(F.conv2d(xs.permute(0, 3, 1, 2).float(), bf16r(w3), None, 1, 1)
+                        .view(b, 4, cout, h, w_).transpose(1, 2).reshape(b, cout * 4, h, w_), 2)
+    want = F.leaky_relu(z * d[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    assert_close_tight(out.permute(0, 3, 1, 2).float(), want, tol=1e-2)
+    # and against the reference formulation (per-sample transposed conv -> blur -> demod)
+    from oracle import upfirdn2d_ref
+    y = torch.cat([F.conv_transpose2d(x[i:i + 1], (wt * s[i][None, :, None, None]).transpose(0, 1), stride=2) for i in range(b)])
+    yb = torch.from_numpy(upfirdn2d_ref(y.cpu().numpy(), k4.cpu().numpy(), 1, 1, (1, 1))).to(DEV)
+    ref = F.leaky_relu(yb * d_ref[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
+    assert psnr(out.permute(0, 3, 1, 2).float(), ref) > 45.0

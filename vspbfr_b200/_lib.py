@@ -170,6 +170,9 @@ SIGNATURES = {
     "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_scale_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "vsp_conv2d_branches_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                         c_int, POINTER(c_int), c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
     "vsp_grouped_linear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "vsp_conv2d_up2_fused_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                           c_int64, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),

@@ -20,6 +20,9 @@ struct ConvParams {
   int ntaps;
   int tap_w[kMaxTaps], tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int tw, th, tiles_w, tiles_h, tiles_n;
+  int tb, tiles_b;         // samples stacked in one 128-row tile (shared weights, images smaller than 128 pixels)
+  int branch_mode;         // channel tile n_i is branch n_i of a SMART layer: tap offsets scaled by n_dil[n_i]
+  int n_dil[4];
   long long total_tiles;
   int kc;                  // channel blocks per tap = ceil(cin / 64)
   int halo_d, halo_w;      // row-halo / row-ring kernels: dilation and padded halo row length (pixels)
@@ -67,33 +70,36 @@ __device__ __forceinline__ float epi_act(float v, int act, float alpha, float sc
   return v;
 }
 
-// Fused epilogue arithmetic of CHUNK accumulator columns (output channels n0 .. n0+CHUNK-1) of one pixel:
-// TMEM -> registers -> demod, [bias1 + lrelu], noise + bias + lrelu, residuals.  Results in v[] (zeros when the
-// pixel / chunk is outside the output).  `vrs`/`vb1`/`vb2` point at this chunk's slice of the per-channel
-// vectors staged in shared memory.  The tcgen05.ld is executed unconditionally (warp-collective).
+// Fused epilogue arithmetic of CHUNK accumulator columns of one pixel: TMEM -> registers -> demod, [bias1 + lrelu],
+// noise + bias + lrelu, residuals.  The chunk covers output channels c0 .. c0+CHUNK-1 of a tensor with `ctot`
+// channels (c0 differs from the GEMM column in the pixel-shuffle mapping); results in v[] (zeros outside the output).
+// `vrs`/`vb1`/`vb2` point at this chunk's slice of the per-channel vectors staged in shared memory; `rs_row`
+// (optional, global) replaces vrs with per-thread demod values when the tile stacks several samples.
+// The tcgen05.ld is executed unconditionally (warp-collective).
 template <int CHUNK>
-__device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
+__device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr, int c0, int ctot, int b, long long pix,
                                             long long plane, bool pix_ok, float nz, const float *vrs,
-                                            const float *vb1, const float *vb2, float (&v)[CHUNK]) {
-  const bool live = pix_ok && n0 < p.cout;
-  const bool fullc = n0 + CHUNK <= p.cout;
+                                            const float *vb1, const float *vb2, const float *rs_row,
+                                            float (&v)[CHUNK]) {
+  const bool live = pix_ok && c0 < ctot;
+  const bool fullc = c0 + CHUNK <= ctot;
   // residual prefetch (independent of the accumulator)
   float rsd[CHUNK];
 #pragma unroll
   for (int j = 0; j < CHUNK; ++j) rsd[j] = 0.f;
   if (live && (p.residual || p.residual2)) {
     if (!p.out_nhwc) {
-      const long long off = ((long long)b * p.cout + n0) * plane + pix;
+      const long long off = ((long long)b * ctot + c0) * plane + pix;
       const float *r1 = static_cast<const float *>(p.residual);
       const float *r2 = static_cast<const float *>(p.residual2);
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        if (fullc || n0 + j < p.cout) {
+        if (fullc || c0 + j < ctot) {
           if (r1) rsd[j] += __ldg(r1 + off + (long long)j * plane);
           if (r2) rsd[j] += __ldg(r2 + off + (long long)j * plane);
         }
     } else {
-      const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+      const long long off = ((long long)b * plane + pix) * p.ldo + p.co_off + c0;
       const __nv_bfloat16 *rr[2] = {static_cast<const __nv_bfloat16 *>(p.residual),
                                     static_cast<const __nv_bfloat16 *>(p.residual2)};
 #pragma unroll
@@ -114,7 +120,7 @@ __device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr,
         } else {
 #pragma unroll
           for (int j = 0; j < CHUNK; ++j)
-            if (n0 + j < p.cout) rsd[j] += __bfloat162float(rr[q][off + j]);
+            if (c0 + j < ctot) rsd[j] += __bfloat162float(rr[q][off + j]);
         }
       }
     }
@@ -129,7 +135,12 @@ __device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr,
 #pragma unroll
   for (int j = 0; j < CHUNK; j += 4) {
     const float4 a = srs[j / 4], c1 = sb1[j / 4], c2 = sb2[j / 4];
-    const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+    float aa[4] = {a.x, a.y, a.z, a.w};
+    const float b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+    if (rs_row != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) aa[e] = (live && (fullc || c0 + j + e < ctot)) ? __ldg(rs_row + j + e) : 1.f;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float x = __uint_as_float(r[j + e]) * aa[e];
@@ -142,24 +153,24 @@ __device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr,
 
 // Direct per-thread stores of one computed chunk: NCHW fp32 (coalesced across the warp's pixels) or NHWC bf16.
 template <int CHUNK>
-__device__ __forceinline__ void epi_store_direct(const ConvParams &p, int n0, int b, long long pix, long long plane,
-                                                 bool pix_ok, const float (&v)[CHUNK]) {
-  if (!(pix_ok && n0 < p.cout)) return;
-  const bool fullc = n0 + CHUNK <= p.cout;
+__device__ __forceinline__ void epi_store_direct(const ConvParams &p, int c0, int ctot, int b, long long pix,
+                                                 long long plane, bool pix_ok, const float (&v)[CHUNK]) {
+  if (!(pix_ok && c0 < ctot)) return;
+  const bool fullc = c0 + CHUNK <= ctot;
   if (!p.out_nhwc) {
-    float *o = static_cast<float *>(p.out) + ((long long)b * p.cout + n0) * plane + pix;
+    float *o = static_cast<float *>(p.out) + ((long long)b * ctot + c0) * plane + pix;
 #pragma unroll
     for (int j = 0; j < CHUNK; ++j)
-      if (fullc || n0 + j < p.cout) o[(long long)j * plane] = v[j];
+      if (fullc || c0 + j < ctot) o[(long long)j * plane] = v[j];
   } else {
-    __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + n0;
+    __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * plane + pix) * p.ldo + p.co_off + c0;
     if (fullc && (((p.ldo | p.co_off) & 7) == 0)) {
 #pragma unroll
       for (int j = 0; j < CHUNK; j += 8) *reinterpret_cast<uint4 *>(o + j) = pack8_bf16(&v[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < CHUNK; ++j)
-        if (n0 + j < p.cout) o[j] = __float2bfloat16_rn(v[j]);
+        if (c0 + j < ctot) o[j] = __float2bfloat16_rn(v[j]);
     }
   }
 }
@@ -209,12 +220,12 @@ struct OutMaps {
 };
 
 template <int CHUNK>
-__device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int n0, int b, long long pix,
+__device__ __forceinline__ void epi_chunk(const ConvParams &p, uint32_t taddr, int c0, int ctot, int b, long long pix,
                                           long long plane, bool pix_ok, float nz, const float *vrs,
-                                          const float *vb1, const float *vb2) {
+                                          const float *vb1, const float *vb2, const float *rs_row) {
   float v[CHUNK];
-  epi_compute<CHUNK>(p, taddr, n0, b, pix, plane, pix_ok, nz, vrs, vb1, vb2, v);
-  epi_store_direct<CHUNK>(p, n0, b, pix, plane, pix_ok, v);
+  epi_compute<CHUNK>(p, taddr, c0, ctot, b, pix, plane, pix_ok, nz, vrs, vb1, vb2, rs_row, v);
+  epi_store_direct<CHUNK>(p, c0, ctot, b, pix, plane, pix_ok, v);
 }
 
 // conv_ring_sm100.cu: returns -1 when the shape is not eligible (caller falls through to the other kernels),

@@ -312,14 +312,14 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
           } else {
             const long long pix = (long long)oh * p.full_w + ow;
             float v[CHUNK];
-            epi_compute<CHUNK>(p, taddr + rr * BLOCK_N + ch * CHUNK, ch * CHUNK, un.b, pix, plane, pix_ok, nzv,
-                               vec_rs + ch * CHUNK, vec_b1 + ch * CHUNK, vec_b2 + ch * CHUNK, v);
+            epi_compute<CHUNK>(p, taddr + rr * BLOCK_N + ch * CHUNK, ch * CHUNK, p.cout, un.b, pix, plane, pix_ok, nzv,
+                               vec_rs + ch * CHUNK, vec_b1 + ch * CHUNK, vec_b2 + ch * CHUNK, nullptr, v);
             if (it == n_items - 1) {
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
-            epi_store_direct<CHUNK>(p, ch * CHUNK, un.b, pix, plane, pix_ok, v);
+            epi_store_direct<CHUNK>(p, ch * CHUNK, p.cout, un.b, pix, plane, pix_ok, v);
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -60,40 +60,52 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
   const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
   int acc = 0;
   uint32_t acc_phase = 0;
+  const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+  const long long plane = (long long)p.full_h * p.full_w;
   for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     long long t = tile;
     const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
     const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
     const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
-    const int b = (int)t;
-    const int oh = h_i * p.th + row / p.tw;
-    const int ow = w_i * p.tw + row % p.tw;
-    const bool pix_ok = oh < p.out_h && ow < p.out_w;
-    const int fh = oh * p.os + p.oo_h, fw = ow * p.os + p.oo_w;
-    const long long pix = (long long)fh * p.full_w + fw;          // within one [full_h, full_w] plane
-    const long long plane = (long long)p.full_h * p.full_w;
+    const int sp = p.th * p.tw;                                    // pixels of one sample inside the tile
+    const int b = (int)t * p.tb + row / sp;                        // stacked tiles: rows [k*sp, (k+1)*sp) = sample k
+    const int rem = row % sp;
+    const int oh = h_i * p.th + rem / p.tw;
+    const int ow = w_i * p.tw + rem % p.tw;
+    const bool pix_ok = oh < p.out_h && ow < p.out_w && b < p.batch;
     const int nbase = n_i * BLOCK_N;
 
-    // stage the channel vectors of this tile
+    // stage the channel vectors of this tile (demod only when the whole tile belongs to one sample)
     for (int c = et; c < BLOCK_N; c += 256) {
       const int n = nbase + c;
+      const int cr = p.shuffle_cout ? n % p.shuffle_cout : n;
       const bool ok = n < p.cout;
-      vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * p.cout + n) : 1.f;
-      vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + n) : 0.f;
-      vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+      vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale && p.tb == 1) ? __ldg(p.row_scale + (long long)b * creal + cr) : 1.f;
+      vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f;
+      vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + cr) : 0.f;
     }
-    float nz = 0.f;
-    if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
+    float nz0 = 0.f;
+    if (p.noise != nullptr && pix_ok && !p.shuffle_cout)
+      nz0 = nw * __ldg(p.noise + b * p.noise_bstride + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);
     asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 
     mbar_wait(&tmem_full[acc], acc_phase);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-    for (int ch = wg; ch < BLOCK_N / C::CHUNK; ch += 2)
-      epi_chunk<C::CHUNK>(p, taddr + ch * C::CHUNK, nbase + ch * C::CHUNK, b, pix, plane, pix_ok, nz,
+    for (int ch = wg; ch < BLOCK_N / C::CHUNK; ch += 2) {
+      const int n0 = nbase + ch * C::CHUNK;
+      const int cls = p.shuffle_cout ? n0 / p.shuffle_cout : 0;
+      const int c0 = p.shuffle_cout ? n0 % p.shuffle_cout : n0;
+      const int ctot = n0 < p.cout ? creal : 0;                   // padded tail of the channel tile: nothing to write
+      const long long pix = (long long)(oh * p.os + p.oo_h + (cls >> 1)) * p.full_w + ow * p.os + p.oo_w + (cls & 1);
+      float nz = nz0;
+      if (p.shuffle_cout && p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
+      const float *rs_row = (p.tb > 1 && p.row_scale && pix_ok) ? p.row_scale + (long long)b * creal + c0 : nullptr;
+      epi_chunk<C::CHUNK>(p, taddr + ch * C::CHUNK, c0, ctot, b, pix, plane, pix_ok, nz,
                           vec_rs + acc * BLOCK_N + ch * C::CHUNK, vec_b1 + acc * BLOCK_N + ch * C::CHUNK,
-                          vec_b2 + acc * BLOCK_N + ch * C::CHUNK);
+                          vec_b2 + acc * BLOCK_N + ch * C::CHUNK, rs_row);
+    }
     tcgen05_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -324,9 +336,10 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
       const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
       const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
       const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
-      const int b = (int)t;
+      const int b = (int)t * p.tb;                       // first sample of the (possibly stacked) tile
       const int g = p.groups == 1 ? 0 : b;
       const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
+      const int dmul = p.branch_mode ? p.n_dil[n_i] : 1;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / p.kc;
         const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -335,7 +348,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
           unsigned char *sa = smem + stage * C::STAGE_BYTES;
           unsigned char *sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, iw0 + p.tap_dx[tap], ih0 + p.tap_dy[tap], b);
+          tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, iw0 + p.tap_dx[tap] * dmul, ih0 + p.tap_dy[tap] * dmul, b);
           tma_load_4d(sb, &tmap_b, &full_bar[stage], c0, n_i * BLOCK_N, p.tap_w[tap], g);
         }
         __syncwarp();
@@ -682,7 +695,7 @@ int launch_conv_impl(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
     }
   }
   p.tiles_n = (p.cout + BLOCK_N - 1) / BLOCK_N;
-  p.total_tiles = (long long)p.batch * p.tiles_h * p.tiles_w * p.tiles_n;
+  p.total_tiles = (long long)p.tiles_b * p.tiles_h * p.tiles_w * p.tiles_n;
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   kern<<<(unsigned)grid, kNumThreads, SMEM, stream>>>(p, ta, tb, om);
   return check_launch("conv_fprop_kernel");
@@ -709,7 +722,8 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
                        int ntaps, const int *tap_w, const int *tap_dy, const int *tap_dx, int stride,
                        int64_t out_h, int64_t out_w, void *out, int out_nhwc, int64_t full_h,
                        int64_t full_w, int os, int oo_h, int oo_w, int64_t ldo, int64_t co_off,
-                       const vsp_conv_epilogue *epi, cudaStream_t stream, int shuffle_cout = 0) {
+                       const vsp_conv_epilogue *epi, cudaStream_t stream, int shuffle_cout = 0, int n_branches = 0,
+                       const int *branch_dils = nullptr) {
   VSP_REQUIRE(batch >= 1 && (groups == 1 || groups == batch), "conv: groups must be 1 or batch");
   VSP_REQUIRE(cin >= 8 && cin % 8 == 0, "conv: cin must be a multiple of 8 (pad NHWC channels), got %lld", (long long)cin);
   VSP_REQUIRE(cout >= 1 && cout_pad >= cout, "conv: bad cout");
@@ -731,8 +745,22 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   }
   p.tw = next_pow2((int)out_w) < kBlockM ? next_pow2((int)out_w) : kBlockM;
   p.th = kBlockM / p.tw;
+  p.tb = 1;
+  if (groups == 1 && next_pow2((int)out_h) < p.th) {
+    // shared weights and an image smaller than one tile: stack several samples into the 128 rows
+    p.th = next_pow2((int)out_h);
+    p.tb = kBlockM / (p.tw * p.th);
+  }
+  p.tiles_b = ((int)batch + p.tb - 1) / p.tb;
   p.tiles_w = ((int)out_w + p.tw - 1) / p.tw;
   p.tiles_h = ((int)out_h + p.th - 1) / p.th;
+  if (n_branches > 0) {
+    VSP_REQUIRE(n_branches <= 4 && branch_dils != nullptr && cout % n_branches == 0, "conv: bad branch description");
+    const int cq = (int)cout / n_branches;
+    VSP_REQUIRE(cq >= 16 && cq <= 256 && (cq & (cq - 1)) == 0, "conv: branch width must be a power of two in 16..256");
+    p.branch_mode = 1;
+    for (int j = 0; j < n_branches; ++j) p.n_dil[j] = branch_dils[j];
+  }
   p.kc = ((int)cin + kBlockK - 1) / kBlockK;
   p.out = out; p.out_nhwc = out_nhwc;
   p.shuffle_cout = shuffle_cout;
@@ -752,15 +780,15 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     static const bool no_staged = getenv("VSP_NO_STAGED") != nullptr;
     const float al = p.alpha, sc = p.scale;
     p.staged = (!no_staged && out_nhwc && (ldo % 8) == 0 && (co_off % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                p.tw >= 32 && al >= 0.f && al <= 1.f && (sc > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
+                p.tw >= 32 && p.tb == 1 && al >= 0.f && al <= 1.f && (sc > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
     if (shuffle_cout) {
-      VSP_REQUIRE(p.staged && os == 2 && oo_h == 0 && oo_w == 0 && shuffle_cout % 32 == 0 && cout == 4 * shuffle_cout,
-                  "conv: pixel-shuffle epilogue needs an NHWC bf16 output (ldo %% 8 == 0), width >= 32, Cout %% 32 == 0");
+      VSP_REQUIRE(os == 2 && oo_h == 0 && oo_w == 0 && shuffle_cout % 32 == 0 && cout == 4 * shuffle_cout,
+                  "conv: pixel-shuffle epilogue needs Cout %% 32 == 0");
     }
   }
 
   // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers
-  {
+  if (!p.branch_mode) {
     const int rc = conv_ring_try_launch(p, x, wq, in_h, in_w, cout_pad, taps_total, ntaps == 9 ? tap_dx[8] : 1, stream);
     if (rc >= 0) return rc;
   }
@@ -768,7 +796,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   // Row-halo path: stride-1 3x3 (dilated) "same" convolution on a wide image, plain output mapping
   {
     static const bool no_halo = getenv("VSP_NO_HALO") != nullptr;
-    bool grid3 = !no_halo && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h;
+    bool grid3 = !no_halo && !p.branch_mode && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h;
     int dd = grid3 ? tap_dx[8] : 0;   // tap (kh,kw) offset must be ((kh-1)*d, (kw-1)*d)
     grid3 = grid3 && dd >= 1 && dd <= 8;
     for (int t = 0; grid3 && t < 9; ++t)
@@ -797,7 +825,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)batch};
     uint64_t strides[4] = {0, (uint64_t)cin * 2, (uint64_t)cin * in_w * 2, (uint64_t)cin * in_w * in_h * 2};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), (uint32_t)p.tb};
     uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     if (int rc = encode_tma(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, es,
                             CU_TENSOR_MAP_SWIZZLE_128B))
@@ -809,8 +837,9 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   int best_bn = 16;
   {
     double best = 1e300;
-    const long long m_tiles = (long long)p.batch * p.tiles_h * p.tiles_w;
+    const long long m_tiles = (long long)p.tiles_b * p.tiles_h * p.tiles_w;
     for (int bn = 256; bn >= 16; bn >>= 1) {
+      if (p.branch_mode && bn != (int)cout / n_branches) continue;   // one channel tile per branch
       if (bn > 16 && bn >= 2 * cout) continue;               // more than half of the tile would be padding
       const long long tiles = m_tiles * ((cout + bn - 1) / bn);
       const long long waves = (tiles + num_sms() - 1) / num_sms();
@@ -916,4 +945,24 @@ extern "C" int vsp_conv2d_up2_fused_bf16(const void *x, const void *wq, void *ou
   return conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, 4 * cout, 4 * cout, 9, 9, tw_, dy, dx, 1, in_h, in_w,
                             out, 1, 2 * in_h, 2 * in_w, 2, 0, 0, ldo, co_off, epi, static_cast<cudaStream_t>(stream_),
                             (int)cout);
+}
+
+extern "C" int vsp_conv2d_branches_bf16(const void *x, const void *wq, void *out, int64_t batch, int64_t groups,
+                                        int64_t in_h, int64_t in_w, int64_t cin, int64_t cout, int n_branches,
+                                        const int *dils, int out_nhwc_bf16, int64_t ldo, int64_t co_off,
+                                        const vsp_conv_epilogue *epi, void *stream_) {
+  using namespace vsp;
+  VSP_REQUIRE(n_branches >= 1 && n_branches <= 4 && dils != nullptr, "conv2d_branches: 1..4 branches");
+  int tw_[9], dy[9], dx[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      tw_[i * 3 + j] = i * 3 + j;
+      dy[i * 3 + j] = i - 1;
+      dx[i * 3 + j] = j - 1;
+    }
+  for (int j = 0; j < n_branches; ++j) VSP_REQUIRE(dils[j] >= 1 && dils[j] <= 64, "conv2d_branches: bad dilation");
+  if (!out_nhwc_bf16) { ldo = cout; co_off = 0; }
+  return conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout, 9, 9, tw_, dy, dx, 1, in_h, in_w, out,
+                            out_nhwc_bf16, in_h, in_w, 1, 0, 0, ldo, co_off, epi, static_cast<cudaStream_t>(stream_), 0,
+                            n_branches, dils);
 }

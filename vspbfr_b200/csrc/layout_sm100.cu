@@ -127,6 +127,30 @@ weight_sumsq_kernel(const float *__restrict__ w, float *__restrict__ wsq, long l
   wsq[e] = acc;
 }
 
+// ---- y[b,p,c] = bf16(x[b,p,c] * s[b,c]): per-sample channel scaling of an NHWC bf16 activation (the
+// "modulate the input instead of the weights" form of ModulatedConv2d, models/RestoreNet.py:481-508)
+__global__ void __launch_bounds__(kThreads)
+scale_nhwc_kernel(const uint4 *__restrict__ x, const float *__restrict__ s, uint4 *__restrict__ y, long long hw,
+                  int cg, long long s_bstride, long long total) {
+  for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+    const int g = (int)(idx % cg);
+    const long long b = idx / ((long long)cg * hw);
+    const uint4 v = __ldg(x + idx);
+    const float4 s0 = __ldg(reinterpret_cast<const float4 *>(s + b * s_bstride + g * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4 *>(s + b * s_bstride + g * 8 + 4));
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&v);
+    uint4 o;
+    __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      oh[i] = __floats2bfloat162_rn(f.x * sv[2 * i], f.y * sv[2 * i + 1]);
+    }
+    y[idx] = o;
+  }
+}
+
 // ---- demod[b,o] = rsqrt(wscale^2 * sum_i s[b,i]^2 * wsq[o,i] + eps): one warp per (b,o)
 __global__ void __launch_bounds__(kThreads)
 demod_from_wsq_kernel(const float *__restrict__ wsq, const float *__restrict__ s, float *__restrict__ demod,
@@ -361,4 +385,21 @@ extern "C" int vsp_modconv_weight_style_grad(const float *gw, const float *w, co
   }
   if (corr) VSP_CUDA(cudaFreeAsync(corr, stream));
   return 0;
+}
+
+extern "C" int vsp_scale_nhwc_bf16(const void *x, const float *s, void *y, int64_t batch, int64_t hw, int64_t c,
+                                   void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 0 && hw >= 0 && c >= 8 && c % 8 == 0, "scale_nhwc: channels must be a positive multiple of 8");
+  if (batch == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && s && y, "scale_nhwc: null pointer");
+  VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(s) & 15) == 0,
+              "scale_nhwc: pointers must be 16-byte aligned");
+  const long long total = batch * hw * (c / 8);
+  long long nb = ceil_div64(total, kThreads);
+  if (nb > (long long)num_sms() * 32) nb = (long long)num_sms() * 32;
+  scale_nhwc_kernel<<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(x), s, static_cast<uint4 *>(y), hw,
+                                                          (int)(c / 8), c, total);
+  return check_launch("scale_nhwc_kernel");
 }

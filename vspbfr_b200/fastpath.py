@@ -28,6 +28,12 @@ _cache: dict = {}
 # ModulatedConv2d(upsample=True) layers with Cin up to this run as the fused up-convolution (4x the transposed
 # conv's FLOPs, but no (2H+1)^2 intermediate and no blur pass): a win wherever the layer is bandwidth-bound
 _UP_FUSED_MAX_CIN = int(os.environ.get("VSP_UP_FUSED_MAX_CIN", "256"))
+# Activations with at most this many pixels per sample run in the input-modulated form (x * s, shared cached
+# weights, demodulation in the epilogue: models/RestoreNet.py:481-508): below it the per-sample weight prologue
+# costs more than scaling the activation, and shared weights let one 128-row tile stack several samples
+_LOWRES_PIXELS = int(os.environ.get("VSP_LOWRES_PIXELS", "1024"))
+# SMART layers up to this width run their four dilated branches as one launch of the generic kernel
+_BRANCH_MAX_W = int(os.environ.get("VSP_BRANCH_MAX_W", "64"))
 
 
 def _cached(owner, tag, tensors, build):
@@ -182,6 +188,26 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     wsq = _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(w4)) if conv.demodulate else None
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
                noise_weight_dev=m.noise.weight.detach())
+    if h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
+        # input-modulated form: scale the (small) activation, convolve with shared cached weights
+        xs = mc.scale_nhwc(x, s)
+        d = mc.demod_from_wsq(s, wsq, conv.scale, conv.eps) if conv.demodulate else None
+        if conv.upsample and k == 3 and cout % 32 == 0:
+            wq3 = _cached(conv, "wq_up2_shared", [conv.weight, conv.blur.kernel], lambda: mc.pack_weights(
+                mc.compose_up2_weights(w4, conv.blur.kernel), wscale=conv.scale)[0])
+            nz = _noise_for(noise, b, 2 * h, 2 * w, x.device)
+            return mc.conv_up2_fused(xs, wq3, cout, epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual,
+                                                                         residual2=residual2, **act))
+        if not conv.upsample:
+            wqs = _cached(conv, "wq_shared", [conv.weight], lambda: mc.pack_weights(w4, wscale=conv.scale)[0])
+            if conv.downsample:
+                xb = upfirdn_nhwc(xs, conv.blur.kernel, pad=conv.blur.pad)
+                nz = _noise_for(noise, b, (xb.shape[1] - k) // 2 + 1, (xb.shape[2] - k) // 2 + 1, x.device)
+                return mc.conv_fprop(xb, wqs, cout, k, k, 2, 0, 1, out_nhwc=True,
+                                     epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual, residual2=residual2, **act))
+            nz = _noise_for(noise, b, h, w, x.device)
+            return mc.conv_fprop(xs, wqs, cout, k, k, 1, conv.padding, 1, out_nhwc=True,
+                                 epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual, residual2=residual2, **act))
     if conv.upsample and k == 3 and cin <= _UP_FUSED_MAX_CIN and cout % 32 == 0 and w >= 32:
         # transposed conv + blur as ONE dense conv with the composite weights and a pixel-shuffle epilogue
         w3 = _cached(conv, "w_up2", [conv.weight, conv.blur.kernel], lambda: mc.compose_up2_weights(w4, conv.blur.kernel))
@@ -226,13 +252,26 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     wcat = _cached(m, "wcat", [br.weight for br in branches],
                    lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
     wsq = _cached(m, "wsq", [br.weight for br in branches], lambda: mc.weight_sumsq(wcat)) if branches[0].demodulate else None
-    wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate,
-                            wsq=wsq)
-    buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
-    for j, br in enumerate(branches):
-        dj = d[:, j * cq:(j + 1) * cq].contiguous() if d is not None else None
-        mc.conv_fprop(x, wq[:, :, j * cq:(j + 1) * cq, :], cq, k, k, 1, br.padding, br.dilation, out=buf, out_nhwc=True,
-                      co_off=j * cq, epi=mc.make_epilogue(row_scale=dj) if dj is not None else None)
+    dils = [br.dilation for br in branches]
+    one_launch = (k == 3 and w <= _BRANCH_MAX_W and cq >= 16 and (cq & (cq - 1)) == 0 and len(branches) <= 4
+                  and all(br.padding == br.dilation for br in branches))
+    if one_launch and h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
+        # input-modulated form on shared cached weights, all branches in one launch
+        xs = mc.scale_nhwc(x, s)
+        d = mc.demod_from_wsq(s, wsq, branches[0].scale, branches[0].eps) if wsq is not None else None
+        wqs = _cached(m, "wq_shared", [br.weight for br in branches], lambda: mc.pack_weights(wcat, wscale=branches[0].scale)[0])
+        buf = mc.conv_branches(xs, wqs, cout, dils, epi=mc.make_epilogue(row_scale=d) if d is not None else None)
+    else:
+        wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate,
+                                wsq=wsq)
+        if one_launch:
+            buf = mc.conv_branches(x, wq, cout, dils, epi=mc.make_epilogue(row_scale=d) if d is not None else None)
+        else:
+            buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
+            for j, br in enumerate(branches):
+                dj = d[:, j * cq:(j + 1) * cq].contiguous() if d is not None else None
+                mc.conv_fprop(x, wq[:, :, j * cq:(j + 1) * cq, :], cq, k, k, 1, br.padding, br.dilation, out=buf,
+                              out_nhwc=True, co_off=j * cq, epi=mc.make_epilogue(row_scale=dj) if dj is not None else None)
     fconv, fact = m.fusion[0], m.fusion[1]
     nz = _noise_for(noise, b, h, w, x.device)
     kw = dict(pre_bias=fact.bias.detach(), pre_act=3, noise=nz, noise_weight_dev=m.noise.weight.detach(),
@@ -256,6 +295,11 @@ def large_conv_layer(m: LargeConvLayer, x):
         wq = _cached(m, "wq1x1", [c.weight for c in convs], lambda: _pack_padded(
             torch.cat([c.weight.detach() for c in convs], 0), convs[0].scale, cin))
         buf = mc.conv_fprop(x, wq, cout, 1, 1, 1, 0, 1, out_nhwc=True)
+    elif (k == 3 and w <= _BRANCH_MAX_W and cq >= 16 and (cq & (cq - 1)) == 0 and len(convs) <= 4
+          and all(c.padding == c.dilation for c in convs)):
+        wq = _cached(m, "wq_branches", [c.weight for c in convs], lambda: mc.pack_weights(
+            torch.cat([c.weight.detach() for c in convs], 0).contiguous(), wscale=convs[0].scale)[0])
+        buf = mc.conv_branches(x, wq, cout, [c.dilation for c in convs])
     else:
         buf = torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x.device)
         for j, c in enumerate(convs):

@@ -262,6 +262,51 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
     return out
 
 
+def scale_nhwc(x_nhwc, s):
+    """bf16(x[b,h,w,c] * s[b,c]) — input-side style modulation (models/RestoreNet.py:481-508, `fused=False`)."""
+    b, h, w, c = x_nhwc.shape
+    if s.shape[1] != c:
+        s = torch.nn.functional.pad(s, (0, c - s.shape[1]))
+    s = s.contiguous()
+    y = torch.empty_like(x_nhwc)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _lib.load().vsp_scale_nhwc_bf16(ptr(x_nhwc), ptr(s), ptr(y), b, h * w, c, stream_ptr())
+    _lib.check(rc, "scale_nhwc_bf16")
+    return y
+
+
+def demod_from_wsq(s, wsq, wscale, eps=1e-8):
+    """d[b,o] = rsqrt(wscale^2 * sum_i s[b,i]^2 * wsq[o,i] + eps) (models/RestoreNet.py:513-516 with cached sum_t W^2)."""
+    b, cin = s.shape
+    cout = wsq.shape[0]
+    d = torch.empty((b, cout), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = _lib.load().vsp_modulate_weights_bf16(ptr(wsq), ptr(s.contiguous()), ptr(d), None, b, cout, cin, 1, wscale, eps,
+                                                   0, 0, cout, cin, ptr(wsq), stream_ptr())
+    _lib.check(rc, "modulate_weights_bf16(demod)")
+    return d
+
+
+def conv_branches(x_nhwc, wq, cout, dils, epi=None, out=None, out_nhwc=True, co_off=0):
+    """The dilated 3x3 branches of a SMART layer in one launch (vsp_conv2d_branches_bf16)."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps, rows, k_pad = wq.shape
+    assert taps == 9 and k_pad == cin and rows == cout, (wq.shape, cout, cin)
+    if out is None:
+        out = (torch.empty((b, h, w, cout), dtype=torch.bfloat16, device=x_nhwc.device) if out_nhwc
+               else torch.empty((b, cout, h, w), dtype=torch.float32, device=x_nhwc.device))
+    ldo = out.shape[3] if out_nhwc else cout
+    e, keep = epi if epi is not None else (None, None)
+    dl = _int_array(dils)
+    with torch.cuda.device(x_nhwc.device):
+        rc = _prof("conv_branches", 2.0 * b * h * w * cout * cin * 9, lambda: _lib.load().vsp_conv2d_branches_bf16(
+            ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, len(dils), dl, int(out_nhwc), ldo, co_off,
+            ctypes.byref(e) if e is not None else None, stream_ptr()),
+            detail=f"b{b} {cin}->{cout} k3 x{len(dils)} branches {h}x{w} g{g}", nbytes=2.0 * b * h * w * (cin + cout))
+    _lib.check(rc, "conv2d_branches_bf16")
+    return out
+
+
 def compose_up2_weights(weight, blur_kernel):
     """Composite weights of `conv_transpose2d(stride=2, 3x3)` followed by `Blur(4x4, pad=(1,1))`
     (models/RestoreNet.py:522-535), split into the four output-parity classes of the 6x6 stride-2 kernel.
