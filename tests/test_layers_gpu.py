@@ -183,3 +183,24 @@ def test_grouped_linear_matches_equal_linear():
         for m, idx in zip(lins, (0, 5, 2, 2)):
             want = m(styles[:, idx])
             np.testing.assert_allclose(got[id(m)].cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130)])
+def test_torgb_kernel_both_variants(c, h):
+    """ToRGB (models/RestoreNet.py:647-666) through both kernel variants (warp-per-pixel for small images,
+    pixel-per-thread for large ones) against the modulated 1x1 conv in fp32 on the same bf16 activations."""
+    torch.manual_seed(c + h)
+    m = L.ToRGB(c, 512, upsample=True).to(DEV)
+    m.bias.data.normal_()
+    b = 3
+    x = torch.randn(b, c, h, h, device=DEV)
+    style = torch.randn(b, 512, device=DEV)
+    skip = torch.randn(b, 3, h // 2, h // 2, device=DEV)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    got = fp.to_rgb(m, xq, style, skip)
+    s = m.conv.modulation(style)
+    w = m.conv.weight.view(3, c) * m.conv.scale
+    xr = xq.float()                                                     # [B,H,W,C]
+    rgb = torch.einsum("bhwc,oc,bc->bohw", xr, w, s) + m.bias
+    want = rgb + m.upsample(skip)
+    np.testing.assert_allclose(got.cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-4, atol=2e-4)

@@ -183,3 +183,40 @@ def test_errors_are_runtime_errors():
         op.upfirdn2d(x, torch.ones(2, 2, device=DEV, dtype=torch.float64))
     with pytest.raises(RuntimeError):
         op.fused_leaky_relu(torch.zeros(2, 4, device=DEV), torch.zeros(5, device=DEV))
+
+
+@pytest.mark.parametrize("n,c,h,w,pad,epi", [(2, 64, 33, 33, (1, 1), True), (1, 32, 65, 40, (1, 1), False),
+                                             (2, 64, 32, 32, (2, 2), False), (1, 128, 17, 130, (2, 2), True),
+                                             (3, 8, 9, 9, (1, 1), True), (1, 16, 100, 7, (2, 2), False)])
+@pytest.mark.parametrize("separable", [True, False])
+def test_blur_nhwc_bf16_streaming_kernel(n, c, h, w, pad, epi, separable):
+    """Channels-last bf16 blur (Blur of models/RestoreNet.py:85-101 inside the fused pipeline): the streaming separable
+    kernel and its direct branch for non-separable filters, with the noise + bias + lrelu + residual epilogue,
+    against the CPU oracle on the same bf16-rounded input."""
+    import math
+    import oracle
+    from vspbfr_b200 import fastpath as fp
+    from vspbfr_b200.op import modconv as mc
+    rng = np.random.default_rng(n * 1000 + c + h + w)
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    k = (np.outer([1, 3, 3, 1], [1, 3, 3, 1]) / 64).astype(np.float32)
+    if not separable:
+        k = k.copy()
+        k[1, 2] += 0.03125
+    xq = mc.nchw_to_nhwc_bf16(torch.from_numpy(x).cuda())
+    xr = xq.float().permute(0, 3, 1, 2).contiguous().cpu().numpy()
+    want = oracle.upfirdn2d_ref(xr, k, 1, 1, pad)
+    e = None
+    if epi:
+        oh, ow = want.shape[2:]
+        noise = torch.from_numpy(rng.standard_normal((n, 1, oh, ow)).astype(np.float32)).cuda()
+        bias = torch.from_numpy(rng.standard_normal(c).astype(np.float32)).cuda()
+        res = torch.from_numpy(rng.standard_normal((n, c, oh, ow)).astype(np.float32)).cuda()
+        resq = mc.nchw_to_nhwc_bf16(res)
+        e = mc.make_epilogue(noise=noise, noise_weight=0.25, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2), residual=resq)
+        v = want + 0.25 * noise.cpu().numpy() + bias.cpu().numpy()[None, :, None, None]
+        want = np.where(v > 0, v, 0.2 * v) * math.sqrt(2) + resq.float().permute(0, 3, 1, 2).cpu().numpy()
+    y = fp.upfirdn_nhwc(xq, torch.from_numpy(k).cuda(), pad=pad, epi=e)
+    got = y.float().permute(0, 3, 1, 2).cpu().numpy()
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(want).max())))

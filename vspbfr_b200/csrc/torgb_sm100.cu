@@ -65,6 +65,46 @@ torgb_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, const flo
   }
 }
 
+// Small images (hw <= 4096): one warp per pixel, lanes split the channel groups and reduce with shuffles —
+// the pixel-per-thread form above would leave most SMs idle and serialise 64 dependent loads per thread.
+__global__ void __launch_bounds__(kThreads)
+torgb_warp_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, const float *__restrict__ s,
+                  const float *__restrict__ bias, const float *__restrict__ skip, float *__restrict__ out,
+                  long long hw, int c, float wscale) {
+  extern __shared__ float4 wm[];
+  const long long b = blockIdx.y;
+  for (int ch = threadIdx.x; ch < c; ch += kThreads) {
+    const float f = wscale * (s ? __ldg(s + b * c + ch) : 1.f);
+    wm[ch] = make_float4(__ldg(w + ch) * f, __ldg(w + c + ch) * f, __ldg(w + 2 * c + ch) * f, 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (p >= hw) return;
+  const int cg = c / 8;
+  const uint4 *xp = x + (b * hw + p) * cg;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int g = lane; g < cg; g += 32) {
+    const uint4 v = __ldg(xp + g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const uint32_t word = (&v.x)[e >> 1];
+      const float xv = __uint_as_float((e & 1) ? (word & 0xFFFF0000u) : (word << 16));
+      const float4 wv = wm[g * 8 + e];
+      a0 = fmaf(xv, wv.x, a0);
+      a1 = fmaf(xv, wv.y, a1);
+      a2 = fmaf(xv, wv.z, a2);
+    }
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane < 3) {
+    const long long off = (b * 3 + lane) * hw + p;
+    float v = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + (bias ? __ldg(bias + lane) : 0.f);
+    if (skip) v += __ldg(skip + off);
+    out[off] = v;
+  }
+}
+
 }  // namespace
 }  // namespace vsp
 
@@ -78,6 +118,12 @@ extern "C" int vsp_torgb_nhwc_bf16(const void *x, const float *w, const float *s
   VSP_REQUIRE(x && w && out, "torgb: null pointer");
   VSP_REQUIRE(batch <= 65535 && c <= 2048, "torgb: batch/channel extent too large");
   VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "torgb: x must be 16-byte aligned");
+  if (hw <= 4096) {
+    dim3 grid((unsigned)ceil_div64(hw, kThreads / 32), (unsigned)batch);
+    torgb_warp_kernel<<<grid, kThreads, sizeof(float4) * c, stream>>>(static_cast<const uint4 *>(x), w, s, bias, skip, out,
+                                                                      hw, (int)c, wscale);
+    return check_launch("torgb_warp_kernel");
+  }
   dim3 grid((unsigned)ceil_div64(hw, kThreads * kPix), (unsigned)batch);
   torgb_kernel<<<grid, kThreads, sizeof(float4) * c, stream>>>(static_cast<const uint4 *>(x), w, s, bias, skip, out,
                                                                hw, (int)c, wscale);

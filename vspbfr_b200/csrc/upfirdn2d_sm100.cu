@@ -600,13 +600,21 @@ extern "C" int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y
     e.residual2 = static_cast<const uint4 *>(epi->residual2);
   }
   if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 && kh <= kK && kw <= kK) {
-    constexpr int R = 4;
+    static const int blur_r = getenv("VSP_BLUR_R") ? atoi(getenv("VSP_BLUR_R")) : 4;
+    const int R = blur_r == 8 ? 8 : (blur_r == 2 ? 2 : 4);
     const int row_blocks = (int)((out_h + R - 1) / R);
     const long long tot = (long long)n * row_blocks * out_w * cg;
     long long nb = (tot + kThreads - 1) / kThreads;
     if (nb > (long long)num_sms() * 64) nb = (long long)num_sms() * 64;
-    blur_nhwc_kernel<R><<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(x), filt,
-                                                              static_cast<uint4 *>(y), p, e, cg, row_blocks, tot);
+    if (R == 8)
+      blur_nhwc_kernel<8><<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(x), filt,
+                                                                static_cast<uint4 *>(y), p, e, cg, row_blocks, tot);
+    else if (R == 2)
+      blur_nhwc_kernel<2><<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(x), filt,
+                                                                static_cast<uint4 *>(y), p, e, cg, row_blocks, tot);
+    else
+      blur_nhwc_kernel<4><<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(x), filt,
+                                                                static_cast<uint4 *>(y), p, e, cg, row_blocks, tot);
     return check_launch("blur_nhwc_kernel");
   }
   upfirdn2d_nhwc_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import weakref
 
 import torch
 from torch.nn import functional as F
@@ -40,12 +41,12 @@ def _cached(owner, tag, tensors, build):
     """Memoise a derived tensor per module, invalidated when any source tensor is modified in place
     or re-assigned (weights are static during inference, so this runs once)."""
     key = (id(owner), tag)
-    ver = tuple((t.data_ptr(), t._version) for t in tensors)
+    ver = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
     hit = _cache.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[2]() is owner:     # id() may be recycled: check the owner itself
         return hit[1]
     val = build()
-    _cache[key] = (ver, val)
+    _cache[key] = (ver, val, weakref.ref(owner))
     return val
 
 
@@ -119,9 +120,9 @@ _bank_cache: dict = {}
 
 def _banks_for(owner, build):
     hit = _bank_cache.get(id(owner))
-    if hit is None:
-        hit = _bank_cache[id(owner)] = build()
-    return hit
+    if hit is None or hit[1]() is not owner:
+        hit = _bank_cache[id(owner)] = (build(), weakref.ref(owner))
+    return hit[0]
 
 
 def _modulation(lin, style):
