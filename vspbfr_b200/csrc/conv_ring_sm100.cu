@@ -336,6 +336,341 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// kh-folded variant for very narrow layers (Cout <= 32: the dilated SMART branches at 256^2 / 512^2 and the 32-channel
+// 1024^2 layer).  With N = Cout <= 32 the nine-tap formulation above is bound by the tensor core's shared-memory
+// OPERAND bandwidth, not by math or HBM: every MMA re-reads its 128 x 16 activation slab (32 wavefronts) to do only
+// 128 x N x 16 MACs (ncu: l1tex__data_pipe_tc_wavefronts at 55 % with the tensor pipe 12 % busy).  Here the three
+// vertical taps are folded into the GEMM's N dimension instead: for each INPUT row and each horizontal tap kw
+//     Z_k[p, (kh, c)] += X_k[p + (kw-1) d, :] . W[kh, kw, c, :]        (one MMA chain with N = 3 C)
+// so an input row is read three times (once per kw) instead of nine, and the output row r is assembled in the epilogue
+// from the TMEM blocks of three consecutive input rows:  out_r = Z_{r-1}[kh=0] + Z_r[kh=1] + Z_{r+1}[kh=2]  (lane-wise
+// adds, no cross-lane traffic).  TMEM is a ring of NR input-row slots of 3 C columns; an input row's shared-memory
+// slot is released as soon as its own MMAs retire (each row is consumed once), its TMEM slot after the three output
+// rows that read it.  Cin up to 128 (two 64-channel blocks accumulated into the same slots).
+template <int C, bool STAGED>
+__global__ void __launch_bounds__(kRingThreads, 1)
+conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o) {
+  constexpr int NR = (512 / (3 * C));                // TMEM row slots: 10 (C = 16) or 5 (C = 32)
+  constexpr int B_BYTES = C * 128;                    // one (kh, kw) weight tile of a 64-channel block
+  constexpr int ROW_BYTES = C * 2;
+  constexpr int SBUF_BYTES = 32 * ROW_BYTES;
+  constexpr int STAGE_BYTES = STAGED ? 2 * SBUF_BYTES : 0;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.rr_S, kc = p.kc;
+  const int d = p.halo_d;
+  const uint32_t slot_bytes = (uint32_t)p.halo_w * 128u;
+  const uint32_t b_total = (uint32_t)(kc * 9) * B_BYTES;
+  unsigned char *a_buf = smem;
+  unsigned char *b_buf = smem + (size_t)S * slot_bytes;
+  unsigned char *o_buf = b_buf + ((b_total + 1023u) & ~1023u);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(o_buf + 8 * STAGE_BYTES);
+  uint64_t *a_full = bars, *a_empty = bars + kMaxSlots;
+  uint64_t *b_full = bars + 2 * kMaxSlots, *b_empty = b_full + 1;
+  uint64_t *acc_full = b_empty + 1, *acc_empty = acc_full + NR;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + NR);
+  float *epi_vec = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 512);  // [3][C]
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (STAGED) tma_prefetch_desc(&tmap_o);
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    for (int i = 0; i < NR; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 12);   // three reading output rows x four lane-quadrant warps
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
+
+  if (warp == 0) {
+    // ===================== activation rows (kc slots per row) =====================
+    int slot = 0;
+    uint32_t ph = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const RingUnit un = ring_decode(p, u, d);
+      const int w0 = un.strip * kBlockM - d;
+      for (int k = 0; k < un.L + 2; ++k) {
+        const int ih = un.o0 + (k - 1) * d;
+        for (int cb = 0; cb < kc; ++cb) {
+          mbar_wait(&a_empty[slot], ph ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&a_full[slot], slot_bytes);
+            tma_load_4d(a_buf + (size_t)slot * slot_bytes, &tmap_a, &a_full[slot], cb * kBlockK, w0, ih, un.b);
+          }
+          __syncwarp();
+          if (++slot == S) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weights, resident: smem tile order [cb][kw][kh] so that one kw is an [3C x 64] operand =====
+    int cur_g = -1;
+    uint32_t res_ph = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const RingUnit un = ring_decode(p, u, d);
+      const int g = p.groups == 1 ? 0 : un.b;
+      if (g == cur_g) continue;
+      mbar_wait(b_empty, res_ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, b_total);
+        for (int cb = 0; cb < kc; ++cb)
+          for (int kw = 0; kw < 3; ++kw)
+            for (int kh = 0; kh < 3; ++kh)
+              tma_load_4d(b_buf + (size_t)((cb * 3 + kw) * 3 + kh) * B_BYTES, &tmap_b, b_full, cb * kBlockK, 0,
+                          p.tap_w[kh * 3 + kw], g);
+      }
+      __syncwarp();
+      cur_g = g;
+      res_ph ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one input row = 3 (kw) x kk MMAs with N = 3C =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, 3 * C);
+    const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
+    int aslot = 0, rslot = 0;
+    uint32_t aph = 0, rph = 0, res_ph = 0;
+    int cur_g = -1;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const RingUnit un = ring_decode(p, u, d);
+      const int g = p.groups == 1 ? 0 : un.b;
+      if (g != cur_g) {
+        mbar_wait(b_full, res_ph);
+        res_ph ^= 1;
+        cur_g = g;
+      }
+      bool release_b = u + gridDim.x >= units;
+      if (!release_b && p.groups != 1) release_b = ring_decode(p, u + gridDim.x, d).b != un.b;
+      for (int k = 0; k < un.L + 2; ++k) {
+        mbar_wait(&acc_empty[rslot], rph ^ 1);        // the output rows that read this TMEM slot last time are done
+        int s0 = aslot;
+        for (int cb = 0; cb < kc; ++cb) {
+          mbar_wait(&a_full[aslot], aph);
+          if (++aslot == S) { aslot = 0; aph ^= 1; }
+        }
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(rslot * 3 * C);
+          int s = s0;
+          for (int cb = 0; cb < kc; ++cb) {
+            const int kk = min(kBlockK / kUmmaK, (p.cin - cb * kBlockK + kUmmaK - 1) / kUmmaK);
+            const uint32_t arow = a_base + (uint32_t)s * slot_bytes;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint64_t adesc = umma_smem_desc(arow + (uint32_t)(kw * d) * 128u, 128);
+              const uint64_t bdesc = umma_smem_desc(b_base + (uint32_t)((cb * 3 + kw) * 3) * B_BYTES, 128);
+#pragma unroll
+              for (int ks = 0; ks < kBlockK / kUmmaK; ++ks)
+                if (ks < kk)
+                  umma_bf16_ss(d_tmem, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc,
+                               (cb > 0 || kw > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&a_empty[s]);                  // this row block is consumed exactly once
+            if (++s == S) s = 0;
+          }
+          umma_commit(&acc_full[rslot]);
+          if (k == un.L + 1 && release_b) umma_commit(b_empty);
+        }
+        __syncwarp();
+        if (++rslot == NR) { rslot = 0; rph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps): out_j = Z_j[kh=0] + Z_{j+1}[kh=1] + Z_{j+2}[kh=2] =====================
+    const int wg = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int et = threadIdx.x - 128;
+    float *vec_rs = epi_vec, *vec_b1 = epi_vec + C, *vec_b2 = epi_vec + 2 * C;
+    const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
+    const long long plane = (long long)p.full_h * p.full_w;
+    unsigned char *stage = o_buf + (warp - 4) * STAGE_BYTES;
+    const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+    const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
+    const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
+    uint32_t sbuf = 0;
+    long long rg0 = 0;                                  // running index of the unit's first input row
+    int cur_b = -1;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const RingUnit un = ring_decode(p, u, d);
+      if (un.b != cur_b) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = et; c < C; c += 256) {
+          const bool ok = c < p.cout;
+          vec_rs[c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)un.b * p.cout + c) : 1.f;
+          vec_b1[c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + c) : 0.f;
+          vec_b2[c] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_b = un.b;
+      }
+      const int ow = un.strip * kBlockM + row;
+      const bool pix_ok = ow < p.out_w;
+      const int L = un.L;
+      for (int j = wg; j < L; j += 2) {
+        const int oh = un.o0 + j * d;
+        const long long pix = (long long)oh * p.full_w + ow;
+        float nz = 0.f;
+        if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + un.b * p.noise_bstride + pix);
+        const long long r0 = rg0 + j;
+        const int s0 = (int)(r0 % NR), s1 = (int)((r0 + 1) % NR), s2 = (int)((r0 + 2) % NR);
+        mbar_wait(&acc_full[s2], (uint32_t)(((r0 + 2) / NR) & 1));      // MMAs retire in order: rows r0, r0+1 are done too
+        tcgen05_fence_after();
+        const uint32_t tq = tmem_base + ((uint32_t)(quad * 32) << 16);
+        uint32_t r[C], t[C];
+        if constexpr (C == 32) {
+          tmem_ld_32x32b_x32(tq + s0 * 3 * C, r);
+          tmem_ld_32x32b_x32(tq + s1 * 3 * C + C, t);
+        } else {
+          tmem_ld_32x32b_x16(tq + s0 * 3 * C, reinterpret_cast<uint32_t(&)[16]>(r));
+          tmem_ld_32x32b_x16(tq + s1 * 3 * C + C, reinterpret_cast<uint32_t(&)[16]>(t));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < C; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t[i]));
+        if constexpr (C == 32) tmem_ld_32x32b_x32(tq + s2 * 3 * C + 2 * C, t);
+        else tmem_ld_32x32b_x16(tq + s2 * 3 * C + 2 * C, reinterpret_cast<uint32_t(&)[16]>(t));
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < C; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(t[i]));
+        // release the three TMEM slots; output rows that do not exist at the unit's ends are accounted for by the
+        // row min(k, L-1), which reads slot k in any case
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int k = j + q;                                   // unit-local input row
+            const int readers = min(k, L - 1) - max(k - 2, 0) + 1;
+            const int mine = 1 + ((min(k, L - 1) == j) ? 3 - readers : 0);
+            mbar_arrive_n(&acc_empty[q == 0 ? s0 : (q == 1 ? s1 : s2)], (uint32_t)mine);
+          }
+        }
+        if constexpr (STAGED) {
+          unsigned char *buf = stage + (sbuf & 1) * SBUF_BYTES;
+          ++sbuf;
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < C / 8; ++i)
+            *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) =
+                epi_lean8(&r[8 * i], vec_rs + 8 * i, vec_b1 + 8 * i, vec_b2 + 8 * i, nz, m1, m1a, m2, m2a);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmap_o, buf, (int)p.co_off, un.strip * kBlockM + quad * 32, oh, un.b);
+            bulk_commit_group();
+          }
+        } else {
+          // direct stores (fp32 NCHW or residual epilogues): same arithmetic as epi_compute on the summed accumulator
+          float v[C];
+          const bool live = pix_ok;
+#pragma unroll
+          for (int i = 0; i < C; ++i) {
+            float xv = __uint_as_float(r[i]) * vec_rs[i];
+            if (p.pre_act) xv = epi_act(xv + vec_b1[i], p.pre_act, p.alpha, p.scale);
+            xv = epi_act(xv + nz + vec_b2[i], p.act, p.alpha, p.scale);
+            v[i] = xv;
+          }
+          if (live && (p.residual || p.residual2)) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+              if (i >= p.cout) break;
+              if (!p.out_nhwc) {
+                const long long off = ((long long)un.b * p.cout + i) * plane + pix;
+                if (p.residual) v[i] += __ldg(static_cast<const float *>(p.residual) + off);
+                if (p.residual2) v[i] += __ldg(static_cast<const float *>(p.residual2) + off);
+              } else {
+                const long long off = ((long long)un.b * plane + pix) * p.ldo + p.co_off + i;
+                if (p.residual) v[i] += __bfloat162float(static_cast<const __nv_bfloat16 *>(p.residual)[off]);
+                if (p.residual2) v[i] += __bfloat162float(static_cast<const __nv_bfloat16 *>(p.residual2)[off]);
+              }
+            }
+          }
+          epi_store_direct<C>(p, 0, p.cout, un.b, pix, plane, pix_ok, v);
+        }
+      }
+      rg0 += L + 2;
+    }
+    if (STAGED && lane == 0) bulk_wait_group<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int C, bool STAGED>
+int launch_ringfold(const ConvParams &p, const void *x, const void *wq, int64_t in_h, int64_t in_w, int64_t cout_pad,
+                    int taps_total, size_t smem_bytes, cudaStream_t stream) {
+  auto kern = conv_ringfold_kernel<C, STAGED>;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  CUtensorMap ta, tb, to;
+  {
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)p.batch};
+    uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * in_w * 2, (uint64_t)p.cin * in_w * in_h * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.halo_w, 1, 1};
+    if (int rc = encode_tma(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
+    uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
+                           (uint64_t)p.cin * cout_pad * taps_total * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)C, 1, 1};
+    if (int rc = encode_tma(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, wq, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  if (STAGED) {
+    uint64_t dims[4] = {(uint64_t)(p.co_off + p.cout), (uint64_t)p.full_w, (uint64_t)p.full_h, (uint64_t)p.batch};
+    uint64_t strides[4] = {0, (uint64_t)p.ldo * 2, (uint64_t)p.ldo * p.full_w * 2,
+                           (uint64_t)p.ldo * p.full_w * p.full_h * 2};
+    uint32_t box[4] = {(uint32_t)C, 32, 1, 1};
+    if (int rc = encode_tma(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out, dims, strides, box, nullptr,
+                            C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
+      return rc;
+  } else {
+    to = ta;
+  }
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
+  const long long grid = units < num_sms() ? units : num_sms();
+  kern<<<(unsigned)grid, kRingThreads, smem_bytes, stream>>>(p, ta, tb, to);
+  return check_launch("conv_ringfold_kernel");
+}
+
 template <int BLOCK_N, int TAPS, bool STAGED>
 int launch_ring(const ConvParams &p, const void *x, const void *wq, int64_t in_h, int64_t in_w, int64_t cout_pad,
                 int taps_total, size_t smem_bytes, cudaStream_t stream) {
@@ -406,7 +741,9 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   if (p.stride != 1 || p.os != 1 || p.oo_h != 0 || p.oo_w != 0) return -1;
   if (p.out_w < kBlockM || p.out_w != in_w || p.out_h != in_h || p.full_w != p.out_w || p.full_h != p.out_h) return -1;
   if (p.ntaps != 9 && p.ntaps != 1) return -1;
-  if (p.kc != 1 || p.cout > 64) return -1;
+  static const bool no_fold = getenv("VSP_NO_FOLD") != nullptr;
+  const bool fold = !no_fold && p.ntaps == 9 && p.cout <= 32 && p.kc <= 2;
+  if (!fold && (p.kc != 1 || p.cout > 64)) return -1;
   const int taps = p.ntaps;
   const int halo = taps == 9 ? 1 : 0;
   int d = 1;
@@ -427,13 +764,13 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
                  p.residual == nullptr && p.residual2 == nullptr && p.alpha >= 0.f && p.alpha <= 1.f &&
                  (p.scale > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
   const int slot = p.halo_w * 128;
-  const int b_bytes = (taps * bn * 128 + 1023) & ~1023;
+  const int b_bytes = (taps * p.kc * bn * 128 + 1023) & ~1023;
   const int chunk = bn < 32 ? bn : 32;
   const int o_bytes = p.rr_staged ? 8 * 2 * 32 * chunk * 2 : 0;
   const int fixed = 1024 + b_bytes + o_bytes + 512 + 3 * bn * 4;
   int S = (232448 - fixed) / slot;
   if (S > kMaxSlots) S = kMaxSlots;
-  if (S < 1 + 2 * halo + 2) return -1;
+  if (S < (1 + 2 * halo + 2) * p.kc) return -1;
   p.rr_R = kRingR; p.rr_S = S; p.rr_nb = 0;
   p.tiles_n = 1;
   p.rr_strips = (p.out_w + kBlockM - 1) / kBlockM;
@@ -456,6 +793,13 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   p.rr_L = best_L;
   p.rr_segs = (rows_chain + best_L - 1) / best_L;
   const size_t smem_bytes = (size_t)fixed + (size_t)S * slot;
+  if (fold) {
+    if (bn == 16)
+      return p.rr_staged ? launch_ringfold<16, true>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream)
+                         : launch_ringfold<16, false>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);
+    return p.rr_staged ? launch_ringfold<32, true>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream)
+                       : launch_ringfold<32, false>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);
+  }
   switch (bn) {
     case 16: return dispatch_ring<16>(p, taps, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);
     case 32: return dispatch_ring<32>(p, taps, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);

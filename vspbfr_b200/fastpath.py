@@ -475,5 +475,8 @@ def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent
     restored = restoration_forward(net, low_imgs, feats, codes, noise_styles)
     size = low_imgs.shape[-1]
     if image.shape[-1] != size:
-        image = F.adaptive_avg_pool2d(image, (size, size))      # face_pool, e4e/models/psp.py:245-246
+        # face_pool (e4e/models/psp.py:245-246): AdaptiveAvgPool2d to (size, size) is an exact k x k mean when divisible
+        k = image.shape[-1] // size
+        image = (F.avg_pool2d(image, k) if image.shape[-1] == k * size and image.shape[-2] == k * size
+                 else F.adaptive_avg_pool2d(image, (size, size)))
     return restored, image
