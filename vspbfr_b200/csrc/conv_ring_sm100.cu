@@ -770,7 +770,7 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   const int fixed = 1024 + b_bytes + o_bytes + 512 + 3 * bn * 4;
   int S = (232448 - fixed) / slot;
   if (S > kMaxSlots) S = kMaxSlots;
-  if (S < (1 + 2 * halo + 2) * p.kc) return -1;
+  if (S < (fold ? 2 * p.kc : 1 + 2 * halo + 2)) return -1;
   p.rr_R = kRingR; p.rr_S = S; p.rr_nb = 0;
   p.tiles_n = 1;
   p.rr_strips = (p.out_w + kBlockM - 1) / kBlockM;
