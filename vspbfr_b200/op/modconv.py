@@ -338,7 +338,8 @@ def conv_up2_fused(x_nhwc, wq, cout, epi=None, out=None, co_off=0):
         out = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x_nhwc.device)
     e, keep = epi if epi is not None else (None, None)
     with torch.cuda.device(x_nhwc.device):
-        rc = _prof("conv_up2_fused", 2.0 * b * h * w * 4 * cout * cin * 9,
+        # algorithmic FLOPs of the layer it replaces (the transposed conv); the dense form executes 4x as many
+        rc = _prof("conv_up2_fused", 2.0 * b * h * w * cout * cin * 9,
                    lambda: _lib.load().vsp_conv2d_up2_fused_bf16(
                        ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, out.shape[3], co_off,
                        ctypes.byref(e) if e is not None else None, stream_ptr()),
