@@ -6,7 +6,8 @@ inference, 256 synthetic 512x512 low-quality faces per step, random-init weights
 style decoder @1024^2 (features) + Restoration_net @512^2 (restoration_test.py:130-131).  The e4e
 encoder and the 4-step code diffuser that produce the w+ codes are outside the hot path
 (north_star): synthetic codes stand in for them.  The 256 images are sharded
-contiguously over the ranks (no collective), each rank runs micro-batches of ``--micro``.
+contiguously over the ranks (no collective), each rank runs micro-batches of ``--micro`` (default 32: at 8 GPUs a rank's whole shard; measured
+767 / 833 / 880 faces/s at micro-batch 8 / 16 / 32 on one B200 — the low-resolution layers are latency-bound).
 
 One JSON line on rank 0 (see the contract in the task statement):
   value          faces/s with inputs resident in HBM (device-timed, max over ranks)
@@ -159,7 +160,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--micro", type=int, default=8)
+    ap.add_argument("--micro", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=30.0)
     args = ap.parse_args()

@@ -13,6 +13,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kPix = 4;  // pixels per thread
+constexpr int kWarpPix = 8;  // pixels per warp in the warp-per-pixel variant
 
 __global__ void __launch_bounds__(kThreads)
 torgb_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, const float *__restrict__ s,
@@ -79,29 +80,33 @@ torgb_warp_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, cons
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long p = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (p >= hw) return;
   const int cg = c / 8;
-  const uint4 *xp = x + (b * hw + p) * cg;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int g = lane; g < cg; g += 32) {
-    const uint4 v = __ldg(xp + g);
+  // kWarpPix consecutive pixels per warp: amortises the per-block weight staging above
+  const long long p0 = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * kWarpPix;
+  for (int i = 0; i < kWarpPix; ++i) {
+    const long long p = p0 + i;
+    if (p >= hw) return;
+    const uint4 *xp = x + (b * hw + p) * cg;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int g = lane; g < cg; g += 32) {
+      const uint4 v = __ldg(xp + g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const uint32_t word = (&v.x)[e >> 1];
-      const float xv = __uint_as_float((e & 1) ? (word & 0xFFFF0000u) : (word << 16));
-      const float4 wv = wm[g * 8 + e];
-      a0 = fmaf(xv, wv.x, a0);
-      a1 = fmaf(xv, wv.y, a1);
-      a2 = fmaf(xv, wv.z, a2);
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t word = (&v.x)[e >> 1];
+        const float xv = __uint_as_float((e & 1) ? (word & 0xFFFF0000u) : (word << 16));
+        const float4 wv = wm[g * 8 + e];
+        a0 = fmaf(xv, wv.x, a0);
+        a1 = fmaf(xv, wv.y, a1);
+        a2 = fmaf(xv, wv.z, a2);
+      }
     }
-  }
-  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-  if (lane < 3) {
-    const long long off = (b * 3 + lane) * hw + p;
-    float v = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + (bias ? __ldg(bias + lane) : 0.f);
-    if (skip) v += __ldg(skip + off);
-    out[off] = v;
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane < 3) {
+      const long long off = (b * 3 + lane) * hw + p;
+      float v = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + (bias ? __ldg(bias + lane) : 0.f);
+      if (skip) v += __ldg(skip + off);
+      out[off] = v;
+    }
   }
 }
 
@@ -119,7 +124,7 @@ extern "C" int vsp_torgb_nhwc_bf16(const void *x, const float *w, const float *s
   VSP_REQUIRE(batch <= 65535 && c <= 2048, "torgb: batch/channel extent too large");
   VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "torgb: x must be 16-byte aligned");
   if (hw <= 4096) {
-    dim3 grid((unsigned)ceil_div64(hw, kThreads / 32), (unsigned)batch);
+    dim3 grid((unsigned)ceil_div64(hw, (kThreads / 32) * kWarpPix), (unsigned)batch);
     torgb_warp_kernel<<<grid, kThreads, sizeof(float4) * c, stream>>>(static_cast<const uint4 *>(x), w, s, bias, skip, out,
                                                                       hw, (int)c, wscale);
     return check_launch("torgb_warp_kernel");
