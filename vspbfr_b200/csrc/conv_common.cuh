@@ -27,7 +27,7 @@ struct ConvParams {
   int kc;                  // channel blocks per tap = ceil(cin / 64)
   int halo_d, halo_w;      // row-halo / row-ring kernels: dilation and padded halo row length (pixels)
   // row-ring kernel: R output rows per accumulator hand-off, S row slots, segments of L rows per chain
-  int rr_R, rr_S, rr_L, rr_segs, rr_chains, rr_strips, rr_nb, rr_staged;
+  int rr_R, rr_S, rr_L, rr_segs, rr_chains, rr_strips, rr_nb, rr_staged, rr_nslices;
   // output addressing: logical (oh, ow) -> (oh*os + oo_h, ow*os + oo_w) inside [full_h, full_w]
   void *out;
   int out_nhwc;
@@ -175,29 +175,65 @@ __device__ __forceinline__ void epi_store_direct(const ConvParams &p, int c0, in
   }
 }
 
-// Lean staged epilogue arithmetic for 8 channels: demod, [bias1 + lrelu], noise + bias + lrelu, branch-free
-// (a disabled stage has alpha = scale = 1: max(t, t) = t).  lrelu(t) * s == max(t * s, t * s * a) for 0 <= a <= 1, s > 0.
-__device__ __forceinline__ void epi_lean8f(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
-                                           float nz, float m1, float m1a, float m2, float m2a, float (&v)[8]) {
+// Lean staged-epilogue arithmetic for 8 channels: demod, [bias1 + lrelu], noise + bias + lrelu, branch-free.
+// lrelu(t) * s == max(t * s, t * s * a) for 0 <= a <= 1, s > 0, so the gains are folded into the per-channel vectors
+// when they are staged (lean_scale_*): vrs = demod * (pre ? m1 : m2), vb1 = bias1 * m1, vb2 = bias * m2, and the
+// caller passes nzs = noise * m2.  A disabled stage has m = a = 1 (max(t, t) = t).
+//   no first stage : t = acc * vrs + (nzs + vb2);                      out = max(t, t * a2)        (4 ops / element)
+//   first stage    : t1 = acc * vrs + vb1; y = max(t1, t1 * a1);  t2 = y * m2 + (nzs + vb2);  out = max(t2, t2 * a2)
+struct LeanK {
+  float m1, a1, m2, a2;
+  int pre;
+};
+__device__ __forceinline__ LeanK lean_consts(const ConvParams &p) {
+  LeanK k;
+  k.pre = p.pre_act != 0;
+  k.m1 = k.pre ? p.scale : 1.f;
+  k.a1 = k.pre ? p.alpha : 1.f;
+  k.m2 = p.act ? p.scale : 1.f;
+  k.a2 = p.act ? p.alpha : 1.f;
+  return k;
+}
+__device__ __forceinline__ float lean_scale_rs(const LeanK &k, float rs) { return rs * (k.pre ? k.m1 : k.m2); }
+__device__ __forceinline__ float lean_scale_b1(const LeanK &k, float b1) { return b1 * k.m1; }
+__device__ __forceinline__ float lean_scale_b2(const LeanK &k, float b2) { return b2 * k.m2; }
+
+template <bool PRE>
+__device__ __forceinline__ void epi_lean8f_t(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
+                                             float nzs, const LeanK &k, float (&v)[8]) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const float4 a = reinterpret_cast<const float4 *>(vrs)[h];
-    const float4 c1 = reinterpret_cast<const float4 *>(vb1)[h];
     const float4 c2 = reinterpret_cast<const float4 *>(vb2)[h];
-    const float aa[4] = {a.x, a.y, a.z, a.w}, b1[4] = {c1.x, c1.y, c1.z, c1.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+    const float aa[4] = {a.x, a.y, a.z, a.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w};
+    if constexpr (PRE) {
+      const float4 c1 = reinterpret_cast<const float4 *>(vb1)[h];
+      const float b1[4] = {c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], b1[e]);
-      const float y = fmaxf(t * m1, t * m1a);
-      const float t2 = y + (nz + b2[e]);
-      v[4 * h + e] = fmaxf(t2 * m2, t2 * m2a);
+      for (int e = 0; e < 4; ++e) {
+        const float t1 = fmaf(__uint_as_float(r[4 * h + e]), aa[e], b1[e]);
+        const float y = fmaxf(t1, t1 * k.a1);
+        const float t2 = fmaf(y, k.m2, nzs + b2[e]);
+        v[4 * h + e] = fmaxf(t2, t2 * k.a2);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], nzs + b2[e]);
+        v[4 * h + e] = fmaxf(t, t * k.a2);
+      }
     }
   }
 }
+__device__ __forceinline__ void epi_lean8f(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
+                                           float nzs, const LeanK &k, float (&v)[8]) {
+  if (k.pre) epi_lean8f_t<true>(r, vrs, vb1, vb2, nzs, k, v);
+  else epi_lean8f_t<false>(r, vrs, vb1, vb2, nzs, k, v);
+}
 __device__ __forceinline__ uint4 epi_lean8(const uint32_t *r, const float *vrs, const float *vb1, const float *vb2,
-                                           float nz, float m1, float m1a, float m2, float m2a) {
+                                           float nzs, const LeanK &k) {
   float v[8];
-  epi_lean8f(r, vrs, vb1, vb2, nz, m1, m1a, m2, m2a, v);
+  epi_lean8f(r, vrs, vb1, vb2, nzs, k, v);
   return pack8_bf16(v);
 }
 

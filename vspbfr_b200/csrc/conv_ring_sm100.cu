@@ -32,12 +32,13 @@ constexpr int kMaxSlots = 16;
 constexpr int kRingR = 4;
 
 struct RingUnit {
-  int b, strip, o0, L;
+  int b, strip, o0, L, slice;
 };
 
 // unit -> (sample, strip, chain, segment); the host guarantees every unit has L >= 1 rows.
 __device__ __forceinline__ RingUnit ring_decode(const ConvParams &p, long long u, int d_eff) {
   RingUnit r;
+  r.slice = (int)(u % p.rr_nslices); u /= p.rr_nslices;   // fastest: the slices of one strip segment run side by side (L2 reuse)
   const int seg = (int)(u % p.rr_segs); u /= p.rr_segs;
   const int chain = (int)(u % p.rr_chains); u /= p.rr_chains;
   r.strip = (int)(u % p.rr_strips); u /= p.rr_strips;
@@ -109,7 +110,7 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs * p.rr_nslices;
 
   if (warp == 0) {
     // ===================== activation rows: each input row of the strip is loaded once =====================
@@ -232,8 +233,7 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
     unsigned char *stage = o_buf + (warp - 4) * STAGE_BYTES;
     // 16-byte chunk swizzle of a staged row (must match the TMA store's swizzle mode: 64B or 32B rows)
     const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
-    const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
-    const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
+    const LeanK lk = lean_consts(p);
     int acc = 0;
     uint32_t acc_phase = 0, sbuf = 0;
     int cur_b = -1;
@@ -244,9 +244,12 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int c = et; c < BLOCK_N; c += 256) {
           const bool ok = c < p.cout;
-          vec_rs[c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)un.b * p.cout + c) : 1.f;
-          vec_b1[c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + c) : 0.f;
-          vec_b2[c] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+          const float rs = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)un.b * p.cout + c) : 1.f;
+          const float b1 = (ok && p.pre_bias) ? __ldg(p.pre_bias + c) : 0.f;
+          const float b2 = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+          vec_rs[c] = STAGED ? lean_scale_rs(lk, rs) : rs;      // staged path: activation gains folded in
+          vec_b1[c] = STAGED ? lean_scale_b1(lk, b1) : b1;
+          vec_b2[c] = STAGED ? lean_scale_b2(lk, b2) : b2;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_b = un.b;
@@ -302,7 +305,7 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
             for (int i = 0; i < CHUNK / 8; ++i)
               *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) =
                   epi_lean8(&r[8 * i], vec_rs + ch * CHUNK + 8 * i, vec_b1 + ch * CHUNK + 8 * i,
-                            vec_b2 + ch * CHUNK + 8 * i, nzv, m1, m1a, m2, m2a);
+                            vec_b2 + ch * CHUNK + 8 * i, nzv * lk.m2, lk);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -351,7 +354,7 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
 template <int C, bool STAGED>
 __global__ void __launch_bounds__(kRingThreads, 1)
 conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
-                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o) {
+                     const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ OutMaps omaps) {
   constexpr int NR = (512 / (3 * C));                // TMEM row slots: 10 (C = 16) or 5 (C = 32)
   constexpr int B_BYTES = C * 128;                    // one (kh, kw) weight tile of a 64-channel block
   constexpr int ROW_BYTES = C * 2;
@@ -381,7 +384,7 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (STAGED) tma_prefetch_desc(&tmap_o);
+    if (STAGED) tma_prefetch_desc(&omaps.m[0]);
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
@@ -403,7 +406,7 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs * p.rr_nslices;
 
   if (warp == 0) {
     // ===================== activation rows (kc slots per row) =====================
@@ -427,23 +430,24 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
     }
   } else if (warp == 2) {
     // ===================== weights, resident: smem tile order [cb][kw][kh] so that one kw is an [3C x 64] operand =====
-    int cur_g = -1;
+    int cur_key = -1;
     uint32_t res_ph = 0;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       const RingUnit un = ring_decode(p, u, d);
       const int g = p.groups == 1 ? 0 : un.b;
-      if (g == cur_g) continue;
+      const int key = g * p.rr_nslices + un.slice;
+      if (key == cur_key) continue;
       mbar_wait(b_empty, res_ph ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(b_full, b_total);
         for (int cb = 0; cb < kc; ++cb)
           for (int kw = 0; kw < 3; ++kw)
             for (int kh = 0; kh < 3; ++kh)
-              tma_load_4d(b_buf + (size_t)((cb * 3 + kw) * 3 + kh) * B_BYTES, &tmap_b, b_full, cb * kBlockK, 0,
-                          p.tap_w[kh * 3 + kw], g);
+              tma_load_4d(b_buf + (size_t)((cb * 3 + kw) * 3 + kh) * B_BYTES, &tmap_b, b_full, cb * kBlockK,
+                          un.slice * C, p.tap_w[kh * 3 + kw], g);
       }
       __syncwarp();
-      cur_g = g;
+      cur_key = key;
       res_ph ^= 1;
     }
   } else if (warp == 1) {
@@ -452,17 +456,20 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
     const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
     int aslot = 0, rslot = 0;
     uint32_t aph = 0, rph = 0, res_ph = 0;
-    int cur_g = -1;
+    int cur_key = -1;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       const RingUnit un = ring_decode(p, u, d);
-      const int g = p.groups == 1 ? 0 : un.b;
-      if (g != cur_g) {
+      const int key = (p.groups == 1 ? 0 : un.b) * p.rr_nslices + un.slice;
+      if (key != cur_key) {
         mbar_wait(b_full, res_ph);
         res_ph ^= 1;
-        cur_g = g;
+        cur_key = key;
       }
       bool release_b = u + gridDim.x >= units;
-      if (!release_b && p.groups != 1) release_b = ring_decode(p, u + gridDim.x, d).b != un.b;
+      if (!release_b) {
+        const RingUnit nx = ring_decode(p, u + gridDim.x, d);
+        release_b = ((p.groups == 1 ? 0 : nx.b) * p.rr_nslices + nx.slice) != key;
+      }
       for (int k = 0; k < un.L + 2; ++k) {
         mbar_wait(&acc_empty[rslot], rph ^ 1);        // the output rows that read this TMEM slot last time are done
         int s0 = aslot;
@@ -508,32 +515,67 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
     const long long plane = (long long)p.full_h * p.full_w;
     unsigned char *stage = o_buf + (warp - 4) * STAGE_BYTES;
     const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
-    const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
-    const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
+    const LeanK lk = lean_consts(p);
+    // channel slices: GEMM columns [slice*C, slice*C + C); with the pixel-shuffle mapping the column is
+    // class * shuffle_cout + channel, so a slice is (class, channel part)
+    const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+    const int parts = p.shuffle_cout ? p.shuffle_cout / C : 1;
+    const __nv_bfloat16 *res1 = static_cast<const __nv_bfloat16 *>(p.residual);
+    const __nv_bfloat16 *res2 = static_cast<const __nv_bfloat16 *>(p.residual2);
+    const bool has_res = STAGED && (res1 != nullptr || res2 != nullptr);
+    constexpr int PIECES = C / 8, PPR = 32 / PIECES;
     uint32_t sbuf = 0;
     long long rg0 = 0;                                  // running index of the unit's first input row
-    int cur_b = -1;
+    int cur_key = -1;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       const RingUnit un = ring_decode(p, u, d);
-      if (un.b != cur_b) {
+      const int cls = p.shuffle_cout ? un.slice / parts : 0;
+      const int c0 = p.shuffle_cout ? (un.slice % parts) * C : un.slice * C;
+      const int key = un.b * p.rr_nslices + un.slice;
+      if (key != cur_key) {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int c = et; c < C; c += 256) {
-          const bool ok = c < p.cout;
-          vec_rs[c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)un.b * p.cout + c) : 1.f;
-          vec_b1[c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + c) : 0.f;
-          vec_b2[c] = (ok && p.bias) ? __ldg(p.bias + c) : 0.f;
+          const bool ok = c0 + c < creal;
+          const float rs = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)un.b * creal + c0 + c) : 1.f;
+          const float b1 = (ok && p.pre_bias) ? __ldg(p.pre_bias + c0 + c) : 0.f;
+          const float b2 = (ok && p.bias) ? __ldg(p.bias + c0 + c) : 0.f;
+          vec_rs[c] = STAGED ? lean_scale_rs(lk, rs) : rs;      // staged path: activation gains folded in
+          vec_b1[c] = STAGED ? lean_scale_b1(lk, b1) : b1;
+          vec_b2[c] = STAGED ? lean_scale_b2(lk, b2) : b2;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        cur_b = un.b;
+        cur_key = key;
       }
       const int ow = un.strip * kBlockM + row;
       const bool pix_ok = ow < p.out_w;
+      const int fw = ow * p.os + (cls & 1);
       const int L = un.L;
+      // residuals (staged path): sector-coalesced warp loads of the 32-pixel x C-channel tile, one row ahead
+      uint4 pr1[PIECES], pr2[PIECES];
+      auto load_res = [&](int j) {
+        const int fh = (un.o0 + j * d) * p.os + (cls >> 1);
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+          const int px = un.strip * kBlockM + quad * 32 + i * PPR + lane / PIECES;
+          const bool ok = px < p.out_w;
+          const long long off = (((long long)un.b * p.full_h + fh) * p.full_w + px * p.os + (cls & 1)) * p.ldo + p.co_off +
+                                c0 + (lane % PIECES) * 8;
+          pr1[i] = (res1 && ok) ? __ldg(reinterpret_cast<const uint4 *>(res1 + off)) : make_uint4(0u, 0u, 0u, 0u);
+          pr2[i] = (res2 && ok) ? __ldg(reinterpret_cast<const uint4 *>(res2 + off)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (has_res && wg < L) load_res(wg);
+      // noise one row ahead as well (an HBM round trip per row would otherwise sit on the epilogue's critical path)
+      auto load_noise = [&](int j) -> float {
+        if (p.noise == nullptr || !pix_ok || j >= L) return 0.f;
+        return __ldg(p.noise + un.b * p.noise_bstride + (long long)((un.o0 + j * d) * p.os + (cls >> 1)) * p.full_w + fw);
+      };
+      float nz_next = load_noise(wg);
       for (int j = wg; j < L; j += 2) {
         const int oh = un.o0 + j * d;
-        const long long pix = (long long)oh * p.full_w + ow;
-        float nz = 0.f;
-        if (p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + un.b * p.noise_bstride + pix);
+        const long long pix = (long long)(oh * p.os + (cls >> 1)) * p.full_w + fw;
+        const float nz = nw * nz_next;
+        nz_next = load_noise(j + 2);
         const long long r0 = rg0 + j;
         const int s0 = (int)(r0 % NR), s1 = (int)((r0 + 1) % NR), s2 = (int)((r0 + 2) % NR);
         mbar_wait(&acc_full[s2], (uint32_t)(((r0 + 2) / NR) & 1));      // MMAs retire in order: rows r0, r0+1 are done too
@@ -573,20 +615,56 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
           ++sbuf;
           if (lane == 0) bulk_wait_group_read<1>();
           __syncwarp();
+          // activation in place (r holds fp32 bits), then the residual tiles are transposed through the staging
+          // buffer one after the other and added, so only one transposed tile is live at a time
 #pragma unroll
-          for (int i = 0; i < C / 8; ++i)
-            *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) =
-                epi_lean8(&r[8 * i], vec_rs + 8 * i, vec_b1 + 8 * i, vec_b2 + 8 * i, nz, m1, m1a, m2, m2a);
+          for (int i = 0; i < PIECES; ++i) {
+            float v[8];
+            epi_lean8f(&r[8 * i], vec_rs + 8 * i, vec_b1 + 8 * i, vec_b2 + 8 * i, nz * lk.m2, lk, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[8 * i + e] = __float_as_uint(v[e]);
+          }
+          if (has_res) {
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+#pragma unroll
+              for (int i = 0; i < PIECES; ++i) {
+                const int px = i * PPR + lane / PIECES;
+                const int swp = ROW_BYTES == 64 ? ((px >> 1) & 3) : ((px >> 2) & 1);
+                *reinterpret_cast<uint4 *>(buf + px * ROW_BYTES + (((lane % PIECES) ^ swp) << 4)) = which == 0 ? pr1[i] : pr2[i];
+              }
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < PIECES; ++i) {
+                const uint4 own = *reinterpret_cast<const uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4));
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&own);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  r[8 * i + 2 * e] = __float_as_uint(__uint_as_float(r[8 * i + 2 * e]) + f.x);
+                  r[8 * i + 2 * e + 1] = __float_as_uint(__uint_as_float(r[8 * i + 2 * e + 1]) + f.y);
+                }
+              }
+              __syncwarp();
+            }
+            if (j + 2 < L) load_res(j + 2);
+          }
+#pragma unroll
+          for (int i = 0; i < PIECES; ++i) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * i + e]);
+            *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tmap_o, buf, (int)p.co_off, un.strip * kBlockM + quad * 32, oh, un.b);
+            tma_store_4d(&omaps.m[cls], buf, (int)p.co_off + c0, un.strip * kBlockM + quad * 32, oh, un.b);
             bulk_commit_group();
           }
         } else {
-          // direct stores (fp32 NCHW or residual epilogues): same arithmetic as epi_compute on the summed accumulator
+          // direct stores (fp32 NCHW outputs / unaligned layouts): same arithmetic on the summed accumulator
           float v[C];
-          const bool live = pix_ok;
 #pragma unroll
           for (int i = 0; i < C; ++i) {
             float xv = __uint_as_float(r[i]) * vec_rs[i];
@@ -594,22 +672,22 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
             xv = epi_act(xv + nz + vec_b2[i], p.act, p.alpha, p.scale);
             v[i] = xv;
           }
-          if (live && (p.residual || p.residual2)) {
+          if (pix_ok && (p.residual || p.residual2)) {
 #pragma unroll
             for (int i = 0; i < C; ++i) {
-              if (i >= p.cout) break;
+              if (c0 + i >= creal) break;
               if (!p.out_nhwc) {
-                const long long off = ((long long)un.b * p.cout + i) * plane + pix;
+                const long long off = ((long long)un.b * creal + c0 + i) * plane + pix;
                 if (p.residual) v[i] += __ldg(static_cast<const float *>(p.residual) + off);
                 if (p.residual2) v[i] += __ldg(static_cast<const float *>(p.residual2) + off);
               } else {
-                const long long off = ((long long)un.b * plane + pix) * p.ldo + p.co_off + i;
+                const long long off = ((long long)un.b * plane + pix) * p.ldo + p.co_off + c0 + i;
                 if (p.residual) v[i] += __bfloat162float(static_cast<const __nv_bfloat16 *>(p.residual)[off]);
                 if (p.residual2) v[i] += __bfloat162float(static_cast<const __nv_bfloat16 *>(p.residual2)[off]);
               }
             }
           }
-          epi_store_direct<C>(p, 0, p.cout, un.b, pix, plane, pix_ok, v);
+          epi_store_direct<C>(p, c0, creal, un.b, pix, plane, pix_ok, v);
         }
       }
       rg0 += L + 2;
@@ -636,7 +714,9 @@ int launch_ringfold(const ConvParams &p, const void *x, const void *wq, int64_t 
     VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb;
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
   {
     uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)p.batch};
     uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * in_w * 2, (uint64_t)p.cin * in_w * in_h * 2};
@@ -655,19 +735,29 @@ int launch_ringfold(const ConvParams &p, const void *x, const void *wq, int64_t 
       return rc;
   }
   if (STAGED) {
-    uint64_t dims[4] = {(uint64_t)(p.co_off + p.cout), (uint64_t)p.full_w, (uint64_t)p.full_h, (uint64_t)p.batch};
-    uint64_t strides[4] = {0, (uint64_t)p.ldo * 2, (uint64_t)p.ldo * p.full_w * 2,
-                           (uint64_t)p.ldo * p.full_w * p.full_h * 2};
-    uint32_t box[4] = {(uint32_t)C, 32, 1, 1};
-    if (int rc = encode_tma(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.out, dims, strides, box, nullptr,
-                            C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
-      return rc;
-  } else {
-    to = ta;
+    // one map per output parity class (pixel-shuffle: class origin in the base pointer, pixel strides x os)
+    const int ncls = p.shuffle_cout ? 4 : 1;
+    const int os = p.os;
+    const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+    for (int cls = 0; cls < ncls; ++cls) {
+      const int oh0 = cls >> 1, ow0 = cls & 1;
+      const __nv_bfloat16 *base = static_cast<const __nv_bfloat16 *>(p.out) + ((long long)oh0 * p.full_w + ow0) * p.ldo;
+      uint64_t dims[4] = {(uint64_t)(p.co_off + creal), (uint64_t)((p.full_w - ow0 + os - 1) / os),
+                          (uint64_t)((p.full_h - oh0 + os - 1) / os), (uint64_t)p.batch};
+      uint64_t strides[4] = {0, (uint64_t)p.ldo * 2 * os, (uint64_t)p.ldo * p.full_w * 2 * os,
+                             (uint64_t)p.ldo * p.full_w * p.full_h * 2};
+      uint32_t box[4] = {(uint32_t)C, 32, 1, 1};
+      if (int rc = encode_tma(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, nullptr,
+                              C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B))
+        return rc;
+    }
   }
-  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
-  const long long grid = units < num_sms() ? units : num_sms();
-  kern<<<(unsigned)grid, kRingThreads, smem_bytes, stream>>>(p, ta, tb, to);
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs * p.rr_nslices;
+  // a CTA keeps its channel slice (weights stay resident): grid = a multiple of the slice count
+  long long grid = (num_sms() / p.rr_nslices) * p.rr_nslices;
+  if (grid < p.rr_nslices) grid = p.rr_nslices;
+  if (units < grid) grid = units;
+  kern<<<(unsigned)grid, kRingThreads, smem_bytes, stream>>>(p, ta, tb, om);
   return check_launch("conv_ringfold_kernel");
 }
 
@@ -714,7 +804,7 @@ int launch_ring(const ConvParams &p, const void *x, const void *wq, int64_t in_h
   } else {
     to = ta;
   }
-  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs;
+  const long long units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_segs * p.rr_nslices;
   const long long grid = units < num_sms() ? units : num_sms();
   kern<<<(unsigned)grid, kRingThreads, smem_bytes, stream>>>(p, ta, tb, to);
   return check_launch("conv_ring_kernel");
@@ -737,12 +827,21 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
                          int64_t cout_pad, int taps_total, int dil, cudaStream_t stream) {
   static const bool disabled = getenv("VSP_NO_RING") != nullptr;
   static const bool no_stage = getenv("VSP_RING_NO_TMA_STORE") != nullptr;
-  if (disabled) return -1;
-  if (p.stride != 1 || p.os != 1 || p.oo_h != 0 || p.oo_w != 0) return -1;
-  if (p.out_w < kBlockM || p.out_w != in_w || p.out_h != in_h || p.full_w != p.out_w || p.full_h != p.out_h) return -1;
-  if (p.ntaps != 9 && p.ntaps != 1) return -1;
   static const bool no_fold = getenv("VSP_NO_FOLD") != nullptr;
-  const bool fold = !no_fold && p.ntaps == 9 && p.cout <= 32 && p.kc <= 2;
+  static const bool no_slices = getenv("VSP_NO_FOLD_SLICES") != nullptr;
+  if (disabled) return -1;
+  if (p.stride != 1 || p.oo_h != 0 || p.oo_w != 0) return -1;
+  if (p.out_w < kBlockM || p.out_w != in_w || p.out_h != in_h) return -1;
+  if (p.ntaps != 9 && p.ntaps != 1) return -1;
+  // kh-folded kernel: Cout <= 32 directly, wider layers (and the pixel-shuffle up-convolution) as 32-channel slices
+  // (measured: four slices win clearly — 128->128 @256^2 172 -> 148 us, fused 64->32 up-conv 428 -> 328 us; two slices
+  // of a 64-channel block only tie with the resident nine-tap ring, eight slices lose to the generic kernel)
+  const bool fold = !no_fold && p.ntaps == 9 && p.kc <= 2 &&
+                    (p.cout <= 32 || (!no_slices && p.cout % 32 == 0 && p.cout <= 128 && !(p.kc == 1 && p.cout == 64) &&
+                                      (p.shuffle_cout == 0 || p.shuffle_cout % 32 == 0)));
+  if (p.shuffle_cout ? !(fold && p.os == 2 && p.full_w == 2 * p.out_w && p.full_h == 2 * p.out_h)
+                     : !(p.os == 1 && p.full_w == p.out_w && p.full_h == p.out_h))
+    return -1;
   if (!fold && (p.kc != 1 || p.cout > 64)) return -1;
   const int taps = p.ntaps;
   const int halo = taps == 9 ? 1 : 0;
@@ -758,11 +857,18 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   }
   int bn = 16;
   while (bn < p.cout) bn <<= 1;
+  p.rr_nslices = 1;
+  if (fold && p.cout > 32) {
+    bn = 32;
+    p.rr_nslices = p.cout / 32;
+  }
   p.halo_d = d;
   p.halo_w = taps == 9 ? ((kBlockM + 2 * d + 7) & ~7) : kBlockM;
-  p.rr_staged = (!no_stage && p.out_nhwc && (p.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
-                 p.residual == nullptr && p.residual2 == nullptr && p.alpha >= 0.f && p.alpha <= 1.f &&
+  p.rr_staged = (!no_stage && p.out_nhwc && (p.ldo % 8) == 0 && (p.co_off % 8) == 0 &&
+                 (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                 ((p.residual == nullptr && p.residual2 == nullptr) || fold) && p.alpha >= 0.f && p.alpha <= 1.f &&
                  (p.scale > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
+  if (p.shuffle_cout && !p.rr_staged) return -1;
   const int slot = p.halo_w * 128;
   const int b_bytes = (taps * p.kc * bn * 128 + 1023) & ~1023;
   const int chunk = bn < 32 ? bn : 32;
@@ -777,7 +883,7 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   p.rr_chains = d;
   // segments: minimise waves x (rows per unit + per-unit overhead)
   const int rows_chain = p.out_h / d;
-  const long long base_units = (long long)p.batch * p.rr_strips * p.rr_chains;
+  const long long base_units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_nslices;
   double best = 1e300;
   int best_L = rows_chain;
   for (int segs = 1; segs <= rows_chain; ++segs) {

@@ -130,8 +130,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   const int et = threadIdx.x - 64;
   float *vec_rs = epi_vec, *vec_b1 = epi_vec + 2 * BLOCK_N, *vec_b2 = epi_vec + 4 * BLOCK_N;
   const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
-  const float m1 = p.pre_act ? p.scale : 1.f, m1a = p.pre_act ? p.scale * p.alpha : 1.f;
-  const float m2 = p.act ? p.scale : 1.f, m2a = p.act ? p.scale * p.alpha : 1.f;
+  const LeanK lk = lean_consts(p);
   const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
   unsigned char *stage = o_buf + (warp - 2) * C::NBUF * C::SBUF_BYTES;
   const long long plane = (long long)p.full_h * p.full_w;
@@ -155,9 +154,9 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
       const int n = nbase + c;
       const int cr = p.shuffle_cout ? n % p.shuffle_cout : n;
       const bool ok = n < p.cout;
-      vec_rs[acc * BLOCK_N + c] = (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * creal + cr) : 1.f;
-      vec_b1[acc * BLOCK_N + c] = (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f;
-      vec_b2[acc * BLOCK_N + c] = (ok && p.bias) ? __ldg(p.bias + cr) : 0.f;
+      vec_rs[acc * BLOCK_N + c] = lean_scale_rs(lk, (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * creal + cr) : 1.f);
+      vec_b1[acc * BLOCK_N + c] = lean_scale_b1(lk, (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f);
+      vec_b2[acc * BLOCK_N + c] = lean_scale_b2(lk, (ok && p.bias) ? __ldg(p.bias + cr) : 0.f);
     }
     // noise of this thread's pixel in every output class of the tile, fetched before the accumulator wait
     float nzc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -267,7 +266,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
 #pragma unroll
       for (int i = 0; i < PIECES; ++i) {
         float v[8];
-        epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz, m1, m1a, m2, m2a, v);
+        epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz * lk.m2, lk, v);
         if (has_res) add2_bf16x8(v, own1[i], own2[i]);
         *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
       }

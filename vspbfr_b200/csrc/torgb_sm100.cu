@@ -81,31 +81,50 @@ torgb_warp_kernel(const uint4 *__restrict__ x, const float *__restrict__ w, cons
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int cg = c / 8;
-  // kWarpPix consecutive pixels per warp: amortises the per-block weight staging above
+  // kWarpPix consecutive pixels per warp (amortises the per-block weight staging above), four at a time so that
+  // every lane keeps 4 x cg/32 independent 128-bit loads in flight
   const long long p0 = ((long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * kWarpPix;
-  for (int i = 0; i < kWarpPix; ++i) {
-    const long long p = p0 + i;
-    if (p >= hw) return;
-    const uint4 *xp = x + (b * hw + p) * cg;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int i0 = 0; i0 < kWarpPix; i0 += 4) {
+    if (p0 + i0 >= hw) return;
+    float acc[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
     for (int g = lane; g < cg; g += 32) {
-      const uint4 v = __ldg(xp + g);
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        v[q] = (p0 + i0 + q < hw) ? __ldg(x + (b * hw + p0 + i0 + q) * cg + g) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const uint32_t word = (&v.x)[e >> 1];
-        const float xv = __uint_as_float((e & 1) ? (word & 0xFFFF0000u) : (word << 16));
         const float4 wv = wm[g * 8 + e];
-        a0 = fmaf(xv, wv.x, a0);
-        a1 = fmaf(xv, wv.y, a1);
-        a2 = fmaf(xv, wv.z, a2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t word = (&v[q].x)[e >> 1];
+          const float xv = __uint_as_float((e & 1) ? (word & 0xFFFF0000u) : (word << 16));
+          acc[q][0] = fmaf(xv, wv.x, acc[q][0]);
+          acc[q][1] = fmaf(xv, wv.y, acc[q][1]);
+          acc[q][2] = fmaf(xv, wv.z, acc[q][2]);
+        }
       }
     }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane < 3) {
-      const long long off = (b * 3 + lane) * hw + p;
-      float v = (lane == 0 ? a0 : (lane == 1 ? a1 : a2)) + (bias ? __ldg(bias + lane) : 0.f);
-      if (skip) v += __ldg(skip + off);
-      out[off] = v;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) acc[q][o] = warp_sum(acc[q][o]);
+    if (lane < 12) {
+      const int q = lane / 3, o = lane % 3;
+      const long long p = p0 + i0 + q;
+      if (p < hw) {
+        float v = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+          for (int oo = 0; oo < 3; ++oo) v = (qq == q && oo == o) ? acc[qq][oo] : v;
+        const long long off = (b * 3 + o) * hw + p;
+        v += bias ? __ldg(bias + o) : 0.f;
+        if (skip) v += __ldg(skip + off);
+        out[off] = v;
+      }
     }
   }
 }
