@@ -92,8 +92,8 @@ def main():
 
     def step(sync=True):
         import contextlib
-        nosync_g = generator.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
-        nosync_d = discriminator.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+        def nosync(m):      # a fresh context per use (generator-based context managers are single-shot)
+            return m.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
         with torch.no_grad():
             _, de_feats = decoder([codes], input_is_latent=True, return_features=True)
         # ---- D
@@ -102,7 +102,7 @@ def main():
         noise = mixing_noise(args.batch, 512, 0.9, dev)
         with torch.no_grad():
             restored = generator(low_img, de_feats, codes, noise)
-        with nosync_d:
+        with nosync(discriminator):
             fake_pred = discriminator(restored.detach())
             real_pred = discriminator(real_img)
             d_loss = d_logistic_loss(real_pred, fake_pred)
@@ -111,7 +111,7 @@ def main():
         d_optim.step()
         # ---- R1 (forced every step here: the double-backward path is what this benchmark is about)
         tmp = real_img.detach().clone().requires_grad_(True)
-        with nosync_d:
+        with nosync(discriminator):
             real_pred = discriminator(tmp)
             r1 = d_r1_loss(real_pred, tmp)
             discriminator.zero_grad()
@@ -121,7 +121,7 @@ def main():
         requires_grad(generator, True)
         requires_grad(discriminator, False)
         noise = mixing_noise(args.batch, 512, 0.9, dev)
-        with nosync_g:
+        with nosync(generator):
             restored = generator(low_img, de_feats, codes, noise)
             g_loss = g_nonsaturating_loss(discriminator(restored))
             generator.zero_grad()
