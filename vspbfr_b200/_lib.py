@@ -170,6 +170,8 @@ SIGNATURES = {
     "vsp_conv_transpose2d_s2_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                              c_int, c_int, c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_blur_sep_nhwc_bf16": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_int64, c_int64, c_int64,
+                                       c_int64, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(ConvEpilogue), c_void_p]),
     "vsp_scale_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "vsp_conv2d_branches_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                          c_int, POINTER(c_int), c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),

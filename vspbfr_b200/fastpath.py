@@ -35,6 +35,7 @@ _UP_FUSED_MAX_CIN = int(os.environ.get("VSP_UP_FUSED_MAX_CIN", "256"))
 _LOWRES_PIXELS = int(os.environ.get("VSP_LOWRES_PIXELS", "1024"))
 # SMART layers up to this width run their four dilated branches as one launch of the generic kernel
 _BRANCH_MAX_W = int(os.environ.get("VSP_BRANCH_MAX_W", "64"))
+_SEP_BLUR = os.environ.get("VSP_NO_SEP_BLUR") is None
 
 
 def _cached(owner, tag, tensors, build):
@@ -131,6 +132,27 @@ def _modulation(lin, style):
     return hit if hit is not None else _linear(lin, style)
 
 
+_sep_cache: dict = {}
+
+
+def _separable_taps(kernel):
+    """(fy, fx) ctypes float arrays with kernel == outer(fy, fx), or None.  Factorised once per filter tensor on the
+    host (one device->host copy, cached on data_ptr/version): the model's blur filters never change."""
+    key = (kernel.data_ptr(), kernel._version, tuple(kernel.shape), str(kernel.device))
+    hit = _sep_cache.get(key)
+    if hit is None:
+        k = kernel.detach().double().cpu()
+        kh, kw = k.shape
+        res = False
+        if kh <= 4 and kw <= 4 and float(k.abs().max()) > 0:
+            j0, i0 = divmod(int(k.abs().argmax()), kw)
+            fx, fy = k[j0, :].clone(), k[:, i0] / k[j0, i0]
+            if float((torch.outer(fy, fx) - k).abs().max()) <= 1e-7 * float(k.abs().max()):
+                res = ((ctypes.c_float * kh)(*[float(v) for v in fy]), (ctypes.c_float * kw)(*[float(v) for v in fx]))
+        hit = _sep_cache[key] = (res, kernel)      # keep the tensor alive so the key cannot be recycled
+    return hit[0] or None
+
+
 def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
     """NHWC bf16 up-FIR-down with an optional fused epilogue."""
     n, h, w, c = x.shape
@@ -140,6 +162,13 @@ def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
     ow = lib.vsp_upfirdn2d_out_size(w, kw, up, down, pad[0], pad[1])
     y = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=x.device)
     e, keep = epi if epi is not None else (None, None)
+    taps = _separable_taps(kernel) if (up == 1 and down == 1 and _SEP_BLUR) else None
+    if taps is not None:
+        with torch.cuda.device(x.device):
+            rc = lib.vsp_blur_sep_nhwc_bf16(ptr(x), taps[0], taps[1], ptr(y), n, h, w, c, kh, kw, pad[0], pad[1], pad[0],
+                                            pad[1], ctypes.byref(e) if e is not None else None, stream_ptr())
+        _lib.check(rc, "blur_sep_nhwc_bf16")
+        return y
     with torch.cuda.device(x.device):
         rc = lib.vsp_upfirdn2d_nhwc_bf16(ptr(x), ptr(kernel), ptr(y), n, h, w, c, kh, kw, up, up, down, down,
                                          pad[0], pad[1], pad[0], pad[1],
