@@ -270,7 +270,8 @@ def main():
         result["roofline"] = {
             "bound": "tensor", "kernel": "tcgen05 convolution kernels (conv_fprop / conv_ring / conv_ringfold / conv_rowhalo), all launches of one micro-batch",
             "achieved": tflops, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": tflops / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+            "frac": tflops / pk["bf16_tflops_sustained"], "traffic": conv_traffic(micro),
+            "peak_source": pk["source"] + " (sustained)",
             "launches_per_microbatch": conv["launches"], "algorithmic_gflop_per_image": step_flops / micro / 1e9,
             "share_of_step": conv["seconds"] / (t_res / args.steps / n_micro),
         }
@@ -281,6 +282,16 @@ def main():
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def conv_traffic(micro):
+    """DRAM bytes (read + written) of all tcgen05 conv launches of one micro-batch, from the committed ncu launch list
+    (profiles/r01_launches_microbatch32_v20.*: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over
+    tools/prof_step.py 32); None when the bench runs at another micro-batch size."""
+    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v20.json")
+    if micro != 32 or not os.path.exists(path):
+        return None
+    return json.load(open(path))["conv_kernels"]["dram_bytes"]
 
 
 def _time_launch(fn, iters=10):
