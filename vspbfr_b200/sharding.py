@@ -53,3 +53,46 @@ def restore_sharded(net, decoder, low_imgs, codes, noise_z, rank: int, world: in
         restored, _ = fastpath.restore_faces(net, decoder, low_imgs[s:e], codes[s:e], [noise_z[s:e]])
         out[s - lo:e - lo] = restored
     return lo, hi, out
+
+
+def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int = 32, device=None):
+    """Restore a job whose inputs and outputs live in (pinned) HOST memory: micro-batches are copied in on one
+    stream, processed on the current stream and copied out on a third, so the PCIe transfers of batch m+1 / m-1
+    overlap the kernels of batch m (restoration_test.py:125-157 moves every batch synchronously).
+
+    low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S] (filled asynchronously; the call
+    returns after the last device->host copy has been enqueued AND completed)."""
+    import torch
+
+    from . import fastpath
+
+    device = torch.device(device if device is not None else torch.cuda.current_device())
+    n = low_h.shape[0]
+    compute = torch.cuda.current_stream(device)
+    h2d, d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    spans = list(micro_batches(0, n, micro))
+
+    def stage_in(span):
+        s, e = span
+        with torch.cuda.stream(h2d):
+            t = tuple(x[s:e].to(device, non_blocking=True) for x in (low_h, codes_h, noise_z_h))
+            ev = torch.cuda.Event()
+            ev.record(h2d)
+        return t, ev
+
+    nxt = stage_in(spans[0]) if spans else None
+    for i, (s, e) in enumerate(spans):
+        (lo, co, zz), ready = nxt
+        nxt = stage_in(spans[i + 1]) if i + 1 < len(spans) else None      # prefetch while this batch computes
+        compute.wait_event(ready)
+        for t in (lo, co, zz):
+            t.record_stream(compute)
+        restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
+        done = torch.cuda.Event()
+        done.record(compute)
+        d2h.wait_event(done)
+        restored.record_stream(d2h)
+        with torch.cuda.stream(d2h):
+            out_h[s:e].copy_(restored, non_blocking=True)
+    compute.wait_stream(d2h)
+    return out_h
