@@ -166,7 +166,8 @@ int vsp_weight_sumsq_f32(const float *w, float *wsq, int64_t cout, int64_t cin, 
  * Grouped EqualLinear (models/RestoreNet.py:142-176 without activation): every modulation linear of a network
  * pass in one launch.  Problem j:  y[y_off_j + b*out_dim_j + o] = wscale_j * sum_i w_j[o,i] * x[x_off_j + b*x_bstride + i]
  *                                                               + bscale_j * bias_j[o]
- * `descs_dev` / `row_start_dev` live in device memory; row_start[j] = sum of out_dim of problems < j.
+ * `descs_dev` / `row_start_dev` live in device memory; row_start[j] = sum over problems < j of out_dim rounded up to
+ * a multiple of 8 (a block of 8 warps works on 8 rows of one problem); total_rows = that sum over all problems.
  * w_j must be 16-byte aligned when in_dim % 4 == 0, and x_off_j a multiple of 4 floats.
  */
 typedef struct vsp_linear_desc {
@@ -176,6 +177,7 @@ typedef struct vsp_linear_desc {
   int64_t y_off;      /* element offset of this problem's [batch, out_dim] block in y */
   int32_t in_dim, out_dim;
   float wscale, bscale;
+  int64_t x_bstride;  /* elements between samples of this problem's input rows; 0 = the call's x_bstride */
 } vsp_linear_desc;
 int vsp_grouped_linear_f32(const vsp_linear_desc *descs_dev, const int *row_start_dev, int n_problems,
                            int total_rows, const float *x, int64_t x_bstride, float *y, int batch, void *stream);

@@ -179,10 +179,22 @@ def test_grouped_linear_matches_equal_linear():
     for batch in (1, 3, 8, 11):
         styles = torch.randn(batch, 6, 512, device=DEV)
         bank = fp.ModulationBank([(m, idx) for m, idx in zip(lins, (0, 5, 2, 2))])
-        got = bank(styles)
+        got, _ = bank(styles)
         for m, idx in zip(lins, (0, 5, 2, 2)):
             want = m(styles[:, idx])
             np.testing.assert_allclose(got[id(m)].cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-5)
+    # with demodulation problems attached: d[b,o] = rsqrt(scale^2 * sum_i s^2 * sum_t W^2 + eps) (models/RestoreNet.py:513-516)
+    w1 = torch.randn(48, 64, 3, 3, device=DEV)
+    w2 = torch.randn(20, 130, 3, 3, device=DEV)
+    owners = [object(), object()]
+    bank = fp.ModulationBank([(lins[0], 1, (owners[0], lambda: mc.weight_sumsq(w1), 0.05, 1e-8)), (lins[1], 0),
+                              (lins[3], 3, (owners[1], lambda: mc.weight_sumsq(w2), 0.2, 1e-8))])
+    styles = torch.randn(5, 4, 512, device=DEV)
+    s_out, d_out = bank(styles)
+    for lin, w, owner, idx, sc in ((lins[0], w1, owners[0], 1, 0.05), (lins[3], w2, owners[1], 3, 0.2)):
+        sv = lin(styles[:, idx])
+        want = torch.rsqrt(((sc * w[None] * sv[:, None, :, None, None]) ** 2).sum(dim=(2, 3, 4)) + 1e-8)
+        np.testing.assert_allclose(d_out[id(owner)].cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-4)
 
 
 @pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130)])

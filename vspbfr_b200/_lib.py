@@ -131,6 +131,7 @@ class LinearDesc(Structure):
         ("out_dim", ctypes.c_int32),
         ("wscale", c_float),
         ("bscale", c_float),
+        ("x_bstride", c_int64),
     ]
 
 

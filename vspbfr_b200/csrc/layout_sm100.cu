@@ -43,6 +43,30 @@ nchw_to_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ scale
   }
 }
 
+// ---- NCHW fp32 -> NHWC bf16 for c_pad == 8 (the RGB network input): one thread per pixel, coalesced plane reads,
+// one 128-bit store; the 64 x 64 transpose tile above would be 95 % padding.
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc8_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc, uint4 *__restrict__ y,
+                     int c, long long hw, long long total) {
+  for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+    const long long n = idx / hw, pp = idx % hw;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = 0.f;
+      if (i < c) {
+        v[i] = ld_stream_f1(x + (n * c + i) * hw + pp);
+        if (scale_nc != nullptr) v[i] *= __ldg(scale_nc + n * c + i);
+      }
+    }
+    uint4 o;
+    __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) oh[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    y[idx] = o;
+  }
+}
+
 // ---- NHWC bf16 -> NCHW fp32
 __global__ void __launch_bounds__(kThreads)
 nhwc_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, long long c,
@@ -275,6 +299,13 @@ extern "C" int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, 
   if (n == 0 || c_pad == 0 || hw == 0) return 0;
   VSP_REQUIRE(x && y, "nchw->nhwc: null pointer");
   VSP_REQUIRE(n <= 65535 && ceil_div64(c_pad, 64) <= 65535, "nchw->nhwc: batch/channel extent too large");
+  if (c_pad == 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    const long long total = n * hw;
+    long long nb = ceil_div64(total, kThreads);
+    if (nb > (long long)num_sms() * 32) nb = (long long)num_sms() * 32;
+    nchw_to_nhwc8_kernel<<<(unsigned)nb, kThreads, 0, stream>>>(x, scale_nc, static_cast<uint4 *>(y), (int)c, hw, total);
+    return check_launch("nchw_to_nhwc8_kernel");
+  }
   dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
   nchw_to_nhwc_kernel<<<grid, kThreads, 0, stream>>>(x, scale_nc, static_cast<__nv_bfloat16 *>(y), c, hw, c_pad);
   return check_launch("nchw_to_nhwc_kernel");

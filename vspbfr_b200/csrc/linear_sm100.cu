@@ -12,51 +12,67 @@ namespace vsp {
 namespace {
 
 constexpr int kLinThreads = 256;
-constexpr int kLinB = 8;   // samples accumulated per pass over a weight row
+constexpr int kLinRows = 8;     // output rows per block (one per warp)
+constexpr int kLinB = 8;        // samples accumulated per pass
+constexpr int kLinK = 512;      // style elements staged in shared memory per pass
 
+// One block = kLinRows consecutive output rows of ONE problem (the host pads every problem to a multiple of
+// kLinRows rows in `row_start`), so the block's warps share the problem's style rows: they are staged in shared
+// memory in [kLinB x kLinK] slabs (coalesced) and every warp dots its own weight row (streamed once per slab of
+// samples, 128-bit loads) against them.
 __global__ void __launch_bounds__(kLinThreads)
 grouped_linear_kernel(const vsp_linear_desc *__restrict__ descs, const int *__restrict__ row_start, int n_problems,
-                      int total_rows, const float *__restrict__ x, long long x_bstride, float *__restrict__ y, int batch) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (kLinThreads / 32) + (threadIdx.x >> 5);
-  if (row >= total_rows) return;
-  // problem of this row: largest j with row_start[j] <= row
+                      const float *__restrict__ x, long long x_bstride, float *__restrict__ y, int batch) {
+  __shared__ __align__(16) float xs[kLinB][kLinK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * kLinRows;
   int lo = 0, hi = n_problems - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(row_start + mid) <= row) lo = mid; else hi = mid - 1;
+    if (__ldg(row_start + mid) <= row0) lo = mid; else hi = mid - 1;
   }
   const vsp_linear_desc d = descs[lo];
-  const int o = row - __ldg(row_start + lo);
-  const float *w = d.w + (long long)o * d.in_dim;
+  const int o = row0 - __ldg(row_start + lo) + warp;
+  const bool live = o < d.out_dim;
+  const float *w = d.w + (long long)(live ? o : 0) * d.in_dim;
   const float *xb = x + d.x_off;
-  const float bias = d.bias ? __ldg(d.bias + o) * d.bscale : 0.f;
+  if (d.x_bstride != 0) x_bstride = d.x_bstride;
+  const float bias = (live && d.bias) ? __ldg(d.bias + o) * d.bscale : 0.f;
   for (int b0 = 0; b0 < batch; b0 += kLinB) {
     float acc[kLinB];
 #pragma unroll
     for (int q = 0; q < kLinB; ++q) acc[q] = 0.f;
-    if ((d.in_dim & 3) == 0) {
-      for (int i = lane * 4; i < d.in_dim; i += 128) {
-        const float4 wv = __ldg(reinterpret_cast<const float4 *>(w + i));
+    for (int k0 = 0; k0 < d.in_dim; k0 += kLinK) {
+      const int kn = min(kLinK, d.in_dim - k0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < kLinB * kLinK; i += kLinThreads) {
+        const int q = i / kLinK, k = i % kLinK;
+        xs[q][k] = (b0 + q < batch && k < kn) ? __ldg(xb + (long long)(b0 + q) * x_bstride + k0 + k) : 0.f;
+      }
+      __syncthreads();
+      if (live) {
+        for (int k = lane * 4; k < kn; k += 128) {
+          float4 wv;
+          if (k + 3 < kn && ((reinterpret_cast<uintptr_t>(w + k0 + k) & 15) == 0)) {
+            wv = __ldg(reinterpret_cast<const float4 *>(w + k0 + k));
+          } else {
+            wv.x = __ldg(w + k0 + k);
+            wv.y = k + 1 < kn ? __ldg(w + k0 + k + 1) : 0.f;
+            wv.z = k + 2 < kn ? __ldg(w + k0 + k + 2) : 0.f;
+            wv.w = k + 3 < kn ? __ldg(w + k0 + k + 3) : 0.f;
+          }
 #pragma unroll
-        for (int q = 0; q < kLinB; ++q)
-          if (b0 + q < batch) {
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xb + (long long)(b0 + q) * x_bstride + i));
+          for (int q = 0; q < kLinB; ++q) {
+            const float4 xv = *reinterpret_cast<const float4 *>(&xs[q][k]);
             acc[q] = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, acc[q]))));
           }
-      }
-    } else {
-      for (int i = lane; i < d.in_dim; i += 32) {
-        const float wv = __ldg(w + i);
-#pragma unroll
-        for (int q = 0; q < kLinB; ++q)
-          if (b0 + q < batch) acc[q] = fmaf(wv, __ldg(xb + (long long)(b0 + q) * x_bstride + i), acc[q]);
+        }
       }
     }
 #pragma unroll
     for (int q = 0; q < kLinB; ++q) {
       const float v = warp_sum(acc[q]);
-      if (lane == 0 && b0 + q < batch) y[d.y_off + (long long)(b0 + q) * d.out_dim + o] = v * d.wscale + bias;
+      if (live && lane == 0 && b0 + q < batch) y[d.y_off + (long long)(b0 + q) * d.out_dim + o] = v * d.wscale + bias;
     }
   }
 }
@@ -73,9 +89,9 @@ extern "C" int vsp_grouped_linear_f32(const vsp_linear_desc *descs_dev, const in
   VSP_REQUIRE(descs_dev && row_start_dev && x && y, "grouped_linear: null pointer");
   VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (x_bstride & 3) == 0,
               "grouped_linear: x must be 16-byte aligned with a row stride that is a multiple of 4 floats");
-  const int rows_per_block = kLinThreads / 32;
-  const unsigned blocks = (unsigned)((total_rows + rows_per_block - 1) / rows_per_block);
+  VSP_REQUIRE(total_rows % kLinRows == 0, "grouped_linear: row_start must pad every problem to a multiple of 8 rows");
+  const unsigned blocks = (unsigned)(total_rows / kLinRows);
   grouped_linear_kernel<<<blocks, kLinThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      descs_dev, row_start_dev, n_problems, total_rows, x, x_bstride, y, batch);
+      descs_dev, row_start_dev, n_problems, x, x_bstride, y, batch);
   return check_launch("grouped_linear_kernel");
 }

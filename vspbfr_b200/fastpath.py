@@ -54,7 +54,7 @@ def _cached(owner, tag, tensors, build):
 def clear_cache():
     _cache.clear()
     _bank_cache.clear()
-    _mod_ctx.clear()
+    _bank_clear()
 
 
 def _linear(lin, x):
@@ -65,58 +65,140 @@ def _linear(lin, x):
 
 
 class ModulationBank:
-    """All style-modulation linears of one network pass as a single grouped launch (vsp_grouped_linear_f32).
+    """All style-modulation linears of one network pass as a single grouped launch (vsp_grouped_linear_f32), followed
+    by every demodulation vector d[b,o] = rsqrt(scale^2 * sum_i s[b,i]^2 * wsq[o,i] + eps) as a second grouped launch
+    over the squared styles (models/RestoreNet.py:510-516 with the style-independent sum_t W^2 cached).
 
-    ``entries`` = [(EqualLinear, style_index)]: problem j reads style row ``styles[:, style_index_j]`` of a
-    [B, n, D] style tensor and yields s_j [B, out_dim_j].  The descriptor table is built once and cached on the
-    device while the parameters stay in place."""
+    ``entries`` = [(EqualLinear, style_index, demod)]: problem j reads style row ``styles[:, style_index_j]`` of a
+    [B, n, D] style tensor and yields s_j [B, out_dim_j]; ``demod`` is None or (owner, wsq_fn, wscale, eps), giving
+    d_j [B, Cout] for ``owner``.  Descriptor tables are built once and cached on the device."""
 
     def __init__(self, entries):
-        self.entries = list(entries)
+        self.entries = [(e + (None,))[:3] for e in entries]
         self._key = None
-        self._descs = self._rows = None
-        self._offs = []
-        self._total = 0
+
+    @staticmethod
+    def _table(descs, device):
+        return torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(device)
 
     def _build(self, device, d_style, batch):
-        key = tuple((lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
-                    for lin, _ in self.entries) + (d_style, batch, str(device))
+        wsqs = [dm[1]() if dm is not None else None for _, _, dm in self.entries]
+        key = tuple((lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version,
+                     w.data_ptr() if w is not None else 0) for (lin, _, _), w in zip(self.entries, wsqs))
+        key += (d_style, batch, str(device))
         if key == self._key:
             return
         descs = (_lib.LinearDesc * len(self.entries))()
         rows, offs, y_off, r = [], [], 0, 0
-        for j, (lin, idx) in enumerate(self.entries):
+        for j, (lin, idx, _) in enumerate(self.entries):
             out_dim, in_dim = lin.weight.shape
             assert in_dim == d_style and lin.weight.is_contiguous() and lin.weight.dtype == torch.float32
             dsc = descs[j]
             dsc.w, dsc.bias = lin.weight.data_ptr(), lin.bias.data_ptr()
-            dsc.x_off, dsc.y_off = idx * d_style, y_off
+            dsc.x_off, dsc.y_off, dsc.x_bstride = idx * d_style, y_off, 0
             dsc.in_dim, dsc.out_dim = in_dim, out_dim
             dsc.wscale, dsc.bscale = lin.scale, lin.lr_mul
             rows.append(r)
             offs.append((y_off, out_dim))
-            r += out_dim
+            r += (out_dim + 7) // 8 * 8          # a block of the kernel covers 8 rows of one problem
             y_off += batch * out_dim
-        raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
-        self._descs = raw.to(device)
+        self._descs = self._table(descs, device)
         self._rows = torch.tensor(rows, dtype=torch.int32, device=device)
-        self._offs, self._total, self._rows_total, self._key = offs, y_off, r, key
+        self._offs, self._total, self._rows_total = offs, y_off, r
+        # demodulation problems: weight = wsq [Cout, Cin], input = squared styles of the owning problem
+        dem = [(j, dm, w) for j, ((_, _, dm), w) in enumerate(zip(self.entries, wsqs)) if dm is not None]
+        self._dem = dem
+        if dem:
+            ddesc = (_lib.LinearDesc * len(dem))()
+            drows, doffs, d_off, r = [], [], 0, 0
+            for q, (j, (owner, _, wscale, eps), wsq) in enumerate(dem):
+                cout, cin = wsq.shape
+                assert cin == offs[j][1] and wsq.is_contiguous()
+                dsc = ddesc[q]
+                dsc.w, dsc.bias = wsq.data_ptr(), None
+                dsc.x_off, dsc.x_bstride, dsc.y_off = offs[j][0], cin, d_off
+                dsc.in_dim, dsc.out_dim = cin, cout
+                dsc.wscale, dsc.bscale = wscale * wscale, 0.0
+                drows.append(r)
+                doffs.append((d_off, cout, id(owner), eps))
+                r += (cout + 7) // 8 * 8
+                d_off += batch * cout
+            self._ddescs = self._table(ddesc, device)
+            self._drows = torch.tensor(drows, dtype=torch.int32, device=device)
+            self._doffs, self._dtotal, self._drows_total = doffs, d_off, r
+            self._wsq_keep = wsqs
+        self._key = key
 
     def __call__(self, styles):
-        """styles [B, n, D] fp32 contiguous -> {id(lin): s [B, out_dim]}"""
+        """styles [B, n, D] fp32 -> ({id(lin): s [B, out_dim]}, {id(owner): d [B, Cout]})"""
         b, n, d = styles.shape
         styles = styles.contiguous().float()
         self._build(styles.device, d, b)
+        lib = _lib.load()
         y = torch.empty(self._total, dtype=torch.float32, device=styles.device)
         with torch.cuda.device(styles.device):
-            rc = _lib.load().vsp_grouped_linear_f32(ptr(self._descs), ptr(self._rows), len(self.entries), self._rows_total,
-                                                    ptr(styles), n * d, ptr(y), b, stream_ptr())
+            rc = lib.vsp_grouped_linear_f32(ptr(self._descs), ptr(self._rows), len(self.entries), self._rows_total,
+                                            ptr(styles), n * d, ptr(y), b, stream_ptr())
         _lib.check(rc, "grouped_linear_f32")
-        return {id(lin): y[o:o + b * od].view(b, od) for (lin, _), (o, od) in zip(self.entries, self._offs)}
+        s_out = {id(lin): y[o:o + b * od].view(b, od) for (lin, _, _), (o, od) in zip(self.entries, self._offs)}
+        d_out = {}
+        if self._dem:
+            y2 = y * y
+            dpre = torch.empty(self._dtotal, dtype=torch.float32, device=styles.device)
+            with torch.cuda.device(styles.device):
+                rc = lib.vsp_grouped_linear_f32(ptr(self._ddescs), ptr(self._drows), len(self._dem), self._drows_total,
+                                                ptr(y2), 0, ptr(dpre), b, stream_ptr())
+            _lib.check(rc, "grouped_linear_f32(demod)")
+            eps = self._doffs[0][3]
+            dall = torch.rsqrt(dpre + eps)
+            for o, cout, owner_id, e in self._doffs:
+                assert e == eps
+                d_out[owner_id] = dall[o:o + b * cout].view(b, cout)
+        return s_out, d_out
 
 
 _mod_ctx: dict = {}
+_demod_ctx: dict = {}
 _bank_cache: dict = {}
+
+
+def _bank_apply(bank, styles):
+    s_out, d_out = bank(styles)
+    _mod_ctx.update(s_out)
+    _demod_ctx.update(d_out)
+
+
+def _bank_clear():
+    _mod_ctx.clear()
+    _demod_ctx.clear()
+
+
+def _conv_wsq(conv):
+    """Cached sum_t W^2 [Cout, Cin] of a ModulatedConv2d (style-independent part of its demodulation)."""
+    return _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(
+        conv.weight.detach().view(conv.out_channel, conv.in_channel, conv.kernel_size, conv.kernel_size)))
+
+
+def _smart_wcat(m):
+    branches = list(m.ModulatedConv2ds)
+    cq, k = branches[0].out_channel, branches[0].kernel_size
+    return _cached(m, "wcat", [br.weight for br in branches],
+                   lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
+
+
+def _smart_wsq(m):
+    return _cached(m, "wsq", [br.weight for br in m.ModulatedConv2ds], lambda: mc.weight_sumsq(_smart_wcat(m)))
+
+
+def _demod_entry_conv(sc):
+    """Bank entry of a StyledConv / StyledConv_down: its modulation linear + (when it demodulates) its demod problem."""
+    conv = sc.conv
+    return (conv, lambda: _conv_wsq(conv), conv.scale, conv.eps) if conv.demodulate else None
+
+
+def _demod_entry_smart(m):
+    br = m.ModulatedConv2ds[0]
+    return (m, lambda: _smart_wsq(m), br.scale, br.eps) if br.demodulate else None
 
 
 def _banks_for(owner, build):
@@ -215,13 +297,14 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     cout, cin, k = conv.out_channel, conv.in_channel, conv.kernel_size
     s = _modulation(conv.modulation, style)
     w4 = conv.weight.detach().view(cout, cin, k, k)
-    wsq = _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(w4)) if conv.demodulate else None
+    wsq = _conv_wsq(conv) if conv.demodulate else None
+    d_pre = _demod_ctx.get(id(conv)) if conv.demodulate else None      # from the pass's ModulationBank, if any
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
                noise_weight_dev=m.noise.weight.detach())
     if h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
         # input-modulated form: scale the (small) activation, convolve with shared cached weights
         xs = mc.scale_nhwc(x, s)
-        d = mc.demod_from_wsq(s, wsq, conv.scale, conv.eps) if conv.demodulate else None
+        d = (d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, conv.scale, conv.eps)) if conv.demodulate else None
         if conv.upsample and k == 3 and cout % 32 == 0:
             wq3 = _cached(conv, "wq_up2_shared", [conv.weight, conv.blur.kernel], lambda: mc.pack_weights(
                 mc.compose_up2_weights(w4, conv.blur.kernel), wscale=conv.scale)[0])
@@ -244,11 +327,13 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
         wq3, _ = mc.pack_weights(w3, s, wscale=conv.scale)
         d = None
         if conv.demodulate:
-            d = torch.rsqrt((conv.scale * conv.scale) * ((s * s) @ wsq.t()) + conv.eps)
+            d = d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, conv.scale, conv.eps)
         nz = _noise_for(noise, b, 2 * h, 2 * w, x.device)
         return mc.conv_up2_fused(x, wq3, cout, epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual,
                                                                      residual2=residual2, **act))
-    wq, d = mc.pack_weights(w4, s, wscale=conv.scale, eps=conv.eps, want_demod=conv.demodulate, wsq=wsq)
+    wq, d = mc.pack_weights(w4, s, wscale=conv.scale, eps=conv.eps, want_demod=conv.demodulate and d_pre is None, wsq=wsq)
+    if d_pre is not None:
+        d = d_pre
     if conv.upsample:
         y = mc.conv_transpose_s2(x, wq, cout, k, k, epi=mc.make_epilogue(row_scale=d) if d is not None else None,
                                  out_nhwc=True)
@@ -279,21 +364,23 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     cout = cq * len(branches)
     k = branches[0].kernel_size
     s = _modulation(m.modulation, style)
-    wcat = _cached(m, "wcat", [br.weight for br in branches],
-                   lambda: torch.cat([br.weight.detach().view(cq, br.in_channel, k, k) for br in branches], 0).contiguous())
-    wsq = _cached(m, "wsq", [br.weight for br in branches], lambda: mc.weight_sumsq(wcat)) if branches[0].demodulate else None
+    wcat = _smart_wcat(m)
+    wsq = _smart_wsq(m) if branches[0].demodulate else None
+    d_pre = _demod_ctx.get(id(m)) if branches[0].demodulate else None
     dils = [br.dilation for br in branches]
     one_launch = (k == 3 and w <= _BRANCH_MAX_W and cq >= 16 and (cq & (cq - 1)) == 0 and len(branches) <= 4
                   and all(br.padding == br.dilation for br in branches))
     if one_launch and h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
         # input-modulated form on shared cached weights, all branches in one launch
         xs = mc.scale_nhwc(x, s)
-        d = mc.demod_from_wsq(s, wsq, branches[0].scale, branches[0].eps) if wsq is not None else None
+        d = (d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, branches[0].scale, branches[0].eps)) if wsq is not None else None
         wqs = _cached(m, "wq_shared", [br.weight for br in branches], lambda: mc.pack_weights(wcat, wscale=branches[0].scale)[0])
         buf = mc.conv_branches(xs, wqs, cout, dils, epi=mc.make_epilogue(row_scale=d) if d is not None else None)
     else:
-        wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps, want_demod=branches[0].demodulate,
-                                wsq=wsq)
+        wq, d = mc.pack_weights(wcat, s, wscale=branches[0].scale, eps=branches[0].eps,
+                                want_demod=branches[0].demodulate and d_pre is None, wsq=wsq)
+        if d_pre is not None:
+            d = d_pre
         if one_launch:
             buf = mc.conv_branches(x, wq, cout, dils, epi=mc.make_epilogue(row_scale=d) if d is not None else None)
         else:
@@ -419,12 +506,14 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
 
     enc = net.encoder_convs
     banks = _banks_for(net, lambda: (
-        ModulationBank([(enc[ii + j].modulation if j == 0 else enc[ii + j].conv.modulation, ii)
-                        for ii in range(0, len(enc), 2) for j in (0, 1)]),
-        ModulationBank([(net.conv1.modulation, 0), (net.to_rgb1.conv.modulation, 1)] +
-                       [(m, 1 + 2 * q + j) for q, (up, smart, rgb) in enumerate(zip(net.convs[::2], net.convs[1::2], net.to_rgbs))
-                        for j, m in enumerate((up.conv.modulation, smart.modulation, rgb.conv.modulation))])))
-    _mod_ctx.update(banks[0](lat_rev))
+        ModulationBank([(enc[ii].modulation, ii, _demod_entry_smart(enc[ii])) for ii in range(0, len(enc), 2)] +
+                       [(enc[ii + 1].conv.modulation, ii, _demod_entry_conv(enc[ii + 1])) for ii in range(0, len(enc), 2)]),
+        ModulationBank([(net.conv1.modulation, 0, _demod_entry_smart(net.conv1)), (net.to_rgb1.conv.modulation, 1)] +
+                       [e for q, (up, smart, rgb) in enumerate(zip(net.convs[::2], net.convs[1::2], net.to_rgbs))
+                        for e in ((up.conv.modulation, 1 + 2 * q, _demod_entry_conv(up)),
+                                  (smart.modulation, 2 + 2 * q, _demod_entry_smart(smart)),
+                                  (rgb.conv.modulation, 3 + 2 * q))])))
+    _bank_apply(banks[0], lat_rev)
     out = large_conv_layer(net.down_from_big, mc.nchw_to_nhwc_bf16(images, c_pad=8))
     features = []
     for ii in range(0, len(enc), 2):
@@ -440,7 +529,7 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
 
     n_sty = 2 * len(net.to_rgbs) + 2
     stys = torch.cat([latent[:, :n_sty], x_global[:, None, :].expand(-1, n_sty, -1)], dim=2)   # [B, n, 2048]
-    _mod_ctx.update(banks[1](stys))
+    _bank_apply(banks[1], stys)
 
     def sty(i):
         return stys[:, i]
@@ -454,7 +543,7 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
         out = smart_layer(smart, out, sty(i + 1), n_smart)
         skip = to_rgb(rgb, out, sty(i + 2), skip)
         i += 2
-    _mod_ctx.clear()
+    _bank_clear()
     return skip
 
 
@@ -470,10 +559,12 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
         noise = ([None] * gen.num_layers if randomize_noise
                  else [getattr(gen.noises, f"noise_{i}") for i in range(gen.num_layers)])
     bank = _banks_for(gen, lambda: (ModulationBank(
-        [(gen.conv1.conv.modulation, 0), (gen.to_rgb1.conv.modulation, 1)] +
-        [(m.conv.modulation, 1 + 2 * q + j) for q, trio in enumerate(zip(gen.convs[::2], gen.convs[1::2], gen.to_rgbs))
-         for j, m in enumerate(trio)]),))[0]
-    _mod_ctx.update(bank(latent))
+        [(gen.conv1.conv.modulation, 0, _demod_entry_conv(gen.conv1)), (gen.to_rgb1.conv.modulation, 1)] +
+        [e for q, (up, conv, rgb) in enumerate(zip(gen.convs[::2], gen.convs[1::2], gen.to_rgbs))
+         for e in ((up.conv.modulation, 1 + 2 * q, _demod_entry_conv(up)),
+                   (conv.conv.modulation, 2 + 2 * q, _demod_entry_conv(conv)),
+                   (rgb.conv.modulation, 3 + 2 * q))]),))[0]
+    _bank_apply(bank, latent)
     const = _cached(gen.input, "nhwc", [gen.input.input], lambda: mc.nchw_to_nhwc_bf16(gen.input.input.detach()))
     out = styled_conv(gen.conv1, const.expand(b, -1, -1, -1).contiguous(), latent[:, 0], noise[0])
     skip = to_rgb(gen.to_rgb1, out, latent[:, 1])
@@ -486,7 +577,7 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
         out = styled_conv(conv, out, latent[:, i + 1], n_conv)
         skip = to_rgb(rgb, out, latent[:, i + 2], skip)
         i += 2
-    _mod_ctx.clear()
+    _bank_clear()
     if return_features and features_nchw:
         feats = [mc.nhwc_bf16_to_nchw(f) for f in feats]
     return skip, (feats if return_features else None)
