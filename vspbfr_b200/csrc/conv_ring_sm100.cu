@@ -882,6 +882,7 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   p.rr_strips = (p.out_w + kBlockM - 1) / kBlockM;
   p.rr_chains = d;
   // segments: minimise waves x (rows per unit + per-unit overhead)
+  static const int unit_ovh = getenv("VSP_RING_UNIT_OVH") ? atoi(getenv("VSP_RING_UNIT_OVH")) : 8;   // pipeline fill/drain, in rows
   const int rows_chain = p.out_h / d;
   const long long base_units = (long long)p.batch * p.rr_strips * p.rr_chains * p.rr_nslices;
   double best = 1e300;
@@ -892,7 +893,7 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
     const int se = (rows_chain + L - 1) / L;
     const long long units = base_units * se;
     const long long waves = (units + num_sms() - 1) / num_sms();
-    const double cost = (double)waves * (L + 2 * halo + 3);
+    const double cost = (double)waves * (L + 2 * halo + unit_ovh);
     if (cost < best) { best = cost; best_L = L; }
     if (L <= kRingR) break;
   }
