@@ -286,9 +286,9 @@ def main():
 
 def conv_traffic(micro):
     """DRAM bytes (read + written) of all tcgen05 conv launches of one micro-batch, from the committed ncu launch list
-    (profiles/r01_launches_microbatch32_v20.*: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over
+    (profiles/r01_launches_microbatch32_v23.*: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over
     tools/prof_step.py 32); None when the bench runs at another micro-batch size."""
-    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v20.json")
+    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v23.json")
     if micro != 32 or not os.path.exists(path):
         return None
     return json.load(open(path))["conv_kernels"]["dram_bytes"]
