@@ -298,6 +298,16 @@ int vsp_torgb_nhwc_bf16(const void *x, const float *w, const float *s, const flo
                         float wscale, void *stream);
 
 /*
+ * Last ToRGB of the style decoder fused with the face_pool that follows it (e4e/models/psp.py:245-246):
+ *   out = AvgPool2x2( conv1x1_mod(x) + bias + Upsample(skip) )      out [batch, 3, out_h, out_w], x [batch, 2*out_h, 2*out_w, c]
+ * skip [batch, 3, out_h, out_w] is the previous level's RGB image (same resolution as `out`); k3_host[9] (HOST memory) is
+ * the 3x3 composite of the 2x FIR upsample followed by the 2x2 mean (outer([1/8, 3/4, 1/8]) for the model's filter).
+ */
+int vsp_torgb_pool2_nhwc_bf16(const void *x, const float *w, const float *s, const float *bias,
+                              const float *skip, const float *k3_host, float *out,
+                              int64_t batch, int64_t out_h, int64_t out_w, int64_t c, float wscale, void *stream);
+
+/*
  * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):
  *   gw[g, t, o, i] = sum_{p in sample(s) of group g} dy[b,p,o] * x[b, p*stride + t*dil - pad, i]
  * Replaces aten::cudnn_convolution_backward_weight, op/conv2d_gradfix.py:177-199.

@@ -264,3 +264,18 @@ def test_full_size_hot_path_matches_cpu_oracle():
     err = float((got - want).abs().max())
     assert psnr(got, want) > 45.0, f"restored @512: psnr {psnr(got, want)}"
     assert err <= 3e-2 * peak, f"restored @512: max-abs {err} > 3e-2 * {peak}"
+
+
+@pytest.mark.parametrize("c,h", [(32, 64), (64, 32), (8, 20)])
+def test_torgb_pooled_matches_torgb_then_avgpool(c, h):
+    """Last decoder ToRGB fused with face_pool (e4e/models/psp.py:245-246) == ToRGB -> 2x2 average pooling."""
+    torch.manual_seed(c * h)
+    m = L.ToRGB(c, 512, upsample=True).to(DEV)
+    m.bias.data.normal_()
+    b = 3
+    xq = mc.nchw_to_nhwc_bf16(torch.randn(b, c, h, h, device=DEV))
+    style = torch.randn(b, 512, device=DEV)
+    skip = torch.randn(b, 3, h // 2, h // 2, device=DEV)
+    want = torch.nn.functional.avg_pool2d(fp.to_rgb(m, xq, style, skip), 2)
+    got = fp.to_rgb_pooled(m, xq, style, skip)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-4, atol=2e-4)

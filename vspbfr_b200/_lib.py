@@ -181,6 +181,8 @@ SIGNATURES = {
                                           c_int64, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
     "vsp_torgb_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_float, c_void_p]),
+    "vsp_torgb_pool2_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p,
+                                          c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),

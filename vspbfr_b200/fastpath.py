@@ -462,6 +462,60 @@ def to_rgb(m: ToRGB, x, style, skip=None):
     return out
 
 
+_pool_taps_cache: dict = {}
+
+
+def _pool_upsample_taps(up):
+    """3x3 composite (HOST floats) of ``Upsample`` (2x zero-stuffing + FIR, models/RestoreNet.py:43-61) followed by a 2x2
+    mean: pooled[y, x] = sum_{dy,dx} K[dy, dx] * skip[y + dy - 1, x + dx - 1].  Derived numerically from the module's own
+    filter and pads on an impulse (host, cached)."""
+    kern = up.kernel
+    key = (kern.data_ptr(), kern._version, tuple(kern.shape), up.factor, tuple(up.pad))
+    hit = _pool_taps_cache.get(key)
+    if hit is None:
+        assert up.factor == 2
+        k = kern.detach().double().cpu()
+        kh, kw = k.shape
+        p0, p1 = up.pad
+        n = 7
+        z = torch.zeros(2 * n + p0 + p1, 2 * n + p0 + p1, dtype=torch.float64)
+        z[p0 + 2 * 3, p0 + 2 * 3] = 1.0                                     # impulse at low-res (3, 3), zero-stuffed + padded
+        kf = torch.flip(k, [0, 1])
+        oh, ow = z.shape[0] - kh + 1, z.shape[1] - kw + 1
+        up_img = torch.zeros(oh, ow, dtype=torch.float64)
+        for i in range(oh):
+            for j in range(ow):
+                up_img[i, j] = (z[i:i + kh, j:j + kw] * kf).sum()
+        pooled = up_img[:2 * n, :2 * n].reshape(n, 2, n, 2).mean(dim=(1, 3))  # response at (y, x) to the impulse at (3, 3)
+        taps = torch.zeros(3, 3, dtype=torch.float64)
+        for dy in range(3):
+            for dx in range(3):
+                taps[dy, dx] = pooled[3 - (dy - 1), 3 - (dx - 1)]                 # K[dy,dx] multiplies skip[y+dy-1, x+dx-1]
+        assert abs(float(pooled.sum() - taps.sum())) < 1e-9, "upsample + pool support exceeds 3x3"
+        hit = _pool_taps_cache[key] = ((ctypes.c_float * 9)(*[float(v) for v in taps.flatten()]), kern)
+    return hit[0]
+
+
+def to_rgb_pooled(m: ToRGB, x, style, skip):
+    """Last ToRGB of the decoder + face_pool in one kernel: AvgPool2x2(conv + bias + Upsample(skip)) (see
+    vsp_torgb_pool2_nhwc_bf16); x [B,H,W,C] -> [B,3,H/2,W/2] fp32, skip [B,3,H/2,W/2]."""
+    conv = m.conv
+    b, h, w, c = x.shape
+    assert h % 2 == 0 and w % 2 == 0 and skip is not None and tuple(skip.shape) == (b, 3, h // 2, w // 2)
+    s = _modulation(conv.modulation, style)
+    bias = _cached(m, "bias3", [m.bias], lambda: m.bias.detach().reshape(3).contiguous())
+    w3 = _cached(m, "w3", [conv.weight], lambda: _pad_cols(conv.weight.detach().reshape(3, conv.in_channel), c))
+    if c != conv.in_channel:
+        s = F.pad(s, (0, c - conv.in_channel))
+    out = torch.empty((b, 3, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().vsp_torgb_pool2_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(skip.contiguous()),
+                                                   _pool_upsample_taps(m.upsample), ptr(out), b, h // 2, w // 2, c,
+                                                   conv.scale, stream_ptr())
+    _lib.check(rc, "torgb_pool2_nhwc_bf16")
+    return out
+
+
 def _pad_cols(w, c):
     if w.shape[1] == c:
         return w.contiguous()
@@ -549,7 +603,7 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
 
 @torch.no_grad()
 def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_latent=None, input_is_latent=False,
-                      noise=None, randomize_noise=True, return_features=True, features_nchw=False):
+                      noise=None, randomize_noise=True, return_features=True, features_nchw=False, pool_image=False):
     """Style decoder ``Generator.forward`` (e4e/models/stylegan2/model.py:475-552) fused.
     Returns (image fp32 NCHW, features) — features NHWC bf16, or NCHW fp32 when ``features_nchw``."""
     latent = _mapped_latent(gen.style, gen.n_latent, styles, inject_index, truncation, truncation_latent,
@@ -575,7 +629,10 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
         if return_features:
             feats.append(out)
         out = styled_conv(conv, out, latent[:, i + 1], n_conv)
-        skip = to_rgb(rgb, out, latent[:, i + 2], skip)
+        if pool_image and rgb is gen.to_rgbs[-1]:
+            skip = to_rgb_pooled(rgb, out, latent[:, i + 2], skip)     # image at half resolution (face_pool fused in)
+        else:
+            skip = to_rgb(rgb, out, latent[:, i + 2], skip)
         i += 2
     _bank_clear()
     if return_features and features_nchw:
@@ -590,7 +647,9 @@ def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent
     if noise_styles is None:
         noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
     _noise_pool.begin(low_imgs.device)
-    image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True)
+    size = low_imgs.shape[-1]
+    fuse_pool = decoder.size == 2 * size and len(decoder.to_rgbs) > 0 and decoder.to_rgbs[-1].upsample.factor == 2
+    image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True, pool_image=fuse_pool)
     feats = feats[:out_n_latent]
     restored = restoration_forward(net, low_imgs, feats, codes, noise_styles)
     size = low_imgs.shape[-1]
