@@ -528,7 +528,9 @@ def test_up2_fused_matches_transposed_conv_then_blur(b, cin, cout, h, w_, per_sa
 
 
 @pytest.mark.parametrize("b,cin,cq,h,w_", [(8, 512, 128, 4, 4), (3, 512, 128, 8, 8), (2, 128, 32, 16, 16), (2, 64, 16, 32, 32),
-                                           (2, 256, 64, 64, 64), (5, 64, 64, 4, 8)])
+                                           (2, 256, 64, 64, 64), (5, 64, 64, 4, 8),
+                                           # wide 16/32-channel branches -> branch slices of the kh-folded row-ring kernel
+                                           (2, 64, 16, 64, 128), (1, 128, 32, 32, 256), (3, 64, 16, 128, 130), (1, 32, 16, 16, 128)])
 @pytest.mark.parametrize("per_sample", [False, True])
 def test_conv_branches_one_launch(b, cin, cq, h, w_, per_sample):
     """Four dilated branches (SMART_layer) as one launch == four separate dilated convs written to channel slices;

@@ -32,17 +32,31 @@ constexpr int kMaxSlots = 16;
 constexpr int kRingR = 4;
 
 struct RingUnit {
-  int b, strip, o0, L, slice;
+  int b, strip, o0, L, slice, d;
 };
 
-// unit -> (sample, strip, chain, segment); the host guarantees every unit has L >= 1 rows.
+// unit -> (sample, strip, chain, segment[, slice]); the host guarantees every unit has L >= 1 rows.
+// Branch slices (the dilated branches of a SMART layer in one launch): slice j has its own dilation n_dil[j]; the
+// rr_segs sub-units of a strip are split into n_dil[j] chains x rr_segs / n_dil[j] segments of rr_L rows, so every
+// slice has the same number of equally long units and a CTA (grid = multiple of the slice count) keeps its branch.
 __device__ __forceinline__ RingUnit ring_decode(const ConvParams &p, long long u, int d_eff) {
   RingUnit r;
   r.slice = (int)(u % p.rr_nslices); u /= p.rr_nslices;   // fastest: the slices of one strip segment run side by side (L2 reuse)
+  if (p.branch_mode) {
+    const int sub = (int)(u % p.rr_segs); u /= p.rr_segs;
+    r.strip = (int)(u % p.rr_strips); u /= p.rr_strips;
+    r.b = (int)u;
+    r.d = p.n_dil[r.slice];
+    const int chain = sub % r.d, seg = sub / r.d;
+    r.L = p.rr_L;
+    r.o0 = chain + seg * p.rr_L * r.d;
+    return r;
+  }
   const int seg = (int)(u % p.rr_segs); u /= p.rr_segs;
   const int chain = (int)(u % p.rr_chains); u /= p.rr_chains;
   r.strip = (int)(u % p.rr_strips); u /= p.rr_strips;
   r.b = (int)u;
+  r.d = d_eff;
   const int rows_in_chain = (p.out_h - chain + d_eff - 1) / d_eff;
   const int start = seg * p.rr_L;
   r.L = min(p.rr_L, rows_in_chain - start);
@@ -365,7 +379,7 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.rr_S, kc = p.kc;
-  const int d = p.halo_d;
+  const int d = p.halo_d;                 // (branch slices: per-unit dilation un.d, halo box sized for the largest)
   const uint32_t slot_bytes = (uint32_t)p.halo_w * 128u;
   const uint32_t b_total = (uint32_t)(kc * 9) * B_BYTES;
   unsigned char *a_buf = smem;
@@ -414,9 +428,9 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
     uint32_t ph = 0;
     for (long long u = blockIdx.x; u < units; u += gridDim.x) {
       const RingUnit un = ring_decode(p, u, d);
-      const int w0 = un.strip * kBlockM - d;
+      const int w0 = un.strip * kBlockM - un.d;
       for (int k = 0; k < un.L + 2; ++k) {
-        const int ih = un.o0 + (k - 1) * d;
+        const int ih = un.o0 + (k - 1) * un.d;
         for (int cb = 0; cb < kc; ++cb) {
           mbar_wait(&a_empty[slot], ph ^ 1);
           if (elect_one()) {
@@ -486,7 +500,7 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
             const uint32_t arow = a_base + (uint32_t)s * slot_bytes;
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
-              const uint64_t adesc = umma_smem_desc(arow + (uint32_t)(kw * d) * 128u, 128);
+              const uint64_t adesc = umma_smem_desc(arow + (uint32_t)(kw * un.d) * 128u, 128);
               const uint64_t bdesc = umma_smem_desc(b_base + (uint32_t)((cb * 3 + kw) * 3) * B_BYTES, 128);
 #pragma unroll
               for (int ks = 0; ks < kBlockK / kUmmaK; ++ks)
@@ -553,7 +567,7 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
       // residuals (staged path): sector-coalesced warp loads of the 32-pixel x C-channel tile, one row ahead
       uint4 pr1[PIECES], pr2[PIECES];
       auto load_res = [&](int j) {
-        const int fh = (un.o0 + j * d) * p.os + (cls >> 1);
+        const int fh = (un.o0 + j * un.d) * p.os + (cls >> 1);
 #pragma unroll
         for (int i = 0; i < PIECES; ++i) {
           const int px = un.strip * kBlockM + quad * 32 + i * PPR + lane / PIECES;
@@ -568,11 +582,11 @@ conv_ringfold_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tma
       // noise one row ahead as well (an HBM round trip per row would otherwise sit on the epilogue's critical path)
       auto load_noise = [&](int j) -> float {
         if (p.noise == nullptr || !pix_ok || j >= L) return 0.f;
-        return __ldg(p.noise + un.b * p.noise_bstride + (long long)((un.o0 + j * d) * p.os + (cls >> 1)) * p.full_w + fw);
+        return __ldg(p.noise + un.b * p.noise_bstride + (long long)((un.o0 + j * un.d) * p.os + (cls >> 1)) * p.full_w + fw);
       };
       float nz_next = load_noise(wg);
       for (int j = wg; j < L; j += 2) {
-        const int oh = un.o0 + j * d;
+        const int oh = un.o0 + j * un.d;
         const long long pix = (long long)(oh * p.os + (cls >> 1)) * p.full_w + fw;
         const float nz = nw * nz_next;
         nz_next = load_noise(j + 2);
@@ -833,6 +847,52 @@ int conv_ring_try_launch(ConvParams &p, const void *x, const void *wq, int64_t i
   if (p.stride != 1 || p.oo_h != 0 || p.oo_w != 0) return -1;
   if (p.out_w < kBlockM || p.out_w != in_w || p.out_h != in_h) return -1;
   if (p.ntaps != 9 && p.ntaps != 1) return -1;
+  // branch slices: the dilated branches of a SMART layer (cout / n_branches <= 32 channels each) in one launch
+  int nbr = 0;
+  if (p.branch_mode) {
+    for (int j = 0; j < 4 && p.n_dil[j] > 0; ++j) nbr = j + 1;
+    const int cq = nbr ? p.cout / nbr : 0;
+    bool ok = !no_fold && p.ntaps == 9 && p.kc <= 2 && nbr >= 1 && (cq == 16 || cq == 32) && p.os == 1 &&
+              p.shuffle_cout == 0 && p.full_w == p.out_w && p.full_h == p.out_h && p.residual == nullptr &&
+              p.residual2 == nullptr;
+    int dmax = 1;
+    for (int j = 0; ok && j < nbr; ++j) {
+      const int dj = p.n_dil[j];
+      ok = dj >= 1 && dj <= 8 && (dj & (dj - 1)) == 0;
+      dmax = dj > dmax ? dj : dmax;
+    }
+    if (!ok) return -1;
+    int S = 16;
+    while (S > dmax && p.out_h / S < 8) S >>= 1;
+    if (S < dmax || p.out_h % S != 0 || p.out_h / S < 2) return -1;
+    for (int t = 0; t < 9; ++t)
+      if (p.tap_dy[t] != t / 3 - 1 || p.tap_dx[t] != t % 3 - 1) return -1;
+    p.halo_d = dmax;
+    p.halo_w = (kBlockM + 2 * dmax + 7) & ~7;
+    p.rr_staged = (!no_stage && p.out_nhwc && (p.ldo % 8) == 0 && (p.co_off % 8) == 0 &&
+                   (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && p.alpha >= 0.f && p.alpha <= 1.f &&
+                   (p.scale > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
+    const int slot = p.halo_w * 128;
+    const int b_bytes = (9 * p.kc * cq * 128 + 1023) & ~1023;
+    const int o_bytes = p.rr_staged ? 8 * 2 * 32 * cq * 2 : 0;
+    const int fixed = 1024 + b_bytes + o_bytes + 512 + 3 * cq * 4;
+    int slots = (232448 - fixed) / slot;
+    if (slots > kMaxSlots) slots = kMaxSlots;
+    if (slots < 2 * p.kc) return -1;
+    p.rr_R = kRingR; p.rr_S = slots; p.rr_nb = 0;
+    p.tiles_n = 1;
+    p.rr_nslices = nbr;
+    p.rr_strips = (p.out_w + kBlockM - 1) / kBlockM;
+    p.rr_chains = 1;
+    p.rr_segs = S;
+    p.rr_L = p.out_h / S;
+    const size_t smem_bytes = (size_t)fixed + (size_t)slots * slot;
+    if (cq == 16)
+      return p.rr_staged ? launch_ringfold<16, true>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream)
+                         : launch_ringfold<16, false>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);
+    return p.rr_staged ? launch_ringfold<32, true>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream)
+                       : launch_ringfold<32, false>(p, x, wq, in_h, in_w, cout_pad, taps_total, smem_bytes, stream);
+  }
   // kh-folded kernel: Cout <= 32 directly, wider layers (and the pixel-shuffle up-convolution) as 32-channel slices
   // (measured: four slices win clearly — 128->128 @256^2 172 -> 148 us, fused 64->32 up-conv 428 -> 328 us; two slices
   // of a 64-channel block only tie with the resident nine-tap ring, eight slices lose to the generic kernel)

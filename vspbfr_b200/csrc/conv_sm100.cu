@@ -787,7 +787,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   }
 
   // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers
-  if (!p.branch_mode) {
+  {
     const int rc = conv_ring_try_launch(p, x, wq, in_h, in_w, cout_pad, taps_total, ntaps == 9 ? tap_dx[8] : 1, stream);
     if (rc >= 0) return rc;
   }

@@ -36,6 +36,9 @@ _LOWRES_PIXELS = int(os.environ.get("VSP_LOWRES_PIXELS", "1024"))
 # SMART layers up to this width run their four dilated branches as one launch of the generic kernel
 _BRANCH_MAX_W = int(os.environ.get("VSP_BRANCH_MAX_W", "64"))
 _SEP_BLUR = os.environ.get("VSP_NO_SEP_BLUR") is None
+# (measured: 64->16 x4 @512^2 1250 us merged vs 4 x 295 us separate, 128->32 x4 @256^2 640 vs 4 x 165 us — the fold kernel
+# is bound by its per-row epilogue round trip, not by re-reading x, so the merged form is off by default)
+_BRANCH_FOLD = os.environ.get("VSP_BRANCH_FOLD") is not None
 
 
 def _cached(owner, tag, tensors, build):
@@ -368,7 +371,10 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     wsq = _smart_wsq(m) if branches[0].demodulate else None
     d_pre = _demod_ctx.get(id(m)) if branches[0].demodulate else None
     dils = [br.dilation for br in branches]
-    one_launch = (k == 3 and w <= _BRANCH_MAX_W and cq >= 16 and (cq & (cq - 1)) == 0 and len(branches) <= 4
+    # one launch for all branches: the generic kernel's branch mode up to 64 pixels wide, the kh-folded row-ring kernel's
+    # branch slices (x read from HBM once, the other three branches hit L2) for the wide 16/32-channel branches
+    wide_fold = w >= 128 and cq in (16, 32) and cin <= 128 and _BRANCH_FOLD
+    one_launch = (k == 3 and (w <= _BRANCH_MAX_W or wide_fold) and cq >= 16 and (cq & (cq - 1)) == 0 and len(branches) <= 4
                   and all(br.padding == br.dilation for br in branches))
     if one_launch and h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
         # input-modulated form on shared cached weights, all branches in one launch
