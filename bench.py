@@ -276,12 +276,50 @@ def main():
             "share_of_step": conv["seconds"] / (t_res / args.steps / n_micro),
         }
         # config 2 conv launch and config 1 upfirdn2d launch in isolation (burst peaks)
+        result["full_pipeline"] = full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev)
         result["roofline_config2"] = isolated_conv(mc, pk)
         result["hbm_roofline"] = isolated_upfirdn(upfirdn2d_raw, pk, dev)
         result["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev):
+    """BASELINE configs[2] end to end on rank 0's shard: restoration_test.py:125-131 INCLUDING the stage before the hot
+    path — e4e IR-SE50 encoder (PyTorch/cuDNN, bf16 autocast, channels_last) and the 4-step code diffuser (PyTorch fp32),
+    random-init — then the sm_100a hot path.  Reported next to the headline (which starts from w+ codes)."""
+    from vspbfr_b200 import frontend
+
+    torch.manual_seed(1)
+    front = frontend.WPlusFrontEnd(frontend.Encoder4Editing(50, "ir_se"), n_latent=18).to(dev).eval()
+    front.encoder.to(memory_format=torch.channels_last)
+    ddpm = frontend.My_DDPM(frontend.Code_diffuser(timesteps=4), timesteps=4, linear_start=0.1, linear_end=0.99).to(dev).eval()
+
+    def run():
+        for m in range(n_micro):
+            sl = slice(m * micro, (m + 1) * micro)
+            frontend.restore_pipeline(low_d[sl], front, ddpm, dec, net, [z_d[sl]], autocast_dtype=torch.bfloat16)
+
+    def front_only():
+        for m in range(n_micro):
+            lat = front(low_d[m * micro:(m + 1) * micro], autocast_dtype=torch.bfloat16)
+            ddpm(condi_in=lat)
+
+    out = {}
+    for name, fn in (("pipeline", run), ("front_end", front_only)):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        out[name] = s.elapsed_time(e) * 1e-3
+    n = n_micro * micro
+    return {"value": n / out["pipeline"], "unit": UNIT, "faces": n, "front_end_share": out["front_end"] / out["pipeline"],
+            "front_end": "e4e IR-SE50 encoder @256 (cuDNN bf16 channels_last) + 4-step code diffuser (PyTorch), random-init",
+            "note": "rank 0's shard only; the headline `value` starts from w+ codes"}
 
 
 def conv_traffic(micro):

@@ -279,3 +279,27 @@ def test_torgb_pooled_matches_torgb_then_avgpool(c, h):
     want = torch.nn.functional.avg_pool2d(fp.to_rgb(m, xq, style, skip), 2)
     got = fp.to_rgb_pooled(m, xq, style, skip)
     np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_restore_pipeline_front_end_to_hot_path():
+    """restoration_test.py:125-131 end to end at small size: e4e encoder + code diffuser (PyTorch) feeding the fused hot path;
+    the codes handed over equal the front end run separately, and the restored image equals restore_faces on them."""
+    from vspbfr_b200 import frontend as fe
+    net, dec = _build_nets()
+    torch.manual_seed(4)
+    size = int(NET["size"])
+    n_latent = dec.n_latent
+    enc = fe.Encoder4Editing(50, "ir_se", stylegan_size=1024)
+    front = fe.WPlusFrontEnd(enc, latent_avg=torch.randn(18, 512) * 0.1, n_latent=18).to(DEV).eval()
+    ddpm = fe.My_DDPM(fe.Code_diffuser(timesteps=4), timesteps=4, linear_start=0.1, linear_end=0.99).to(DEV).eval()
+    low = torch.rand(2, 3, size, size, device=DEV) * 2 - 1
+    z = torch.randn(2, 512, device=DEV)
+    torch.manual_seed(9)
+    restored, image, codes = fe.restore_pipeline(low, front, ddpm, dec, net, [z])
+    assert codes.shape == (2, 18, 512) and restored.shape == low.shape and torch.isfinite(restored).all()
+    torch.manual_seed(9)
+    lat = front(low)
+    codes2 = ddpm(condi_in=lat)
+    np.testing.assert_allclose(codes.cpu().numpy(), codes2.cpu().numpy(), rtol=1e-4, atol=1e-4)
+    want, _ = fp.restore_faces(net, dec, low, codes, [z])
+    np.testing.assert_allclose(restored.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=1e-5 * max(1.0, float(want.abs().max())))
