@@ -292,19 +292,18 @@ def full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev):
     from vspbfr_b200 import frontend
 
     torch.manual_seed(1)
-    front = frontend.WPlusFrontEnd(frontend.Encoder4Editing(50, "ir_se"), n_latent=18).to(dev).eval()
-    front.encoder.to(memory_format=torch.channels_last)
+    front = frontend.WPlusFrontEnd(frontend.Encoder4Editing(50, "ir_se"), n_latent=18).to(dev).eval().half_precision_()
     ddpm = frontend.My_DDPM(frontend.Code_diffuser(timesteps=4), timesteps=4, linear_start=0.1, linear_end=0.99).to(dev).eval()
 
     def run():
         for m in range(n_micro):
             sl = slice(m * micro, (m + 1) * micro)
-            frontend.restore_pipeline(low_d[sl], front, ddpm, dec, net, [z_d[sl]], autocast_dtype=torch.bfloat16)
+            frontend.restore_pipeline(low_d[sl], front, ddpm, dec, net, [z_d[sl]], tf32=True)
 
     def front_only():
         for m in range(n_micro):
-            lat = front(low_d[m * micro:(m + 1) * micro], autocast_dtype=torch.bfloat16)
-            ddpm(condi_in=lat)
+            lat = front(low_d[m * micro:(m + 1) * micro])
+            ddpm(condi_in=lat, tf32=True)
 
     out = {}
     for name, fn in (("pipeline", run), ("front_end", front_only)):
@@ -318,7 +317,7 @@ def full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev):
         out[name] = s.elapsed_time(e) * 1e-3
     n = n_micro * micro
     return {"value": n / out["pipeline"], "unit": UNIT, "faces": n, "front_end_share": out["front_end"] / out["pipeline"],
-            "front_end": "e4e IR-SE50 encoder @256 (cuDNN bf16 channels_last) + 4-step code diffuser (PyTorch), random-init",
+            "front_end": "e4e IR-SE50 encoder @256 (cuDNN, bf16 channels_last weights) + 4-step code diffuser (PyTorch, TF32 matmuls), random-init",
             "note": "rank 0's shard only; the headline `value` starts from w+ codes"}
 
 

@@ -160,7 +160,13 @@ class spatial_attention(nn.Module):
     def forward(self, w, attribute):
         q, v = self.q_matrix(w), self.v_matrix(w)                       # [B,18,512]
         k = self.k_matrix(attribute).permute(0, 2, 1)                   # [B,512,18]
-        attention = F.softmax(torch.matmul(k, q) / math.sqrt(self.dk), dim=1)
+        # softmax over dim 1 of the [B,512,512] score, computed on the transposed view so that the reduction runs along
+        # the contiguous axis (PyTorch's strided "spatial" softmax kernel was 24 % of the whole front end)
+        score = torch.matmul(k, q) / math.sqrt(self.dk)
+        if score.is_cuda:
+            attention = F.softmax(score.transpose(1, 2).contiguous(), dim=-1).transpose(1, 2)
+        else:
+            attention = F.softmax(score, dim=1)
         return self.layer_norm(torch.matmul(v, attention))
 
 
@@ -239,14 +245,19 @@ class My_DDPM(nn.Module):
         return self.posterior_mean_coef1[t].view(shape) * x0 + self.posterior_mean_coef2[t].view(shape) * x
 
     @torch.no_grad()
-    def forward(self, x=None, condi_in=None, training=False, x_T=None):
+    def forward(self, x=None, condi_in=None, training=False, x_T=None, tf32=False):
         """Inference branch of ldm/ddpm.py:421-429: start from N(0, I) of the condition's shape (or the given ``x_T``)
         and take ``num_timesteps`` posterior-mean steps conditioned on ``condi_in``."""
         if training:
             raise NotImplementedError("vspbfr_b200.frontend.My_DDPM implements the sampling branch only")
         cur = torch.randn(condi_in.shape, device=condi_in.device) if x_T is None else x_T
-        for i in reversed(range(self.num_timesteps)):
-            cur = self.p_sample(cur, torch.full((condi_in.shape[0],), i, device=condi_in.device, dtype=torch.long), condi_in)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32) or prev      # opt-in: the ~45 small fp32 GEMMs per step on tensor cores
+        try:
+            for i in reversed(range(self.num_timesteps)):
+                cur = self.p_sample(cur, torch.full((condi_in.shape[0],), i, device=condi_in.device, dtype=torch.long), condi_in)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
         return cur
 
 
@@ -263,10 +274,18 @@ class WPlusFrontEnd(nn.Module):
         self.n_latent = n_latent
         self.register_buffer("latent_avg", latent_avg if latent_avg is not None else torch.zeros(encoder.style_count, 512))
 
+    def half_precision_(self):
+        """Inference-only: keep the encoder's parameters in bf16, channels-last (no per-call autocast weight casts)."""
+        self.encoder.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        return self
+
     @torch.no_grad()
     def forward(self, img, autocast_dtype=None):
         x = F.interpolate(img, (256, 256), mode="bilinear")
-        if autocast_dtype is not None and x.is_cuda:
+        wdtype = next(self.encoder.parameters()).dtype
+        if wdtype != torch.float32:
+            codes = self.encoder(x.to(wdtype).contiguous(memory_format=torch.channels_last)).float()
+        elif autocast_dtype is not None and x.is_cuda:
             with torch.autocast("cuda", dtype=autocast_dtype):
                 codes = self.encoder(x.contiguous(memory_format=torch.channels_last))
             codes = codes.float()
@@ -276,12 +295,13 @@ class WPlusFrontEnd(nn.Module):
 
 
 @torch.no_grad()
-def restore_pipeline(low_imgs, front: WPlusFrontEnd, diffusion: My_DDPM, decoder, net, noise_styles=None, autocast_dtype=None):
+def restore_pipeline(low_imgs, front: WPlusFrontEnd, diffusion: My_DDPM, decoder, net, noise_styles=None, autocast_dtype=None,
+                     tf32=False):
     """restoration_test.py:125-131: w+ codes from the degraded image, 4-step code diffusion, then the sm_100a hot path.
     Returns (restored, decoder image at the input size, diffused codes)."""
     from . import fastpath
 
     low_latent = front(low_imgs, autocast_dtype=autocast_dtype)
-    codes = diffusion(x=low_latent, condi_in=low_latent, training=False)
+    codes = diffusion(x=low_latent, condi_in=low_latent, training=False, tf32=tf32)
     restored, image = fastpath.restore_faces(net, decoder, low_imgs, codes, noise_styles)
     return restored, image, codes

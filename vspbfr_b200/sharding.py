@@ -58,10 +58,11 @@ def restore_sharded(net, decoder, low_imgs, codes, noise_z, rank: int, world: in
 def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int = 32, device=None):
     """Restore a job whose inputs and outputs live in (pinned) HOST memory: micro-batches are copied in on one
     stream, processed on the current stream and copied out on a third, so the PCIe transfers of batch m+1 / m-1
-    overlap the kernels of batch m (restoration_test.py:125-157 moves every batch synchronously).
+    overlap the kernels of batch m (restoration_test.py:125-157 moves every batch synchronously).  Device staging
+    buffers are two persistent sets guarded by events — nothing is allocated or freed across streams inside the loop.
 
-    low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S] (filled asynchronously; the call
-    returns after the last device->host copy has been enqueued AND completed)."""
+    low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S]; returns when every device->host copy
+    has completed."""
     import torch
 
     from . import fastpath
@@ -71,28 +72,43 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
     compute = torch.cuda.current_stream(device)
     h2d, d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
     spans = list(micro_batches(0, n, micro))
+    if not spans:
+        return out_h
+    stage = [tuple(torch.empty((micro,) + tuple(x.shape[1:]), dtype=x.dtype, device=device) for x in (low_h, codes_h, noise_z_h))
+             for _ in range(2)]
+    loaded = [torch.cuda.Event() for _ in range(2)]       # staging set i holds its batch
+    consumed = [torch.cuda.Event() for _ in range(2)]     # the kernels reading staging set i have been enqueued and finished
+    copied = [None, None]                                  # (event, tensor) of the device->host copy two batches back
+    h2d.wait_stream(compute)
 
-    def stage_in(span):
-        s, e = span
+    def stage_in(i):
+        s, e = spans[i]
+        k = i & 1
         with torch.cuda.stream(h2d):
-            t = tuple(x[s:e].to(device, non_blocking=True) for x in (low_h, codes_h, noise_z_h))
-            ev = torch.cuda.Event()
-            ev.record(h2d)
-        return t, ev
+            if i >= 2:
+                h2d.wait_event(consumed[k])
+            for dst, src in zip(stage[k], (low_h, codes_h, noise_z_h)):
+                dst[:e - s].copy_(src[s:e], non_blocking=True)
+            loaded[k].record(h2d)
 
-    nxt = stage_in(spans[0]) if spans else None
+    stage_in(0)
     for i, (s, e) in enumerate(spans):
-        (lo, co, zz), ready = nxt
-        nxt = stage_in(spans[i + 1]) if i + 1 < len(spans) else None      # prefetch while this batch computes
-        compute.wait_event(ready)
-        for t in (lo, co, zz):
-            t.record_stream(compute)
+        k = i & 1
+        if i + 1 < len(spans):
+            stage_in(i + 1)                                # prefetch while this batch computes
+        compute.wait_event(loaded[k])
+        lo, co, zz = (t[:e - s] for t in stage[k])
         restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
-        done = torch.cuda.Event()
-        done.record(compute)
-        d2h.wait_event(done)
-        restored.record_stream(d2h)
+        consumed[k].record(compute)
+        if copied[k] is not None:
+            copied[k][0].synchronize()                     # long finished; lets the tensor two batches back be freed safely
+        d2h.wait_event(consumed[k])
         with torch.cuda.stream(d2h):
             out_h[s:e].copy_(restored, non_blocking=True)
-    compute.wait_stream(d2h)
+            ev = torch.cuda.Event()
+            ev.record(d2h)
+        copied[k] = (ev, restored)                         # keep `restored` alive until its copy has completed
+    for c in copied:
+        if c is not None:
+            c[0].synchronize()
     return out_h
