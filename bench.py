@@ -369,6 +369,8 @@ def isolated_conv(mc, pk):
     return {"bound": "tensor", "kernel": "conv_fprop_kernel<256> B=8 512->512 3x3 64x64 (BASELINE configs[1] fprop)",
             "achieved": flops / t / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": flops / t / 1e12 / pk["bf16_tflops"], "us": t * 1e6, "peak_source": pk["source"] + " (burst)",
+            "traffic": 80.5e6,   # ncu --set full, profiles/r01_ncu_prof_cfg2_r1.summary.txt: 71.4 MB read + 9.1 MB written (rest in L2)
+            "tensor_pipe_active_pct_ncu": 68.7,
             "timing": "24 back-to-back launches over 6 rotating operand sets (860 MB > L2), best of 5"}
 
 
@@ -381,7 +383,9 @@ def isolated_upfirdn(upfirdn2d_raw, pk, dev):
     nbytes = xs[0].numel() * 4 * 5
     return {"bound": "hbm", "kernel": "upfirdn2d_tile_kernel up=2 [4,512,64,64] (BASELINE configs[0])",
             "achieved": nbytes / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": nbytes / t / 1e9 / pk["hbm_gbs"],
-            "us": t * 1e6, "traffic": None, "peak_source": pk["source"],
+            "us": t * 1e6, "peak_source": pk["source"],
+            "traffic": 110.6e6,  # ncu --set full, profiles/r01_ncu_prof_ufd_cfg1.summary.txt: 33.6 MB read + 77.0 MB written
+                                 # before the kernel ends (the rest of the 134 MB output drains from L2 afterwards)
             "timing": "24 back-to-back launches over 8 rotating inputs (each launch allocates a fresh 134 MB output; "
                       "1.3 GB > L2), best of 5"}
 
