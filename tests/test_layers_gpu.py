@@ -236,6 +236,39 @@ def test_restore_from_host_pipelined_matches_device_path():
     np.testing.assert_allclose(out_h.numpy(), want.cpu().numpy(), rtol=0, atol=2e-2 * float(want.abs().max()))
 
 
+def test_graphed_restorer_matches_eager_and_feeds_host_pipeline():
+    """One micro-batch captured as a CUDA graph (fastpath.GraphedRestorer) replays to the same bits as the
+    eager launches (noise weights are 0 at init -> deterministic), follows new inputs across replays, and plugs into the
+    host-buffer pipeline; the C ABI is therefore capture-safe (no allocation / sync / host read-back per call)."""
+    from vspbfr_b200 import _lib, sharding
+    net, dec = _build_nets()
+    size, micro = int(NET["size"]), 2
+    g = torch.Generator().manual_seed(5)
+    graphed = fp.GraphedRestorer(net, dec, micro, n_latent=18, device=DEV)
+    assert graphed.launches > 20
+    for _ in range(2):
+        low = (torch.rand(micro, 3, size, size, generator=g) * 2 - 1).to(DEV)
+        codes = torch.randn(micro, 18, 512, generator=g).to(DEV)
+        z = torch.randn(micro, 512, generator=g).to(DEV)
+        want, want_img = fp.restore_faces(net, dec, low, codes, [z])
+        n0 = _lib.launch_count()
+        got, got_img = graphed(low, codes, z)
+        assert _lib.launch_count() == n0           # a replay goes through no host-side entry point
+        torch.testing.assert_close(got, want, rtol=0, atol=0)
+        torch.testing.assert_close(got_img, want_img, rtol=0, atol=0)
+    with pytest.raises(ValueError):
+        graphed(low[:1], codes[:1], z[:1])
+    n = 5                                           # two graph replays + one ragged eager micro-batch
+    low = (torch.rand(n, 3, size, size, generator=g) * 2 - 1).pin_memory()
+    codes = torch.randn(n, 18, 512, generator=g).pin_memory()
+    z = torch.randn(n, 512, generator=g).pin_memory()
+    out_a, out_b = torch.empty(n, 3, size, size).pin_memory(), torch.empty(n, 3, size, size).pin_memory()
+    sharding.restore_from_host(net, dec, low, codes, z, out_a, micro=micro, device=DEV, restorer=graphed)
+    sharding.restore_from_host(net, dec, low, codes, z, out_b, micro=micro, device=DEV)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out_a.numpy(), out_b.numpy())
+
+
 def test_full_size_hot_path_matches_cpu_oracle():
     """BASELINE-size parity: style decoder @1024 + Restoration_net @512 (random init, noise weights 0, batch 2) through
     the fused sm_100a pipeline — row-ring / kh-fold / fused up-conv / branch / low-resolution kernels at the sizes

@@ -55,14 +55,16 @@ def restore_sharded(net, decoder, low_imgs, codes, noise_z, rank: int, world: in
     return lo, hi, out
 
 
-def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int = 32, device=None):
+def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int = 32, device=None, restorer=None):
     """Restore a job whose inputs and outputs live in (pinned) HOST memory: micro-batches are copied in on one
     stream, processed on the current stream and copied out on a third, so the PCIe transfers of batch m+1 / m-1
     overlap the kernels of batch m (restoration_test.py:125-157 moves every batch synchronously).  Device staging
     buffers are two persistent sets guarded by events — nothing is allocated or freed across streams inside the loop.
 
     low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S]; returns when every device->host copy
-    has completed."""
+    has completed.  ``restorer`` (e.g. a ``fastpath.GraphedRestorer`` captured for ``micro``) replaces the eager
+    ``fastpath.restore_faces`` call for full micro-batches: ``restorer(low, codes, z) -> (restored, image)`` must return
+    tensors it does not overwrite later."""
     import torch
 
     from . import fastpath
@@ -98,7 +100,10 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
             stage_in(i + 1)                                # prefetch while this batch computes
         compute.wait_event(loaded[k])
         lo, co, zz = (t[:e - s] for t in stage[k])
-        restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
+        if restorer is not None and e - s == micro:
+            restored, _ = restorer(lo, co, zz)
+        else:
+            restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
         consumed[k].record(compute)
         if copied[k] is not None:
             copied[k][0].synchronize()                     # long finished; lets the tensor two batches back be freed safely
