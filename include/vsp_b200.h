@@ -302,6 +302,8 @@ int vsp_torgb_nhwc_bf16(const void *x, const float *w, const float *s, const flo
  *   out = AvgPool2x2( conv1x1_mod(x) + bias + Upsample(skip) )      out [batch, 3, out_h, out_w], x [batch, 2*out_h, 2*out_w, c]
  * skip [batch, 3, out_h, out_w] is the previous level's RGB image (same resolution as `out`); k3_host[9] (HOST memory) is
  * the 3x3 composite of the 2x FIR upsample followed by the 2x2 mean (outer([1/8, 3/4, 1/8]) for the model's filter).
+ * k3_host == NULL: `skip` has already been passed through that composite (e.g. vsp_upfirdn2d_f32 with the flipped 3x3 taps,
+ * pad 1) and is added as is — the form the lane-split kernel (C = 16/32/64/128, 512 contiguous bytes per warp load) takes.
  */
 int vsp_torgb_pool2_nhwc_bf16(const void *x, const float *w, const float *s, const float *bias,
                               const float *skip, const float *k3_host, float *out,

@@ -197,10 +197,11 @@ def test_grouped_linear_matches_equal_linear():
         np.testing.assert_allclose(d_out[id(owner)].cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-4)
 
 
-@pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130)])
+@pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130), (256, 18), (512, 66), (1024, 6),
+                                 (16, 70), (24, 12)])
 def test_torgb_kernel_both_variants(c, h):
-    """ToRGB (models/RestoreNet.py:647-666) through both kernel variants (warp-per-pixel for small images,
-    pixel-per-thread for large ones) against the modulated 1x1 conv in fp32 on the same bf16 activations."""
+    """ToRGB (models/RestoreNet.py:647-666) through every kernel variant (lane-split for C = 32...1024; warp-per-pixel /
+    pixel-per-thread for other channel counts) against the modulated 1x1 conv in fp32 on the same bf16 activations."""
     torch.manual_seed(c + h)
     m = L.ToRGB(c, 512, upsample=True).to(DEV)
     m.bias.data.normal_()
@@ -299,7 +300,7 @@ def test_full_size_hot_path_matches_cpu_oracle():
     assert err <= 3e-2 * peak, f"restored @512: max-abs {err} > 3e-2 * {peak}"
 
 
-@pytest.mark.parametrize("c,h", [(32, 64), (64, 32), (8, 20)])
+@pytest.mark.parametrize("c,h", [(32, 64), (64, 32), (8, 20), (16, 24), (128, 12), (32, 130)])
 def test_torgb_pooled_matches_torgb_then_avgpool(c, h):
     """Last decoder ToRGB fused with face_pool (e4e/models/psp.py:245-246) == ToRGB -> 2x2 average pooling."""
     torch.manual_seed(c * h)

@@ -514,10 +514,14 @@ def to_rgb_pooled(m: ToRGB, x, style, skip):
     if c != conv.in_channel:
         s = F.pad(s, (0, c - conv.in_channel))
     out = torch.empty((b, 3, h // 2, w // 2), dtype=torch.float32, device=x.device)
+    # upsample-then-pool of the skip = one 3x3 FIR pass at the output resolution (own upfirdn2d kernel, 3 channels: ~1 % of the
+    # feature-map traffic); the ToRGB kernel then only adds it
+    k3 = _cached(m.upsample, "pool_k3", [m.upsample.kernel], lambda: torch.tensor(
+        list(_pool_upsample_taps(m.upsample)), dtype=torch.float32, device=x.device).view(3, 3).flip(0, 1).contiguous())
+    res = upfirdn2d_raw(skip.contiguous(), k3, (1, 1), (1, 1), (1, 1, 1, 1))
     with torch.cuda.device(x.device):
-        rc = _lib.load().vsp_torgb_pool2_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(skip.contiguous()),
-                                                   _pool_upsample_taps(m.upsample), ptr(out), b, h // 2, w // 2, c,
-                                                   conv.scale, stream_ptr())
+        rc = _lib.load().vsp_torgb_pool2_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(res), None,
+                                                   ptr(out), b, h // 2, w // 2, c, conv.scale, stream_ptr())
     _lib.check(rc, "torgb_pool2_nhwc_bf16")
     return out
 
