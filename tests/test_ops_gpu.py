@@ -187,7 +187,12 @@ def test_errors_are_runtime_errors():
 
 @pytest.mark.parametrize("n,c,h,w,pad,epi", [(2, 64, 33, 33, (1, 1), True), (1, 32, 65, 40, (1, 1), False),
                                              (2, 64, 32, 32, (2, 2), False), (1, 128, 17, 130, (2, 2), True),
-                                             (3, 8, 9, 9, (1, 1), True), (1, 16, 100, 7, (2, 2), False)])
+                                             (3, 8, 9, 9, (1, 1), True), (1, 16, 100, 7, (2, 2), False),
+                                             # TMA strip kernel: C % 64 == 0, width >= 35 (partial last strip, several
+                                             # vertical segments, ring wrap-around, odd extents)
+                                             (2, 64, 70, 69, (2, 2), False), (1, 64, 200, 40, (2, 2), True),
+                                             (2, 192, 37, 36, (1, 1), False), (1, 64, 131, 97, (1, 1), True),
+                                             (1, 128, 4, 35, (2, 2), True)])
 @pytest.mark.parametrize("separable", [True, False])
 def test_blur_nhwc_bf16_streaming_kernel(n, c, h, w, pad, epi, separable):
     """Channels-last bf16 blur (Blur of models/RestoreNet.py:85-101 inside the fused pipeline): the streaming separable

@@ -551,6 +551,236 @@ blur_sep_nhwc_kernel(const uint4 *__restrict__ x, uint4 *__restrict__ y, const U
   }
 }
 
+// ---- TMA strip form of the separable NHWC blur -------------------------------------------------------------------------
+// blur_sep_nhwc_kernel is latency- and issue-bound (119 registers -> 16 warps/SM, per-load address arithmetic and bounds
+// tests, ~28 instructions per output element: 2.3 TB/s).  Here a CTA owns a strip of 32 output columns x 64 channels and
+// walks DOWN it: input rows arrive as TMA boxes [64 ch, 35 cols, 4 rows] in a 4-stage mbarrier ring (out-of-bounds zero
+// fill == the blur padding, no address math or predicates in the loop, every input row read once — no vertical halo), each
+// thread (8 channels x 2 adjacent columns) does one horizontal pass per input row from 5 conflict-free 128-bit LDS and
+// scatters it into a rolling window of 4 output-row accumulators; with 4 rows per stage == 4 filter taps the window rotates
+// with compile-time indices.  All arithmetic is packed fp32 (fma.rn.f32x2 on (even, odd) channel pairs): ~11 instructions
+// per output element.
+constexpr int kStripW = 32;
+constexpr int kStripCols = kStripW + kK - 1;
+constexpr int kStageRows = 4;
+constexpr int kStripStages = 4;
+constexpr int kStripThreads = 128;
+constexpr int kStageBytes = kStageRows * kStripCols * 128;
+static_assert(kStageRows == kK, "rolling window rotation assumes rows per stage == filter taps");
+
+struct StripParams {
+  int in_h, in_w, out_h, out_w, pad_x0, pad_y0;
+  int n_strips, n_chunks, n_seg, seg_rows, cg;
+};
+
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2_(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fmul2_(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <bool EPI>
+__global__ void __launch_bounds__(kStripThreads, 3)
+blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y, const StripParams p, const NhwcEpi e,
+                  const SepTaps t) {
+  extern __shared__ __align__(128) unsigned char strip_smem[];
+  __shared__ uint64_t full[kStripStages], empty[kStripStages];
+  const int tid = threadIdx.x, lane = tid & 31;
+  int bid = blockIdx.x;
+  const int sx = bid % p.n_strips; bid /= p.n_strips;
+  const int cz = bid % p.n_chunks; bid /= p.n_chunks;
+  const int sy = bid % p.n_seg;
+  const int b = bid / p.n_seg;
+  const int q_lo = sy * p.seg_rows;
+  const int rows_out = min(p.seg_rows, p.out_h - q_lo);
+  const int n_stage = (rows_out + kK - 1 + kStageRows - 1) / kStageRows;
+  const int ox0 = sx * kStripW, ix0 = ox0 - p.pad_x0, iy0 = q_lo - p.pad_y0;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kStripStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kStripThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tma_prefetch_desc(&tmx);
+    for (int k = 0; k < kStripStages && k < n_stage; ++k) {
+      mbar_arrive_expect_tx(&full[k], kStageBytes);
+      tma_load_4d(strip_smem + k * kStageBytes, &tmx, &full[k], cz * 64, ix0, iy0 + k * kStageRows, b);
+    }
+  }
+  const int cg8 = tid & 7, cp = tid >> 3;
+  const int ox = ox0 + 2 * cp;
+  const bool ok0 = ox < p.out_w, ok1 = ox + 1 < p.out_w;
+  unsigned long long fxp[kK], fyp[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    fxp[j] = pk2(t.fx[j], t.fx[j]);
+    fyp[j] = pk2(t.fy[j], t.fy[j]);
+  }
+  unsigned long long acc[kK][2][4];
+#pragma unroll
+  for (int q = 0; q < kK; ++q)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[q][c][i] = 0ull;
+  float bias[8];
+  float nw = 0.f;
+  if (EPI) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bias[i] = e.bias ? __ldg(e.bias + (cz * 8 + cg8) * 8 + i) : 0.f;
+    nw = e.noise ? (e.noise_weight_dev ? __ldg(e.noise_weight_dev) : e.noise_weight) : 0.f;
+  }
+  const uint32_t tbase = smem_u32(strip_smem) + (uint32_t)(2 * cp) * 128u + (uint32_t)cg8 * 16u;
+  const long long ybase = (long long)b * p.out_h * p.out_w * p.cg + cz * 8 + cg8;
+
+  for (int k = 0; k < n_stage; ++k) {
+    const int s = k % kStripStages;
+    const uint32_t phase = (uint32_t)(k / kStripStages) & 1u;
+    mbar_wait(&full[s], phase);
+    const uint32_t st = tbase + (uint32_t)s * kStageBytes;
+#pragma unroll
+    for (int rr = 0; rr < kStageRows; ++rr) {
+      const int i = k * kStageRows + rr;              // input row of this segment
+      const int oy = q_lo + i - (kK - 1);             // the output row this input row completes
+      const bool emit = i >= kK - 1 && i - (kK - 1) < rows_out;
+      // epilogue operands of the row to be emitted: issued before the arithmetic so their latency is covered
+      uint4 r1[2], r2[2];
+      float nz[2] = {0.f, 0.f};
+      if (EPI && emit) {
+        const long long pix = (long long)oy * p.out_w + ox;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const bool ok = c ? ok1 : ok0;
+          r1[c] = (e.residual && ok) ? __ldg(e.residual + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
+          r2[c] = (e.residual2 && ok) ? __ldg(e.residual2 + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
+          nz[c] = (e.noise && ok) ? nw * __ldg(e.noise + b * e.noise_bstride + pix + c) : 0.f;
+        }
+      }
+      unsigned long long h0[4], h1[4];
+#pragma unroll
+      for (int j = 0; j < kK + 1; ++j) {
+        const uint4 v = lds128(st + (uint32_t)(rr * kStripCols + j) * 128u);
+        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned long long xv = pk2(__uint_as_float(wd[q] << 16), __uint_as_float(wd[q] & 0xFFFF0000u));
+          if (j == 0) h0[q] = fmul2_(xv, fxp[0]);
+          else if (j < kK) h0[q] = ffma2_(xv, fxp[j], h0[q]);
+          if (j == 1) h1[q] = fmul2_(xv, fxp[0]);
+          else if (j > 1) h1[q] = ffma2_(xv, fxp[j - 1], h1[q]);
+        }
+      }
+      // rolling window: slot rr starts output row i (tap 0); slots rr-1, rr-2, rr-3 take taps 1, 2, 3
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[rr][0][q] = fmul2_(h0[q], fyp[0]);
+        acc[rr][1][q] = fmul2_(h1[q], fyp[0]);
+#pragma unroll
+        for (int j = 1; j < kK; ++j) {
+          acc[(rr + kK - j) % kK][0][q] = ffma2_(h0[q], fyp[j], acc[(rr + kK - j) % kK][0][q]);
+          acc[(rr + kK - j) % kK][1][q] = ffma2_(h1[q], fyp[j], acc[(rr + kK - j) % kK][1][q]);
+        }
+      }
+      if (emit) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int slot = (rr + 1) % kK;               // the row that has now seen all kK taps
+        const long long pix = (long long)oy * p.out_w + ox;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!(c ? ok1 : ok0)) continue;
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) unpk2(acc[slot][c][q], v[2 * q], v[2 * q + 1]);
+          if (EPI) {
+            if (e.noise != nullptr || e.bias != nullptr || e.act != 0) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float u = v[q] + nz[c] + bias[q];
+                if (e.act == 3) u = (u > 0.f ? u : u * e.alpha) * e.scale;
+                v[q] = u;
+              }
+            }
+            if (e.residual) add_bf16x8(v, r1[c]);
+            if (e.residual2) add_bf16x8(v, r2[c]);
+          }
+          uint4 o;
+          __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+          y[ybase + (pix + c) * p.cg] = o;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (tid == 0 && k + kStripStages < n_stage) {
+      mbar_wait(&empty[s], phase);
+      mbar_arrive_expect_tx(&full[s], kStageBytes);
+      tma_load_4d(strip_smem + s * kStageBytes, &tmx, &full[s], cz * 64, ix0, iy0 + (k + kStripStages) * kStageRows, b);
+    }
+  }
+}
+
+template <bool EPI>
+int launch_blur_strip(const void *x, void *y, StripParams p, const NhwcEpi &e, const SepTaps &t, int64_t n, int64_t c,
+                      cudaStream_t stream) {
+  auto kern = blur_strip_kernel<EPI>;
+  constexpr int smem = kStripStages * kStageBytes;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  p.n_strips = (p.out_w + kStripW - 1) / kStripW;
+  p.n_chunks = (int)(c / 64);
+  p.cg = (int)(c / 8);
+  // vertical segments only while the strips alone cannot fill the machine (each segment re-reads 3 halo rows)
+  const long long base_blocks = (long long)p.n_strips * p.n_chunks * n;
+  long long n_seg = ((long long)num_sms() * 6 + base_blocks - 1) / base_blocks;
+  const long long max_seg = p.out_h >= 32 ? p.out_h / 32 : 1;
+  if (n_seg > max_seg) n_seg = max_seg;
+  if (n_seg < 1) n_seg = 1;
+  p.seg_rows = (int)((p.out_h + n_seg - 1) / n_seg);
+  p.n_seg = (p.out_h + p.seg_rows - 1) / p.seg_rows;
+  const long long blocks = base_blocks * p.n_seg;
+  VSP_REQUIRE(blocks < 2147483647LL, "blur_strip: grid too large (%lld blocks)", blocks);
+  CUtensorMap tmx;
+  memset(&tmx, 0, sizeof(tmx));
+  uint64_t dims[4] = {(uint64_t)c, (uint64_t)p.in_w, (uint64_t)p.in_h, (uint64_t)n};
+  uint64_t strides[4] = {0, (uint64_t)c * 2, (uint64_t)c * p.in_w * 2, (uint64_t)c * p.in_w * p.in_h * 2};
+  uint32_t box[4] = {64, (uint32_t)kStripCols, (uint32_t)kStageRows, 1};
+  if (int rc = encode_tma(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, nullptr,
+                          CU_TENSOR_MAP_SWIZZLE_NONE))
+    return rc;
+  kern<<<(unsigned)blocks, kStripThreads, smem, stream>>>(tmx, static_cast<uint4 *>(y), p, e, t);
+  return check_launch("blur_strip_kernel");
+}
+
 template <int U, int D, int QX, int QY, int TOW, int TOH, int PZ>
 int launch_tile(UfdParams p, cudaStream_t stream) {
   using C = Cfg<U, D, QX, QY, TOW, TOH, PZ>;
@@ -759,6 +989,16 @@ extern "C" int vsp_blur_sep_nhwc_bf16(const void *x, const float *fy_host, const
     e.scale = epi->scale;
     e.residual = static_cast<const uint4 *>(epi->residual);
     e.residual2 = static_cast<const uint4 *>(epi->residual2);
+  }
+  static const bool strip_on = getenv("VSP_NO_BLUR_STRIP") == nullptr;
+  if (strip_on && c % 64 == 0 && in_w >= kStripCols && in_h >= kStageRows) {
+    StripParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.in_h = (int)in_h; sp.in_w = (int)in_w; sp.out_h = (int)out_h; sp.out_w = (int)out_w;
+    sp.pad_x0 = pad_x0; sp.pad_y0 = pad_y0;
+    const bool has_epi = e.noise || e.bias || e.act != 0 || e.residual || e.residual2;
+    return has_epi ? launch_blur_strip<true>(x, y, sp, e, t, n, c, stream)
+                   : launch_blur_strip<false>(x, y, sp, e, t, n, c, stream);
   }
   constexpr int R = 4;
   const int cg = (int)(c / 8);
