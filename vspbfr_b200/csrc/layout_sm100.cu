@@ -216,6 +216,63 @@ pack_weights_kernel(const float *__restrict__ w, const float *__restrict__ s,
   }
 }
 
+// Vectorised form for the inference prologue (no transpose, cin % 8 == 0): one thread owns 8 consecutive input channels
+// of one output channel for ALL taps — 8*TAPS contiguous fp32 weights, read once with 128-bit loads and reused for kBG
+// samples — and writes one 16-byte bf16 vector per tap and sample (a warp stores 512 contiguous bytes; the scalar kernel
+// above issues 2-byte stores: 1.4 TB/s).
+constexpr int kBG = 4;
+template <int TAPS>
+__global__ void __launch_bounds__(kThreads)
+pack_weights_vec_kernel(const float *__restrict__ w, const float *__restrict__ s, const float *__restrict__ demod,
+                        uint4 *__restrict__ wq, long long cout, long long cin, float wscale, long long n_pad,
+                        long long batch) {
+  const long long kg = cin / 8;
+  const long long idx = blockIdx.x * (long long)kThreads + threadIdx.x;
+  if (idx >= n_pad * kg) return;
+  const long long o = idx / kg, i0 = (idx % kg) * 8;
+  const bool valid = o < cout;
+  float wv[8 * TAPS];
+  if (valid) {
+    const float4 *src = reinterpret_cast<const float4 *>(w + (o * cin + i0) * TAPS);
+#pragma unroll
+    for (int q = 0; q < 2 * TAPS; ++q) {
+      const float4 v = __ldg(src + q);
+      wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8 * TAPS; ++q) wv[q] = 0.f;
+  }
+  const long long b0 = (long long)blockIdx.y * kBG;
+#pragma unroll
+  for (int bb = 0; bb < kBG; ++bb) {
+    const long long b = b0 + bb;
+    if (b >= batch) break;
+    float f[8];
+    const float d = (valid && demod) ? __ldg(demod + b * cout + o) : 1.f;
+    if (s) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4 *>(s + b * cin + i0));
+      const float4 s1 = __ldg(reinterpret_cast<const float4 *>(s + b * cin + i0) + 1);
+      f[0] = s0.x; f[1] = s0.y; f[2] = s0.z; f[3] = s0.w; f[4] = s1.x; f[5] = s1.y; f[6] = s1.z; f[7] = s1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = 1.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= wscale * d;
+    uint4 *dst = wq + (b * TAPS * n_pad + o) * kg + i0 / 8;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      uint4 ov;
+      __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        oh[e] = __floats2bfloat162_rn(wv[(2 * e) * TAPS + t] * f[2 * e], wv[(2 * e + 1) * TAPS + t] * f[2 * e + 1]);
+      dst[(long long)t * n_pad * kg] = ov;
+    }
+  }
+}
+
 // Per-sample raw weight gradients arrive tap-major: G[b][t][o][i] (what wgrad_sm100.cu writes).
 // ---- c[b,o] = demod^2 * sum_{i,t} m*G   (one warp per (b,o))
 __global__ void __launch_bounds__(kThreads)
@@ -368,6 +425,19 @@ extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *
   if (wq) {
     const int64_t n_real = transpose ? cin : cout, k_real = transpose ? cout : cin;
     VSP_REQUIRE(n_pad >= n_real && k_pad >= k_real, "modulate_weights: padded extents smaller than the real ones");
+    const bool vec_ok = !transpose && cin % 8 == 0 && k_pad == cin && (taps == 9 || taps == 1) &&
+                        (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(wq) & 15) == 0 &&
+                        (s == nullptr || (reinterpret_cast<uintptr_t>(s) & 15) == 0);
+    if (vec_ok) {
+      dim3 vgrid((unsigned)ceil_div64(n_pad * (cin / 8), kThreads), (unsigned)ceil_div64(batch, kBG));
+      if (taps == 9)
+        pack_weights_vec_kernel<9><<<vgrid, kThreads, 0, stream>>>(w, s, fold_demod ? demod : nullptr,
+                                                                    static_cast<uint4 *>(wq), cout, cin, wscale, n_pad, batch);
+      else
+        pack_weights_vec_kernel<1><<<vgrid, kThreads, 0, stream>>>(w, s, fold_demod ? demod : nullptr,
+                                                                    static_cast<uint4 *>(wq), cout, cin, wscale, n_pad, batch);
+      return check_launch("pack_weights_vec_kernel");
+    }
     dim3 grid((unsigned)ceil_div64(n_pad * k_pad, kThreads), (unsigned)batch);
     pack_weights_kernel<<<grid, kThreads, 0, stream>>>(w, s, fold_demod ? demod : nullptr,
                                                        static_cast<__nv_bfloat16 *>(wq), cout, cin, taps, wscale,
