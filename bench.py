@@ -346,9 +346,9 @@ def full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev):
 
 def conv_traffic(micro):
     """DRAM bytes (read + written) of all tcgen05 conv launches of one micro-batch, from the committed ncu launch list
-    (profiles/r01_launches_microbatch32_v23.*: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over
-    tools/prof_step.py 32); None when the bench runs at another micro-batch size."""
-    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v23.json")
+    (profiles/r01_launches_microbatch32_v33.*: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
+    dram__bytes_write.sum` over tools/prof_step.py 32); None when the bench runs at another micro-batch size."""
+    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v33.json")
     if micro != 32 or not os.path.exists(path):
         return None
     return json.load(open(path))["conv_kernels"]["dram_bytes"]
