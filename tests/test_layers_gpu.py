@@ -337,3 +337,33 @@ def test_restore_pipeline_front_end_to_hot_path():
     np.testing.assert_allclose(codes.cpu().numpy(), codes2.cpu().numpy(), rtol=1e-4, atol=1e-4)
     want, _ = fp.restore_faces(net, dec, low, codes, [z])
     np.testing.assert_allclose(restored.cpu().numpy(), want.cpu().numpy(), rtol=0, atol=1e-5 * max(1.0, float(want.abs().max())))
+
+
+def test_graphed_pipeline_matches_eager_pipeline():
+    """frontend.GraphedPipeline (encoder + 4-step sampler + hot path as ONE CUDA graph) == the eager pipeline: the hot path on
+    the graph's own codes reproduces its restored image exactly (noise weights are 0), the codes follow new inputs across
+    replays, and with the same generator seed the sampler's x_T — hence the codes — equal the eager run."""
+    from vspbfr_b200 import frontend as fe
+    net, dec = _build_nets()
+    torch.manual_seed(4)
+    size = int(NET["size"])
+    enc = fe.Encoder4Editing(50, "ir_se", stylegan_size=1024)
+    front = fe.WPlusFrontEnd(enc, latent_avg=torch.randn(18, 512) * 0.1, n_latent=18).to(DEV).eval()
+    ddpm = fe.My_DDPM(fe.Code_diffuser(timesteps=4), timesteps=4, linear_start=0.1, linear_end=0.99).to(DEV).eval()
+    g = fe.GraphedPipeline(front, ddpm, dec, net, 2, size=size, device=DEV, tf32=False)
+    prev = None
+    for seed in (21, 22):
+        gen = torch.Generator().manual_seed(seed)
+        low = (torch.rand(2, 3, size, size, generator=gen) * 2 - 1).to(DEV)
+        z = torch.randn(2, 512, generator=gen).to(DEV)
+        torch.manual_seed(seed)
+        restored, image, codes = g(low, z)
+        assert codes.shape == (2, 18, 512) and torch.isfinite(restored).all()
+        want, want_img = fp.restore_faces(net, dec, low, codes, [z])
+        torch.testing.assert_close(restored, want, rtol=0, atol=0)
+        torch.testing.assert_close(image, want_img, rtol=0, atol=0)
+        torch.manual_seed(seed)
+        codes_eager = ddpm(condi_in=front(low))
+        np.testing.assert_allclose(codes.cpu().numpy(), codes_eager.cpu().numpy(), rtol=1e-4, atol=1e-4)
+        assert prev is None or not torch.equal(prev, codes)
+        prev = codes

@@ -13,13 +13,15 @@ namespace {
 
 constexpr int kLinThreads = 256;
 constexpr int kLinRows = 8;     // output rows per block (one per warp)
-constexpr int kLinB = 8;        // samples accumulated per pass
-constexpr int kLinK = 512;      // style elements staged in shared memory per pass
+// kLinB samples are accumulated per pass over kLinK staged style elements (kLinB x kLinK floats of shared memory).
+// Two instantiations: 8 x 512 for small batches, 32 x 256 (32 KB) for micro-batches > 8 — a 32-face micro-batch then streams every
+// weight row ONCE (with 8 samples per pass it was re-streamed and the styles re-staged four times: 0.37 TB/s on the weights).
 
 // One block = kLinRows consecutive output rows of ONE problem (the host pads every problem to a multiple of
 // kLinRows rows in `row_start`), so the block's warps share the problem's style rows: they are staged in shared
 // memory in [kLinB x kLinK] slabs (coalesced) and every warp dots its own weight row (streamed once per slab of
 // samples, 128-bit loads) against them.
+template <int kLinB, int kLinK>
 __global__ void __launch_bounds__(kLinThreads)
 grouped_linear_kernel(const vsp_linear_desc *__restrict__ descs, const int *__restrict__ row_start, int n_problems,
                       const float *__restrict__ x, long long x_bstride, float *__restrict__ y, int batch) {
@@ -91,7 +93,11 @@ extern "C" int vsp_grouped_linear_f32(const vsp_linear_desc *descs_dev, const in
               "grouped_linear: x must be 16-byte aligned with a row stride that is a multiple of 4 floats");
   VSP_REQUIRE(total_rows % kLinRows == 0, "grouped_linear: row_start must pad every problem to a multiple of 8 rows");
   const unsigned blocks = (unsigned)(total_rows / kLinRows);
-  grouped_linear_kernel<<<blocks, kLinThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
-      descs_dev, row_start_dev, n_problems, x, x_bstride, y, batch);
+  if (batch <= 8)
+    grouped_linear_kernel<8, 512><<<blocks, kLinThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        descs_dev, row_start_dev, n_problems, x, x_bstride, y, batch);
+  else
+    grouped_linear_kernel<32, 256><<<blocks, kLinThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        descs_dev, row_start_dev, n_problems, x, x_bstride, y, batch);
   return check_launch("grouped_linear_kernel");
 }

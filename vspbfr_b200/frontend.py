@@ -305,3 +305,43 @@ def restore_pipeline(low_imgs, front: WPlusFrontEnd, diffusion: My_DDPM, decoder
     codes = diffusion(x=low_latent, condi_in=low_latent, training=False, tf32=tf32)
     restored, image = fastpath.restore_faces(net, decoder, low_imgs, codes, noise_styles)
     return restored, image, codes
+
+
+class GraphedPipeline:
+    """One micro-batch of :func:`restore_pipeline` (e4e encoder -> 4-step code diffusion -> sm_100a hot path) captured as
+    ONE CUDA graph: the PyTorch front end alone issues ~1800 small launches per micro-batch, i.e. it is bound by the host's
+    launch rate, not by the GPU.  Same contract as ``fastpath.GraphedRestorer``: fixed micro-batch size, static input /
+    output buffers, noise (the sampler's x_T and the NoiseInjection maps) drawn per replay from the graph-aware generator.
+
+    ``g = GraphedPipeline(front, diffusion, decoder, net, micro); restored, image, codes = g(low, z)``"""
+
+    def __init__(self, front, diffusion, decoder, net, micro, size=None, device=None, warmup=3, tf32=True):
+        from . import _lib
+
+        device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+        size = size or net.size
+        self.micro = micro
+        self.low = torch.zeros(micro, 3, size, size, device=device)
+        self.z = torch.zeros(micro, net.style_dim, device=device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):       # cuDNN algorithm selection, weight / descriptor caches
+                restore_pipeline(self.low, front, diffusion, decoder, net, [self.z], tf32=tf32)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.restored, self.image, self.codes = restore_pipeline(self.low, front, diffusion, decoder, net, [self.z], tf32=tf32)
+        self.launches = _lib.launch_count() - n0
+
+    def __call__(self, low, z, clone=True):
+        if low.shape[0] != self.micro:
+            raise ValueError(f"GraphedPipeline captured for micro-batch {self.micro}, got {low.shape[0]}")
+        self.low.copy_(low, non_blocking=True)
+        self.z.copy_(z, non_blocking=True)
+        self.graph.replay()
+        if clone:
+            return self.restored.clone(), self.image.clone(), self.codes.clone()
+        return self.restored, self.image, self.codes
