@@ -128,6 +128,55 @@ class Encoder4Editing(nn.Module):
         return w
 
 
+class _Stride2(nn.Module):
+    """``MaxPool2d(kernel_size=1, stride=s)`` (helpers.py:101) is a strided view: no kernel launch, no copy."""
+
+    def __init__(self, stride):
+        super().__init__()
+        self.stride = stride
+
+    def forward(self, x):
+        return x[:, :, ::self.stride, ::self.stride]
+
+
+def _fold_bn_into_conv(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> nn.Conv2d:
+    """conv followed by an eval-mode BatchNorm == one conv: w' = w * g / sqrt(var + eps), b' = beta + (b - mean) * g / sqrt(var + eps)."""
+    g = bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)
+    out = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
+                    bias=True).to(device=conv.weight.device, dtype=conv.weight.dtype)
+    b0 = conv.bias.detach() if conv.bias is not None else torch.zeros_like(bn.running_mean)
+    with torch.no_grad():
+        out.weight.copy_(conv.weight.detach() * g.view(-1, 1, 1, 1).to(conv.weight.dtype))
+        out.bias.copy_((bn.bias.detach() + (b0 - bn.running_mean.detach()) * g).to(conv.weight.dtype))
+    return out
+
+
+@torch.no_grad()
+def fold_for_inference_(enc: "Encoder4Editing"):
+    """Inference-only rewrite of the IR-SE backbone (the module tree no longer matches the reference's ``state_dict`` — call it
+    AFTER loading the checkpoint): every BatchNorm that follows a convolution (input layer, second 3x3 of each unit, projection
+    shortcut) is folded into that convolution, ``MaxPool2d(1, 1)`` shortcuts become the identity and ``MaxPool2d(1, 2)`` a
+    strided view.  Removes 28 of the 52 BatchNorm passes and all 21 pooling launches of a forward; the BatchNorm that PRECEDES
+    the first 3x3 stays (zero padding is applied after it, so it cannot be folded exactly)."""
+    if getattr(enc, "_folded", False):
+        return enc
+    assert not enc.training, "fold_for_inference_ needs eval mode (running statistics)"
+    conv, bn, act = enc.input_layer[0], enc.input_layer[1], enc.input_layer[2]
+    enc.input_layer = nn.Sequential(_fold_bn_into_conv(conv, bn), nn.Identity(), act)
+    for unit in enc.body:
+        res = unit.res_layer
+        res[3] = _fold_bn_into_conv(res[3], res[4])
+        res[4] = nn.Identity()
+        sc = unit.shortcut_layer
+        if isinstance(sc, nn.MaxPool2d):
+            stride = sc.stride if isinstance(sc.stride, int) else sc.stride[0]
+            unit.shortcut_layer = nn.Identity() if stride == 1 else _Stride2(stride)
+        else:
+            unit.shortcut_layer = _fold_bn_into_conv(sc[0], sc[1])
+    enc._folded = True
+    return enc
+
+
 # ----------------------------------------------------------------------------------------------
 # code diffuser (4 TACC blocks) and its reverse-diffusion sampler
 # ----------------------------------------------------------------------------------------------
@@ -274,8 +323,12 @@ class WPlusFrontEnd(nn.Module):
         self.n_latent = n_latent
         self.register_buffer("latent_avg", latent_avg if latent_avg is not None else torch.zeros(encoder.style_count, 512))
 
-    def half_precision_(self):
-        """Inference-only: keep the encoder's parameters in bf16, channels-last (no per-call autocast weight casts)."""
+    def half_precision_(self, fold=True):
+        """Inference-only: keep the encoder's parameters in bf16, channels-last (no per-call autocast weight casts), after
+        folding the eval-mode BatchNorms that FOLLOW a convolution into it and dropping the identity shortcuts
+        (``fold_for_inference_``)."""
+        if fold:
+            fold_for_inference_(self.encoder)
         self.encoder.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
         return self
 
