@@ -129,6 +129,16 @@ int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y,
 int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
                               int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
 
+/*
+ * Weight gradient of a 1x1, stride-1, unpadded convolution with 1..8 input channels (NCHW fp32):
+ *   gw[o, i] = sum_{b, p} dy[b, o, p] * x[b, i, p]        dy [batch, cout, hw], x [batch, cin, hw], hw % 4 == 0
+ * Replaces aten::cudnn_convolution_backward_weight (op/conv2d_gradfix.py:180-199) for the RGB-side layers
+ * (LargeConvLayer 3->16, models/RestoreNet.py:725-787; Discriminator stem 3->64, :1218), where the library's
+ * tall-skinny GEMM takes milliseconds.  gw is zeroed by the call (stream-ordered) and accumulated with atomics.
+ */
+int vsp_conv1x1_wgrad_small_f32(const float *dy, const float *x, float *gw, int64_t batch, int64_t cout,
+                                int64_t cin, int64_t hw, void *stream);
+
 /* y[b,p,c] = bf16(x[b,p,c] * s[b,c]) on an NHWC bf16 activation [batch, hw, c] (c % 8 == 0, s [batch, c] fp32):
  * the input-modulated form of ModulatedConv2d (models/RestoreNet.py:481-508, `fused=False`), used where the
  * activation is smaller than the per-sample weights so the convolution can run on shared, cached weights. */

@@ -591,3 +591,18 @@ def test_up2_fused_lowres_shared_weights(b, cin, cout, h, w_):
     yb = torch.from_numpy(upfirdn2d_ref(y.cpu().numpy(), k4.cpu().numpy(), 1, 1, (1, 1))).to(DEV)
     ref = F.leaky_relu(yb * d_ref[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
     assert psnr(out.permute(0, 3, 1, 2).float(), ref) > 45.0
+
+
+@pytest.mark.parametrize("b,cout,cin,h,w", [(2, 16, 3, 64, 64), (3, 20, 5, 12, 12), (1, 64, 3, 96, 40), (4, 7, 8, 10, 6)])
+def test_conv1x1_small_cin_weight_gradient(b, cout, cin, h, w):
+    """Weight gradient of the RGB-side 1x1 convolutions (Cin <= 8: LargeConvLayer 3->16, Discriminator stem 3->64) through
+    conv2d_gradfix == autograd of F.conv2d in fp32 (streaming-reduction kernel, fp32 throughout)."""
+    from vspbfr_b200.op import conv2d_gradfix
+    torch.manual_seed(b * 100 + cout)
+    x = torch.randn(b, cin, h, w, device="cuda")
+    wt = torch.randn(cout, cin, 1, 1, device="cuda", requires_grad=True)
+    go = torch.randn(b, cout, h, w, device="cuda")
+    (got,) = torch.autograd.grad(conv2d_gradfix.conv2d(x, wt), wt, go)
+    w2 = wt.detach().clone().requires_grad_(True)
+    (want,) = torch.autograd.grad(torch.nn.functional.conv2d(x, w2), w2, go)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4 * float(want.abs().max()))

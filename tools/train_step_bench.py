@@ -59,6 +59,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--r1", type=float, default=10.0)
     ap.add_argument("--d_reg_every", type=int, default=16)
+    ap.add_argument("--profile", type=int, default=0, help="N > 0: print the N kernels with the most device time of one eager iteration")
+    ap.add_argument("--graph", type=int, default=0,
+                    help="1 (single GPU only): capture the whole iteration (D, R1, G, both Adam steps, EMA) as ONE CUDA graph")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -82,8 +85,11 @@ def main():
         generator = torch.nn.parallel.DistributedDataParallel(generator, device_ids=[local], broadcast_buffers=False)
         discriminator = torch.nn.parallel.DistributedDataParallel(discriminator, device_ids=[local], broadcast_buffers=False)
     g_reg_ratio, d_reg_ratio = 4 / 5, args.d_reg_every / (args.d_reg_every + 1)
-    g_optim = torch.optim.Adam(generator.parameters(), lr=0.002 * g_reg_ratio, betas=(0.0, 0.99 ** g_reg_ratio))
-    d_optim = torch.optim.Adam(discriminator.parameters(), lr=0.002 * d_reg_ratio, betas=(0.0, 0.99 ** d_reg_ratio))
+    use_graph = bool(args.graph) and world == 1
+    g_optim = torch.optim.Adam(generator.parameters(), lr=0.002 * g_reg_ratio, betas=(0.0, 0.99 ** g_reg_ratio),
+                               capturable=use_graph)
+    d_optim = torch.optim.Adam(discriminator.parameters(), lr=0.002 * d_reg_ratio, betas=(0.0, 0.99 ** d_reg_ratio),
+                               capturable=use_graph)
 
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     real_img = (torch.rand(args.batch, 3, args.size, args.size, generator=g) * 2 - 1).to(dev)
@@ -145,11 +151,46 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), out
 
+    eager_step = step
+    if use_graph:
+        # whole-iteration capture: eager warm-up on a side stream (optimizer state, cuDNN plans), then ONE graph whose replay
+        # is the complete iteration — the eager loop is bound by the host (same step time at batch 4 and 8)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, args.warmup)):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        generator.zero_grad(set_to_none=True)
+        discriminator.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            static_out = eager_step()
+        per_graph = _lib.launch_count() - n0
+
+        def step(sync=True):
+            graph.replay()
+            return static_out
     for _ in range(args.warmup):
         step()
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+            eager_step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=args.profile, max_name_column_width=90),
+              file=sys.stderr)
+        print(prof.key_averages(group_by_input_shape=True).table(sort_by="cuda_time_total", row_limit=25,
+                                                                 max_name_column_width=40, max_shapes_column_width=90),
+              file=sys.stderr)
     l0 = _lib.launch_count()
     t, (d_l, r1_l, g_l) = timed(args.steps)
     launches = _lib.launch_count() - l0
+    if use_graph:
+        launches = per_graph * args.steps
     t_nosync = timed(args.steps, sync=False)[0] if world > 1 else t
     if rank == 0:
         print(json.dumps({
@@ -158,7 +199,8 @@ def main():
             "ms_per_step_no_allreduce": 1e3 * t_nosync / args.steps,
             "allreduce_exposed_frac": max(0.0, 1 - t_nosync / t),
             "config": {"workload": "restoration_train.py step (D + R1 double backward + G + EMA), percept/id weights 0",
-                       "size": args.size, "batch_per_gpu": args.batch, "parallelism": f"DDP x{world} (NCCL)"},
+                       "size": args.size, "batch_per_gpu": args.batch, "parallelism": f"DDP x{world} (NCCL)",
+                       "launch": "one CUDA graph replay per iteration" if use_graph else "eager"},
             "losses": {"d": float(d_l), "r1": float(r1_l), "g": float(g_l)},
             "gpu_launches": int(launches), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
     if world > 1:

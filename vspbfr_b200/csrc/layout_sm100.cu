@@ -488,6 +488,80 @@ extern "C" int vsp_modconv_weight_style_grad(const float *gw, const float *w, co
   return 0;
 }
 
+// ---- weight gradient of a 1x1 convolution with very few input channels (the RGB-side layers: LargeConvLayer 3->16,
+// the Discriminator's 3->64 stem; models/RestoreNet.py:725-787, :1218).  gw[o,i] = sum_{b,p} dy[b,o,p] * x[b,i,p] is a
+// [Cout x Cin] reduction over ~1e6 pixels: ATen hands it to a tall-skinny GEMM that takes 3.5-3.8 ms per call at 512^2
+// (29 ms of a 160 ms training step); as a streaming reduction it is a read of dy (17-67 MB): one block owns 8 output
+// channels x a chunk of pixels of one sample, accumulates 8 x Cin partial sums per thread over 128-bit loads, reduces them
+// with shuffles + shared memory and issues one atomic per (o, i).
+constexpr int kSmallCin = 8;
+__global__ void __launch_bounds__(kThreads)
+conv1x1_wgrad_small_kernel(const float4 *__restrict__ dy, const float4 *__restrict__ x, float *__restrict__ gw,
+                           long long p4, int cout, int cin, int iters) {
+  __shared__ float red[kThreads / 32][8 * kSmallCin];
+  const int og = blockIdx.y * 8;
+  const long long b = blockIdx.z;
+  float acc[8][kSmallCin];
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int i = 0; i < kSmallCin; ++i) acc[o][i] = 0.f;
+  const float4 *dyb = dy + (b * cout + og) * p4;
+  const float4 *xb = x + b * cin * p4;
+  for (int it = 0; it < iters; ++it) {
+    const long long p = ((long long)blockIdx.x * iters + it) * kThreads + threadIdx.x;
+    if (p >= p4) break;
+    float4 xv[kSmallCin];
+#pragma unroll
+    for (int i = 0; i < kSmallCin; ++i) xv[i] = i < cin ? __ldg(xb + i * p4 + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      if (og + o >= cout) break;
+      const float4 g = ld_stream_f4(dyb + o * p4 + p);
+#pragma unroll
+      for (int i = 0; i < kSmallCin; ++i)
+        acc[o][i] = fmaf(g.x, xv[i].x, fmaf(g.y, xv[i].y, fmaf(g.z, xv[i].z, fmaf(g.w, xv[i].w, acc[o][i]))));
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+#pragma unroll
+    for (int i = 0; i < kSmallCin; ++i) {
+      const float v = warp_sum(acc[o][i]);
+      if (lane == 0) red[warp][o * kSmallCin + i] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 8 * kSmallCin) {
+    const int o = threadIdx.x / kSmallCin, i = threadIdx.x % kSmallCin;
+    if (og + o < cout && i < cin) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
+      atomicAdd(gw + (long long)(og + o) * cin + i, v);
+    }
+  }
+}
+
+extern "C" int vsp_conv1x1_wgrad_small_f32(const float *dy, const float *x, float *gw, int64_t batch, int64_t cout,
+                                           int64_t cin, int64_t hw, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 1 && cout >= 1 && cin >= 1 && cin <= kSmallCin && hw >= 4 && hw % 4 == 0,
+              "conv1x1_wgrad_small: needs 1 <= cin <= 8 and a pixel count that is a multiple of 4");
+  VSP_REQUIRE(dy && x && gw, "conv1x1_wgrad_small: null pointer");
+  VSP_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0,
+              "conv1x1_wgrad_small: tensors must be 16-byte aligned");
+  VSP_REQUIRE(batch <= 65535 && cout <= 8 * 65535, "conv1x1_wgrad_small: extent too large");
+  VSP_CUDA(cudaMemsetAsync(gw, 0, sizeof(float) * cout * cin, stream));
+  const long long p4 = hw / 4;
+  const int iters = 8;
+  dim3 grid((unsigned)ceil_div64(p4, (long long)kThreads * iters), (unsigned)ceil_div64(cout, 8), (unsigned)batch);
+  conv1x1_wgrad_small_kernel<<<grid, kThreads, 0, stream>>>(reinterpret_cast<const float4 *>(dy),
+                                                            reinterpret_cast<const float4 *>(x), gw, p4, (int)cout,
+                                                            (int)cin, iters);
+  return check_launch("conv1x1_wgrad_small_kernel");
+}
+
 extern "C" int vsp_scale_nhwc_bf16(const void *x, const float *s, void *y, int64_t batch, int64_t hw, int64_t c,
                                    void *stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
