@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -73,16 +74,32 @@ def _prof(name, flops, fn, detail="", nbytes=0.0):
 # thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------
 
+_nhwc_memo = [None]     # (weakref to the source tensor, its _version, c_pad, converted tensor) of the latest plain conversion
+
+
 def nchw_to_nhwc_bf16(x, scale_nc=None, c_pad=None):
-    """[N,C,H,W] fp32 -> [N,H,W,c_pad] bf16 (optionally * scale_nc[n,c]); extra channels are zero."""
+    """[N,C,H,W] fp32 -> [N,H,W,c_pad] bf16 (optionally * scale_nc[n,c]); extra channels are zero.
+
+    The latest un-scaled conversion is memoised on the identity and version of its source: the four dilated branches of a
+    SMART layer (models/RestoreNet.py:229-233) convert the same input in forward and again in backward — a quarter of the
+    ~500 layout conversions of a training iteration."""
     n, c, h, w = x.shape
     c_pad = c_pad or _round_up(c, 8)
-    x = x.contiguous()
+    memo = _nhwc_memo[0]
+    if (scale_nc is None and memo is not None and memo[0]() is x and memo[1] == x._version and memo[2] == c_pad
+            and not torch.cuda.is_current_stream_capturing()):
+        return memo[3]
+    xc = x.contiguous()
     y = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
     if y.numel():
         with torch.cuda.device(x.device):
-            rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16(ptr(x), ptr(scale_nc), ptr(y), n, c, h * w, c_pad, stream_ptr())
+            rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16(ptr(xc), ptr(scale_nc), ptr(y), n, c, h * w, c_pad, stream_ptr())
         _lib.check(rc, "nchw_f32_to_nhwc_bf16")
+    if scale_nc is None and not torch.cuda.is_current_stream_capturing():
+        try:
+            _nhwc_memo[0] = (weakref.ref(x), x._version, c_pad, y)
+        except TypeError:
+            _nhwc_memo[0] = None
     return y
 
 
@@ -480,7 +497,9 @@ class ModulatedConv2dFunction(Function):
         wscale = 1.0 / math.sqrt(cin * k * k)
         w4 = weight.reshape(cout, cin, k, k)
         xq = nchw_to_nhwc_bf16(x)
-        wq, d = pack_weights(w4, s, wscale=wscale, want_demod=demodulate)
+        # demodulation from sum_t W^2 (one well-parallelised pass over the weights + a [B,Cout] pass over it) instead of the
+        # warp-per-(b,o) walk over all of W (52 us per call at 512x512x9, 165 calls per training iteration)
+        wq, d = pack_weights(w4, s, wscale=wscale, want_demod=demodulate, wsq=weight_sumsq(w4) if demodulate else None)
         epi = make_epilogue(row_scale=d) if demodulate else None
         if mode == "up":
             if dilation != 1:
