@@ -297,6 +297,11 @@ def main():
             "peak_source": pk["source"] + " (sustained)",
             "launches_per_microbatch": conv["launches"], "algorithmic_gflop_per_image": step_flops / micro / 1e9,
             "share_of_step": conv["seconds"] / (t_res / args.steps / n_micro),
+            # the same instrumented pass per launch family (algorithmic FLOPs and bytes of the layer each launch replaces)
+            "by_kind": {name: {"launches": v["launches"], "ms": 1e3 * v["seconds"],
+                               "tflops": v["flops"] / max(v["seconds"], 1e-9) / 1e12,
+                               "gbs": v["bytes"] / max(v["seconds"], 1e-9) / 1e9}
+                        for name, v in sorted(summ.items(), key=lambda kv: -kv[1]["seconds"])},
         }
         # config 2 conv launch and config 1 upfirdn2d launch in isolation (burst peaks)
         result["full_pipeline"] = full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev,

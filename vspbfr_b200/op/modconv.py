@@ -50,12 +50,13 @@ class KernelProfiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for name, flops, s, e in self.records:
-            a = agg.setdefault(name, [0, 0.0, 0.0])
+        for (name, flops, s, e), (_, nbytes) in zip(self.records, self.details):
+            a = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
             a[0] += 1
             a[1] += flops
             a[2] += s.elapsed_time(e) * 1e-3
-        return {k: {"launches": v[0], "flops": v[1], "seconds": v[2]} for k, v in agg.items()}
+            a[3] += nbytes
+        return {k: {"launches": v[0], "flops": v[1], "seconds": v[2], "bytes": v[3]} for k, v in agg.items()}
 
 
 _profiler = None
