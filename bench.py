@@ -37,7 +37,7 @@ import torch  # noqa: E402
 
 METRIC = "restored_faces_per_sec_512"
 UNIT = "faces/s"
-TOTAL_IMAGES = 256
+TOTAL_IMAGES = int(os.environ.get("VSP_BENCH_IMAGES", "256"))    # BASELINE configs[3]: 256 (the override is for experiments)
 SIZE, DEC_SIZE, STYLE_DIM, N_MLP = 512, 1024, 512, 8
 GRAPH_DEFAULT = int(os.environ.get("VSP_BENCH_GRAPH", "1"))
 

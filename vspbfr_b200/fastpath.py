@@ -651,23 +651,34 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
 
 
 @torch.no_grad()
-def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent=16):
-    """The hot path of one restoration batch (restoration_test.py:130-131): style decoder features from
-    the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512)."""
-    if noise_styles is None:
-        noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
-    _noise_pool.begin(low_imgs.device)
-    size = low_imgs.shape[-1]
+def decode_stage(decoder, codes, size, out_n_latent=16):
+    """First half of :func:`restore_faces`: style decoder features (+ its image, pooled to ``size``) from the w+ codes.
+    Needs only the codes — the degraded images are not touched until :func:`restore_stage`."""
+    _noise_pool.begin(codes.device)
     fuse_pool = decoder.size == 2 * size and len(decoder.to_rgbs) > 0 and decoder.to_rgbs[-1].upsample.factor == 2
     image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True, pool_image=fuse_pool)
-    feats = feats[:out_n_latent]
-    restored = restoration_forward(net, low_imgs, feats, codes, noise_styles)
-    size = low_imgs.shape[-1]
     if image.shape[-1] != size:
         # face_pool (e4e/models/psp.py:245-246): AdaptiveAvgPool2d to (size, size) is an exact k x k mean when divisible
         k = image.shape[-1] // size
         image = (F.avg_pool2d(image, k) if image.shape[-1] == k * size and image.shape[-2] == k * size
                  else F.adaptive_avg_pool2d(image, (size, size)))
+    return image, feats[:out_n_latent]
+
+
+@torch.no_grad()
+def restore_stage(net, low_imgs, feats, codes, noise_styles):
+    """Second half of :func:`restore_faces`: the restoration network on the degraded images and the decoder features."""
+    return restoration_forward(net, low_imgs, feats, codes, noise_styles)
+
+
+@torch.no_grad()
+def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent=16):
+    """The hot path of one restoration batch (restoration_test.py:130-131): style decoder features from
+    the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512)."""
+    if noise_styles is None:
+        noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
+    image, feats = decode_stage(decoder, codes, low_imgs.shape[-1], out_n_latent)
+    restored = restore_stage(net, low_imgs, feats, codes, noise_styles)
     return restored, image
 
 
@@ -676,7 +687,8 @@ class GraphedRestorer:
     step in a CUDA graph").  Every entry point of the C ABI is capture-safe (explicit stream, no allocation, no sync;
     tensor maps are encoded on the host from pointers that the graph's private memory pool keeps fixed), so after two
     eager warm-up passes (which fill the weight / descriptor caches) the ~270 launches of a micro-batch are recorded once
-    and replayed with a single ``cudaGraphLaunch``: no Python, ctypes or allocator work per batch.  Noise is still drawn
+    and replayed with two ``cudaGraphLaunch`` calls (decoder half, restorer half): no Python, ctypes or allocator work per
+    batch.  Noise is still drawn
     per replay (the CUDA generator's Philox offset is graph-aware).
 
     ``g = GraphedRestorer(net, decoder, micro); restored, image = g(low, codes, z)`` — inputs must have exactly
@@ -698,19 +710,29 @@ class GraphedRestorer:
                 restore_faces(net, decoder, self.low, self.codes, [self.z])
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
+        # two graphs sharing one memory pool: the decoder half needs only the codes, so a caller that streams its inputs
+        # from the host can start it while the (200x larger) image copy is still in flight (``before_low``)
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_restore = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
-            self.restored, self.image = restore_faces(net, decoder, self.low, self.codes, [self.z])
-        self.launches = _lib.launch_count() - n0          # sm_100a kernels of this library inside one replay
+            self.image, feats = decode_stage(decoder, self.codes, size)
+        with torch.cuda.graph(self.graph_restore, pool=self.graph.pool()):
+            self.restored = restore_stage(net, self.low, feats, self.codes, [self.z])
+        self.launches = _lib.launch_count() - n0          # sm_100a kernels of this library inside one replay of both
 
-    def __call__(self, low, codes, z, clone=True):
+    def __call__(self, low, codes, z, clone=True, before_low=None):
+        """``before_low``: optional callable run after the decoder half has been enqueued and before ``low`` is read (e.g.
+        ``lambda: stream.wait_event(low_arrived)``)."""
         if low.shape[0] != self.micro:
             raise ValueError(f"GraphedRestorer captured for micro-batch {self.micro}, got {low.shape[0]}")
-        self.low.copy_(low, non_blocking=True)
         self.codes.copy_(codes, non_blocking=True)
         self.z.copy_(z, non_blocking=True)
         self.graph.replay()
+        if before_low is not None:
+            before_low()
+        self.low.copy_(low, non_blocking=True)
+        self.graph_restore.replay()
         if clone:
             return self.restored.clone(), self.image.clone()
         return self.restored, self.image

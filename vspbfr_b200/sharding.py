@@ -6,6 +6,7 @@ the only communication is a barrier and a MAX-reduction of the device-side elaps
 """
 from __future__ import annotations
 
+import os
 from typing import Iterator, Tuple
 
 
@@ -79,6 +80,8 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
     stage = [tuple(torch.empty((micro,) + tuple(x.shape[1:]), dtype=x.dtype, device=device) for x in (low_h, codes_h, noise_z_h))
              for _ in range(2)]
     loaded = [torch.cuda.Event() for _ in range(2)]       # staging set i holds its batch
+    loaded_small = [torch.cuda.Event() for _ in range(2)] # ... its codes and noise vectors (copied first: the decoder half needs only them)
+    split = restorer is not None and hasattr(restorer, "graph_restore") and os.environ.get("VSP_NO_SPLIT_H2D") is None
     consumed = [torch.cuda.Event() for _ in range(2)]     # the kernels reading staging set i have been enqueued and finished
     copied = [None, None]                                  # (event, tensor) of the device->host copy two batches back
     h2d.wait_stream(compute)
@@ -89,8 +92,10 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
         with torch.cuda.stream(h2d):
             if i >= 2:
                 h2d.wait_event(consumed[k])
-            for dst, src in zip(stage[k], (low_h, codes_h, noise_z_h)):
+            for dst, src in zip(stage[k][1:], (codes_h, noise_z_h)):
                 dst[:e - s].copy_(src[s:e], non_blocking=True)
+            loaded_small[k].record(h2d)
+            stage[k][0][:e - s].copy_(low_h[s:e], non_blocking=True)
             loaded[k].record(h2d)
 
     stage_in(0)
@@ -98,12 +103,17 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
         k = i & 1
         if i + 1 < len(spans):
             stage_in(i + 1)                                # prefetch while this batch computes
-        compute.wait_event(loaded[k])
         lo, co, zz = (t[:e - s] for t in stage[k])
-        if restorer is not None and e - s == micro:
-            restored, _ = restorer(lo, co, zz)
+        if split and e - s == micro:
+            # the style-decoder half starts as soon as the codes are on the device; the image copy overlaps it
+            compute.wait_event(loaded_small[k])
+            restored, _ = restorer(lo, co, zz, before_low=lambda k=k: compute.wait_event(loaded[k]))
         else:
-            restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
+            compute.wait_event(loaded[k])
+            if restorer is not None and e - s == micro:
+                restored, _ = restorer(lo, co, zz)
+            else:
+                restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
         consumed[k].record(compute)
         if copied[k] is not None:
             copied[k][0].synchronize()                     # long finished; lets the tensor two batches back be freed safely
