@@ -183,19 +183,42 @@ upfirdn2d_tile_kernel(const UfdParams p, const __grid_constant__ CUtensorMap tma
       }
       mbar_wait(&bars[it & 1], (it >> 1) & 1);
     } else {
-      // coalesced LDG staging with zero fill
-#pragma unroll 4
-      for (int idx = tid; idx < C::TILE_FLOATS; idx += kThreads) {
-        const int c = idx % C::TIW;
-        const int rz = idx / C::TIW;
+      // Rows whose pitch is not a multiple of 16 bytes (odd widths: the (2H+1)^2 output of a stride-2 transposed conv)
+      // cannot be described to the TMA.  Staging walks each tile row in ALIGNED 16-byte vectors of the flat tensor (one
+      // LDG.128 + four predicated STS per vector instead of four LDG.32 with per-element index arithmetic; a 4-byte
+      // cp.async ring was tried and is slower); vectors that touch the tensor's first / last bytes fall back to scalars.
+      constexpr int NV = (C::TIW + 6) / 4;                 // vectors overlapping a row at any misalignment
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+      const long long total = p.major * (long long)p.in_h * p.in_w;
+      for (int t = tid; t < PZ * C::TIH * NV; t += kThreads) {
+        const int vi = t % NV;
+        const int rz = t / NV;
         const int r = rz % C::TIH;
         const int z = rz / C::TIH;
-        const int ix = ix_base + c, iy = iy_base + r;
+        const int iy = iy_base + r;
         const long long pl = pz0 + z;
-        float v = 0.f;
-        if (ix >= 0 && ix < p.in_w && iy >= 0 && iy < p.in_h && pl < p.major)
-          v = ld_stream_f1(p.x + (pl * p.in_h + iy) * (long long)p.in_w + ix);
-        tile[idx] = v;
+        const bool row_ok = iy >= 0 && iy < p.in_h && pl < p.major;
+        const long long g0 = (pl * p.in_h + iy) * (long long)p.in_w + ix_base;      // flat index of column 0 (may be < 0)
+        const int a = (int)(g0 & 3);                                               // two's complement: right for negatives
+        const long long gv = g0 - a + 4LL * vi;                                     // aligned vector start
+        const int c0 = 4 * vi - a;                                                  // its first column in the tile row
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row_ok) {
+          if (vec_ok && gv >= 0 && gv + 3 < total) {
+            const float4 q = ld_stream_f4(reinterpret_cast<const float4 *>(p.x + gv));
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gv + e >= 0 && gv + e < total) v[e] = ld_stream_f1(p.x + gv + e);
+          }
+        }
+        float *dst = tile + (z * C::TIH + r) * C::TIW;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c0 + e, ix = ix_base + c;
+          if (c >= 0 && c < C::TIW) dst[c] = (row_ok && ix >= 0 && ix < p.in_w) ? v[e] : 0.f;
+        }
       }
       __syncthreads();
     }
