@@ -139,6 +139,18 @@ int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
 int vsp_conv1x1_wgrad_small_f32(const float *dy, const float *x, float *gw, int64_t batch, int64_t cout,
                                 int64_t cin, int64_t hw, void *stream);
 
+/*
+ * Tail of an IR-SE residual unit of the e4e encoder (e4e/models/encoders/helpers.py:97-123), channels-last bf16, one pass:
+ *   y[n,p,c] = res[n,p,c] * gate[n,c] + shortcut[n,p,c]          (SE scale + residual add)
+ *   z[n,p,c] = bf16(y) * bn_a[c] + bn_b[c]                       (the next unit's leading eval BatchNorm; z may be NULL)
+ * res / y / z [batch, h, w, c] dense NHWC bf16 (c % 8 == 0), gate [batch, c] fp32, bn_a / bn_b [c] fp32.  `shortcut` is
+ * addressed as n*sc_n_stride + y*sc_h_stride + x*sc_w_stride + c (elements; multiples of 8), so the strided view that
+ * MaxPool2d(1, 2) amounts to needs no copy.  First piece of SURVEY.md §8 f-2 (front end) on own kernels.
+ */
+int vsp_se_tail_nhwc_bf16(const void *res, const float *gate, const void *shortcut, void *y, void *z,
+                          const float *bn_a, const float *bn_b, int64_t batch, int64_t h, int64_t w, int64_t c,
+                          int64_t sc_n_stride, int64_t sc_h_stride, int64_t sc_w_stride, void *stream);
+
 /* y[b,p,c] = bf16(x[b,p,c] * s[b,c]) on an NHWC bf16 activation [batch, hw, c] (c % 8 == 0, s [batch, c] fp32):
  * the input-modulated form of ModulatedConv2d (models/RestoreNet.py:481-508, `fused=False`), used where the
  * activation is smaller than the per-sample weights so the convolution can run on shared, cached weights. */

@@ -367,3 +367,29 @@ def test_graphed_pipeline_matches_eager_pipeline():
         np.testing.assert_allclose(codes.cpu().numpy(), codes_eager.cpu().numpy(), rtol=1e-4, atol=1e-4)
         assert prev is None or not torch.equal(prev, codes)
         prev = codes
+
+
+def test_encoder_fused_unit_tail_matches_plain_composition(monkeypatch):
+    """IR-SE backbone in inference form (BatchNorm folded, bf16 channels-last): SE scale + shortcut add + next BatchNorm as one
+    vsp_se_tail_nhwc_bf16 pass per unit == the three library elementwise passes, to bf16 rounding (identity, strided-view
+    and projection shortcuts all occur in the 24 units)."""
+    from vspbfr_b200 import _lib
+    from vspbfr_b200 import frontend as fe
+    torch.manual_seed(8)
+    enc = fe.Encoder4Editing(50, "ir_se").eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.2)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    front = fe.WPlusFrontEnd(enc, n_latent=18).to(DEV).eval().half_precision_()
+    img = torch.rand(2, 3, 128, 128, device=DEV) * 2 - 1
+    n0 = _lib.launch_count()
+    got = front(img)
+    assert _lib.launch_count() - n0 == 24                       # one fused tail per residual unit
+    monkeypatch.setenv("VSP_NO_SE_TAIL", "1")
+    want = front(img)
+    assert _lib.launch_count() - n0 == 24
+    err = float((got - want).abs().max())
+    assert err <= 3e-2 * float(want.abs().max()), (err, float(want.abs().max()))

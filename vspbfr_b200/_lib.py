@@ -174,6 +174,7 @@ SIGNATURES = {
     "vsp_blur_sep_nhwc_bf16": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), c_void_p, c_int64, c_int64, c_int64,
                                        c_int64, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(ConvEpilogue), c_void_p]),
     "vsp_scale_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "vsp_se_tail_nhwc_bf16": (c_int, [c_void_p] * 7 + [c_int64] * 7 + [c_void_p]),
     "vsp_conv1x1_wgrad_small_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "vsp_conv2d_branches_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                          c_int, POINTER(c_int), c_int, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),

@@ -562,6 +562,78 @@ extern "C" int vsp_conv1x1_wgrad_small_f32(const float *dy, const float *x, floa
   return check_launch("conv1x1_wgrad_small_kernel");
 }
 
+// ---- tail of an IR-SE residual unit (e4e encoder, helpers.py:97-123), channels-last bf16:
+//   y = res * gate[n,c] + shortcut            (SE scale + residual add)
+//   z = bf16(y) * bn_a[c] + bn_b[c]           (the NEXT unit's leading eval-mode BatchNorm; optional)
+// One pass instead of three (mul, add, batch_norm) over the activation: reads res + shortcut, writes y (+ z).  The shortcut
+// may be a strided view (MaxPool2d(1, 2) == x[:, :, ::2, ::2]): its pixel strides are passed in elements.
+__global__ void __launch_bounds__(kThreads)
+se_tail_nhwc_kernel(const uint4 *__restrict__ res, const float *__restrict__ gate, const __nv_bfloat16 *__restrict__ sc,
+                    uint4 *__restrict__ y, uint4 *__restrict__ z, const float *__restrict__ bn_a,
+                    const float *__restrict__ bn_b, long long total, int h, int w, int cg, long long sc_n, long long sc_h,
+                    long long sc_w) {
+  for (long long idx = blockIdx.x * (long long)kThreads + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * kThreads) {
+    const int g = (int)(idx % cg);
+    long long t = idx / cg;
+    const int xx = (int)(t % w); t /= w;
+    const int yy = (int)(t % h);
+    const long long n = t / h;
+    const uint4 rv = __ldg(res + idx);
+    const uint4 sv = __ldg(reinterpret_cast<const uint4 *>(sc + n * sc_n + yy * sc_h + xx * sc_w + g * 8));
+    const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gate + n * cg * 8 + g * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4 *>(gate + n * cg * 8 + g * 8) + 1);
+    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const __nv_bfloat162 *rh = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+    const __nv_bfloat162 *sh = reinterpret_cast<const __nv_bfloat162 *>(&sv);
+    uint4 yo;
+    __nv_bfloat162 *yh = reinterpret_cast<__nv_bfloat162 *>(&yo);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 r2 = __bfloat1622float2(rh[i]), s2 = __bfloat1622float2(sh[i]);
+      yh[i] = __floats2bfloat162_rn(fmaf(r2.x, gv[2 * i], s2.x), fmaf(r2.y, gv[2 * i + 1], s2.y));
+    }
+    y[idx] = yo;
+    if (z != nullptr) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4 *>(bn_a + g * 8)), a1 = __ldg(reinterpret_cast<const float4 *>(bn_a + g * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bn_b + g * 8)), b1 = __ldg(reinterpret_cast<const float4 *>(bn_b + g * 8) + 1);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 zo;
+      __nv_bfloat162 *zh = reinterpret_cast<__nv_bfloat162 *>(&zo);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 y2 = __bfloat1622float2(yh[i]);       // the rounded y, as the separate BatchNorm pass would read it
+        zh[i] = __floats2bfloat162_rn(fmaf(y2.x, av[2 * i], bv[2 * i]), fmaf(y2.y, av[2 * i + 1], bv[2 * i + 1]));
+      }
+      z[idx] = zo;
+    }
+  }
+}
+
+extern "C" int vsp_se_tail_nhwc_bf16(const void *res, const float *gate, const void *shortcut, void *y, void *z,
+                                     const float *bn_a, const float *bn_b, int64_t batch, int64_t h, int64_t w, int64_t c,
+                                     int64_t sc_n_stride, int64_t sc_h_stride, int64_t sc_w_stride, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 0 && h >= 0 && w >= 0 && c >= 8 && c % 8 == 0, "se_tail: channels must be a positive multiple of 8");
+  if (batch == 0 || h == 0 || w == 0) return 0;
+  VSP_REQUIRE(res && gate && shortcut && y && (z == nullptr || (bn_a && bn_b)), "se_tail: null pointer");
+  VSP_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(shortcut) | reinterpret_cast<uintptr_t>(y) |
+                reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(gate) | reinterpret_cast<uintptr_t>(bn_a) |
+                reinterpret_cast<uintptr_t>(bn_b)) & 15) == 0 &&
+                  ((sc_n_stride | sc_h_stride | sc_w_stride) & 7) == 0,
+              "se_tail: pointers must be 16-byte aligned and shortcut strides multiples of 8 elements");
+  const long long total = batch * h * w * (c / 8);
+  long long nb = (total + kThreads - 1) / kThreads;
+  if (nb > (long long)num_sms() * 32) nb = (long long)num_sms() * 32;
+  se_tail_nhwc_kernel<<<(unsigned)nb, kThreads, 0, stream>>>(static_cast<const uint4 *>(res), gate,
+                                                            static_cast<const __nv_bfloat16 *>(shortcut),
+                                                            static_cast<uint4 *>(y), static_cast<uint4 *>(z), bn_a, bn_b,
+                                                            total, (int)h, (int)w, (int)(c / 8), sc_n_stride, sc_h_stride,
+                                                            sc_w_stride);
+  return check_launch("se_tail_nhwc_kernel");
+}
+
 extern "C" int vsp_scale_nhwc_bf16(const void *x, const float *s, void *y, int64_t batch, int64_t hw, int64_t c,
                                    void *stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -15,6 +15,7 @@ sampler of `My_DDPM` (ldm/ddpm.py:253-430).  `restore_pipeline` is restoration_t
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -109,13 +110,64 @@ class Encoder4Editing(nn.Module):
         self.latlayer1 = nn.Conv2d(256, 512, kernel_size=1, stride=1, padding=0)
         self.latlayer2 = nn.Conv2d(128, 512, kernel_size=1, stride=1, padding=0)
 
-    def forward(self, x):
-        x = self.input_layer(x)
+    def _body_fused(self, x):
+        """Inference form of the backbone after ``fold_for_inference_`` on a CUDA bf16 channels-last activation: per unit,
+        SE scale + shortcut add + the NEXT unit's leading BatchNorm run as ONE pass (vsp_se_tail_nhwc_bf16) instead of three
+        elementwise launches; convolutions / PReLU / the SE gate stay with the library.  Returns the three FPN taps."""
+        from . import _lib
+
+        lib = _lib.load()
+        affine = getattr(self, "_bn1_affine", None)
+        if affine is None:      # eval-mode BatchNorm as y * a + b, fp32 (cached: weights are frozen after the fold)
+            affine = []
+            for unit in self.body:
+                bn = unit.res_layer[0]
+                a = (bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)).contiguous()
+                affine.append((a, (bn.bias.detach().float() - bn.running_mean.detach().float() * a).contiguous()))
+            self._bn1_affine = affine
         taps = {}
+        z = self.body[0].res_layer[0](x)
+        n_units = len(self.body)
         for i, unit in enumerate(self.body):
-            x = unit(x)
+            res = unit.res_layer
+            r = res[3](res[2](res[1](z)))
+            se = res[5] if len(res) > 5 else None
+            n, c, h, w = r.shape
+            if se is not None:
+                gate = se.sigmoid(se.fc2(se.relu(se.fc1(se.avg_pool(r))))).float().reshape(n, c).contiguous()
+            else:
+                gate = torch.ones(n, c, device=r.device, dtype=torch.float32)
+            sc = unit.shortcut_layer(x)
+            ok = (r.is_contiguous(memory_format=torch.channels_last) and sc.stride(1) == 1 and c % 8 == 0
+                  and all(st % 8 == 0 for st in (sc.stride(0), sc.stride(2), sc.stride(3))) and sc.shape == r.shape)
+            if not ok:          # unusual layout: the plain composition
+                x = r * gate.to(r.dtype).view(n, c, 1, 1) + sc
+                z = self.body[i + 1].res_layer[0](x) if i + 1 < n_units else None
+            else:
+                y = torch.empty_like(r)
+                zz = torch.empty_like(r) if i + 1 < n_units else None
+                a, b = affine[i + 1] if i + 1 < n_units else (None, None)
+                with torch.cuda.device(r.device):
+                    rc = lib.vsp_se_tail_nhwc_bf16(_lib.ptr(r), _lib.ptr(gate), _lib.ptr(sc), _lib.ptr(y), _lib.ptr(zz),
+                                                   _lib.ptr(a), _lib.ptr(b), n, h, w, c, sc.stride(0), sc.stride(2),
+                                                   sc.stride(3), _lib.stream_ptr())
+                _lib.check(rc, "se_tail_nhwc_bf16")
+                x, z = y, zz
             if i in (6, 20, 23):
                 taps[i] = x
+        return taps
+
+    def forward(self, x):
+        x = self.input_layer(x)
+        if (getattr(self, "_folded", False) and x.is_cuda and x.dtype == torch.bfloat16 and not self.training
+                and x.is_contiguous(memory_format=torch.channels_last) and os.environ.get("VSP_NO_SE_TAIL") is None):
+            taps = self._body_fused(x)
+        else:
+            taps = {}
+            for i, unit in enumerate(self.body):
+                x = unit(x)
+                if i in (6, 20, 23):
+                    taps[i] = x
         c1, c2, c3 = taps[6], taps[20], taps[23]
         w = self.styles[0](c3)[:, None, :].repeat(1, self.style_count, 1)
         feats = c3
