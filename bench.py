@@ -184,7 +184,24 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly ONE line (the JSON): whatever NCCL prints while the communicator comes up (its version
+        # banner at NCCL_DEBUG >= VERSION) is sent to stderr — file-descriptor level, C stdio flushed before stdout returns
+        import ctypes
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            try:
+                ctypes.CDLL(None).fflush(None)
+            except Exception:
+                pass
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.load()
 
     per_rank = TOTAL_IMAGES // world
