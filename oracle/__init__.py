@@ -6,6 +6,9 @@ upfirdn2d, fused bias+leaky-ReLU and the modulated convolution.  Only ``tests/``
 legs may import this package; the product path (``vspbfr_b200``) never does and
 fails loudly when its CUDA library is missing.
 
+``oracle/c/vsp_oracle.c`` restates the two memory-bound operators in plain C (built by
+``oracle/build_c.py`` with gcc; ``build_c.upfirdn2d_c`` / ``build_c.bias_act_c``).
+
 Parity pinning: the reference ships NO tests or golden vectors, so
 the oracle is pinned against outputs of the reference's own Python/CPU code run in
 the build container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``);

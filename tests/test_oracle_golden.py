@@ -123,3 +123,43 @@ def test_network_oracle_matches_reference():
         np.testing.assert_allclose(f.numpy(), net_g[f"decoder_feat{i}"], rtol=1e-3, atol=2e-4)
     restored = oracle.restoration_ref(net.state_dict(), low, feats, codes, z, size, 2)
     np.testing.assert_allclose(restored.numpy(), net_g["restored"], rtol=1e-3, atol=5e-4)
+
+
+# ---- plain-C restatement (oracle/c/vsp_oracle.c, built by oracle/build_c.py) against the same reference goldens --------
+@pytest.mark.parametrize("name", [str(n) for n in UFD["names"]])
+def test_c_oracle_upfirdn2d_matches_reference(name):
+    from oracle import build_c as bc
+    up, down, pad = _ufd_args(name)
+    x, k, y, go, gx = (UFD[f"{name}.{s}"] for s in ("x", "k", "y", "go", "gx"))
+    got = bc.upfirdn2d_c(x, k, up, down, pad)
+    assert got.shape == y.shape
+    np.testing.assert_allclose(got, y, rtol=1e-5, atol=1e-6)
+    if x.size:      # and the backward form (op/upfirdn2d.py:229-240) through the same C routine
+        gpad = oracle.upfirdn2d_grad_pads(x.shape[2:], go.shape[2:], k.shape, up, down, pad)
+        np.testing.assert_allclose(bc.upfirdn2d_c(go, k[::-1, ::-1].copy(), down, up, gpad), gx, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", [str(n) for n in ACT["names"]])
+def test_c_oracle_bias_act_matches_reference(name):
+    from oracle import build_c as bc
+    x, y, go, gx, ggo, vx = (ACT[f"{name}.{s}"] for s in ("x", "y", "go", "gx", "ggo", "vx"))
+    b = ACT[f"{name}.b"] if f"{name}.b" in ACT.files else None
+    np.testing.assert_allclose(bc.bias_act_c(x, b), y, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(bc.bias_act_c(go, None, y, 3, 1), gx, rtol=1e-6, atol=1e-7)
+    vb = ACT[f"{name}.vb"] if b is not None else None
+    np.testing.assert_allclose(bc.bias_act_c(vx, vb, y, 3, 1), ggo, rtol=1e-5, atol=1e-6)
+
+
+def test_c_oracle_agrees_with_numpy_oracle_on_random_modes():
+    from oracle import build_c as bc
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        x = rng.standard_normal((2, 2, int(rng.integers(1, 12)), int(rng.integers(1, 12)))).astype(np.float32)
+        k = rng.standard_normal((int(rng.integers(1, 5)), int(rng.integers(1, 5)))).astype(np.float32)
+        up = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        down = (int(rng.integers(1, 4)), int(rng.integers(1, 4)))
+        pad = tuple(int(v) for v in rng.integers(-2, 5, size=4))
+        want = oracle.upfirdn2d_ref(x, k, up, down, pad)
+        got = bc.upfirdn2d_c(x, k, up, down, pad)
+        assert got.shape == want.shape, (x.shape, k.shape, up, down, pad)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
