@@ -291,7 +291,7 @@ def test_full_size_hot_path_matches_cpu_oracle():
     check_bf16(got_img.cpu(), want_img, "decoder image @512 (pooled)")
     # The restorer output goes through ~45 bf16 layers of a RANDOM-INIT network (dynamic range ~700, i.e. the network
     # amplifies): its max-abs error is a chaotic function of rounding order — measured 1.05e-2 .. 2.0e-2 of the range
-    # (PSNR 50.2 .. 53.5 dB) across permutations of the kernel paths (tools/dbg_fullsize.py with VSP_NO_* flags), with
+    # (PSNR 50.2 .. 53.5 dB) across permutations of the kernel paths (tests/dbg_fullsize.py with VSP_NO_* flags), with
     # no spatial structure.  PSNR is the robust criterion here; max-abs is bounded at 3e-2 of the range.
     got, want = got.cpu(), want
     peak = float(want.max() - want.min())
