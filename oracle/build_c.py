@@ -19,9 +19,13 @@ def build(force: bool = False) -> str:
         return LIB
     cc = shutil.which("gcc") or shutil.which("cc")
     if cc is None:
+        if os.path.exists(LIB):         # a prebuilt checker travelled with the tree: use it rather than fail the build step
+            return LIB
         raise RuntimeError("oracle.build_c: no C compiler (gcc/cc) on PATH")
     os.makedirs(OUT_DIR, exist_ok=True)
-    subprocess.run([cc, "-O2", "-std=c99", "-shared", "-fPIC", "-o", LIB, SRC], check=True)
+    tmp = LIB + f".{os.getpid()}.tmp"   # atomic replace: several ranks / test workers may build at once
+    subprocess.run([cc, "-O2", "-std=c99", "-shared", "-fPIC", "-o", tmp, SRC], check=True)
+    os.replace(tmp, LIB)
     return LIB
 
 
