@@ -83,8 +83,11 @@ int vsp_upfirdn2d_nhwc_bf16(const void *x, const float *filt, void *y,
 
 /*
  * Same blur for a SEPARABLE filter filt[j][i] = fy[j] * fx[i] (the model's outer([1,3,3,1]) kernels,
- * models/RestoreNet.py:32-40): up = down = 1, filter up to 4x4, 1-D taps passed from HOST memory.  One horizontal
- * pass per input row shared by two output columns, then a vertical scatter: ~1.5x fewer instructions than the 2-D form.
+ * models/RestoreNet.py:32-40): up = down = 1, filter up to 4x4, 1-D taps passed from HOST memory.  For c % 64 == 0 and
+ * in_w >= 35 this is the TMA strip kernel (32 output columns x 64 channels per CTA walking down the image, input rows as
+ * TMA boxes in a 4-stage ring with out-of-bounds zero fill as the padding, rolling 4-row window, packed fp32 FMA:
+ * 5.3-6.0 TB/s); other shapes take the register-tiled form (one horizontal pass per input row shared by two output
+ * columns, then a vertical scatter).
  */
 int vsp_blur_sep_nhwc_bf16(const void *x, const float *fy_host, const float *fx_host, void *y,
                            int64_t n, int64_t in_h, int64_t in_w, int64_t c, int kh, int kw,
