@@ -133,6 +133,25 @@ int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
                               int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
 
 /*
+ * The two conversions with the reductions of the modulated convolution's backward pass fused in (they ride on data the
+ * conversion already holds; hw % 4 == 0 and 16-byte aligned tensors when `other` or, for the second, `scale_nc` is given).
+ * The modulated convolution runs as y = d[b,o] * conv(x * s[b,i], wscale * W) (models/RestoreNet.py:481-508, the
+ * reference's un-fused branch, algebraically its fused one :510-553), so no per-sample weights or weight gradients exist:
+ *
+ *   vsp_nchw_f32_to_nhwc_bf16_dot:  y[n,p,c] = bf16(x[n,c,p] * scale_nc[n,c]);  dot_nc[n,c] = sum_p x[n,c,p] * other[n,c,p]
+ *       forward:  x = activation, scale_nc = s           (style modulation inside the layout conversion)
+ *       backward: x = dy, scale_nc = d, other = y        (dz = d * dy; dot = sum_p dy * y gives dL/dd = dot / d)
+ *   vsp_nhwc_bf16_to_nchw_f32_dot:  y[n,c,p] = x[n,p,c] * scale_nc[n,c];        dot_nc[n,c] = sum_p x[n,p,c] * other[n,c,p]
+ *       backward: x = d(x*s) from the adjoint convolution, scale_nc = s, other = the forward activation
+ *                 (dx = s * dxs; dot = ds, the style gradient, with no per-sample weight gradient)
+ * `scale_nc`, and `other` together with `dot_nc`, may be NULL.  dot_nc [n, c] is overwritten (zeroed on `stream` first).
+ */
+int vsp_nchw_f32_to_nhwc_bf16_dot(const float *x, const float *scale_nc, const float *other, void *y, float *dot_nc,
+                                  int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
+int vsp_nhwc_bf16_to_nchw_f32_dot(const void *x, const float *scale_nc, const float *other, float *y, float *dot_nc,
+                                  int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
+
+/*
  * Weight gradient of a 1x1, stride-1, unpadded convolution with 1..8 input channels (NCHW fp32):
  *   gw[o, i] = sum_{b, p} dy[b, o, p] * x[b, i, p]        dy [batch, cout, hw], x [batch, cin, hw], hw % 4 == 0
  * Replaces aten::cudnn_convolution_backward_weight (op/conv2d_gradfix.py:180-199) for the RGB-side layers
@@ -347,19 +366,6 @@ int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw,
                           int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
                           int64_t cin, int64_t cout, int64_t out_h, int64_t out_w,
                           int kh, int kw, int stride, int pad, int dil, void *stream);
-
-/*
- * Style / shared-weight gradients of the modulated convolution from the
- * per-sample raw weight gradient G = gw[b,t,o,i] (tap-major, as written by
- * vsp_conv2d_wgrad_bf16; of the un-demodulated
- * product z, i.e. computed from dz = demod * dy):
- *   m = wscale*W*s ; dm = G - demod^2 * (sum_{i,t} m*G) * m      (demod != NULL)
- *   dW[o,i,t] = wscale * sum_b s[b,i] * dm ;  ds[b,i] = wscale * sum_{o,t} W * dm
- */
-int vsp_modconv_weight_style_grad(const float *gw, const float *w, const float *s,
-                                  const float *demod, float *dw, float *ds,
-                                  int64_t batch, int64_t cout, int64_t cin, int taps,
-                                  float wscale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -26,3 +26,6 @@ __all__ = [
 from .network_ref import generator_ref, restoration_ref, restore_faces_ref  # noqa: E402
 
 __all__ += ["generator_ref", "restoration_ref", "restore_faces_ref"]
+from .discriminator_ref import discriminator_ref, r1_step_ref  # noqa: E402
+
+__all__ += ["discriminator_ref", "r1_step_ref"]

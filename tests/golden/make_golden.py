@@ -302,8 +302,98 @@ def gen_networks():
     print("manifest written")
 
 
+def gen_gradfix():
+    """conv2d_gradfix closed set (op/conv2d_gradfix.py:134-223) and its consumers: plain / strided / dilated / transposed /
+    grouped convolutions with first- and second-order gradients, the Discriminator forward (minibatch-stddev,
+    models/RestoreNet.py:1244-1265) and the R1 penalty step (restoration_train.py:66-73, :200-216)."""
+    from op import conv2d_gradfix as gf
+
+    out, names = {}, []
+    g = torch.Generator().manual_seed(77)
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=g)
+
+    cases = [
+        # name, transposed, x shape, w shape, bias, kwargs
+        ("c3_s1_p1", False, (2, 16, 12, 12), (24, 16, 3, 3), True, dict(padding=1)),
+        ("c3_s2_p0_odd", False, (2, 16, 13, 13), (24, 16, 3, 3), False, dict(stride=2)),
+        ("c3_s2_p0_even", False, (2, 16, 12, 12), (24, 16, 3, 3), False, dict(stride=2)),
+        ("c1_s2_skip", False, (2, 16, 11, 11), (8, 16, 1, 1), False, dict(stride=2)),
+        ("c1_cin3_stem", False, (2, 3, 16, 16), (16, 3, 1, 1), True, dict()),
+        ("c3_dil2", False, (2, 16, 16, 16), (8, 16, 3, 3), False, dict(padding=2, dilation=2)),
+        ("c3_dil4", False, (1, 8, 16, 16), (8, 8, 3, 3), False, dict(padding=4, dilation=4)),
+        ("c3_cin21_head", False, (4, 21, 4, 4), (16, 21, 3, 3), False, dict(padding=1)),
+        ("c3_pad_asym", False, (1, 8, 9, 10), (8, 8, 3, 3), False, dict(padding=(0, 1))),
+        ("t3_s2_p0", True, (2, 16, 6, 6), (16, 8, 3, 3), False, dict(stride=2)),
+        ("t3_s2_p1_op1", True, (2, 8, 5, 5), (8, 8, 3, 3), True, dict(stride=2, padding=1, output_padding=1)),
+        ("t3_s1_p1", True, (2, 8, 7, 7), (8, 16, 3, 3), False, dict(padding=1)),
+        ("t1_s2", True, (1, 8, 5, 5), (8, 8, 1, 1), False, dict(stride=2)),
+        ("g3_modconv_form", False, (1, 3 * 8, 10, 10), (3 * 12, 8, 3, 3), False, dict(padding=1, groups=3)),
+        ("g3_transposed", True, (1, 3 * 8, 5, 5), (3 * 8, 12, 3, 3), False, dict(stride=2, groups=3)),
+        ("g2_batch2", False, (2, 2 * 8, 6, 6), (2 * 8, 8, 3, 3), False, dict(padding=1, groups=2)),
+    ]
+    for name, tr, xs, ws, has_b, kw in cases:
+        x = rnd(*xs).requires_grad_(True)
+        w = (rnd(*ws) / (ws[1] * ws[2] * ws[3]) ** 0.5).requires_grad_(True)
+        b = rnd(ws[1] * kw.get("groups", 1) if tr else ws[0]).requires_grad_(True) if has_b else None
+        fn = gf.conv_transpose2d if tr else gf.conv2d
+        y = fn(x, w, b, **kw)
+        go = rnd(*y.shape).requires_grad_(True)
+        ins = [x, w] + ([b] if has_b else [])
+        grads = torch.autograd.grad(y, ins, go, create_graph=True)
+        gx, gw = grads[0], grads[1]
+        # second order: penalties on the input gradient (R1 form) and on the weight gradient
+        pen_x = gx.pow(2).sum()
+        ggw_from_x, ggo_from_x = torch.autograd.grad(pen_x, [w, go], retain_graph=True)
+        pen_w = gw.pow(2).sum()
+        ggx_from_w, ggo_from_w = torch.autograd.grad(pen_w, [x, go], retain_graph=True)
+        out.update({f"{name}.x": np_(x), f"{name}.w": np_(w), f"{name}.go": np_(go), f"{name}.y": np_(y),
+                    f"{name}.gx": np_(gx), f"{name}.gw": np_(gw), f"{name}.ggw_from_x": np_(ggw_from_x),
+                    f"{name}.ggo_from_x": np_(ggo_from_x), f"{name}.ggx_from_w": np_(ggx_from_w),
+                    f"{name}.ggo_from_w": np_(ggo_from_w), f"{name}.transposed": np.array(tr),
+                    f"{name}.kw": np.array(repr(kw))})
+        if has_b:
+            out[f"{name}.b"], out[f"{name}.gb"] = np_(b), np_(grads[2])
+        names.append(name)
+    out["names"] = np.array(names)
+
+    # Discriminator: forward at batch 8 (two minibatch-stddev groups) and the R1 step at batch 4
+    size = 16
+    torch.manual_seed(4242)
+    disc = R.Discriminator(size)
+    with torch.no_grad():
+        for n_, p in disc.named_parameters():
+            if n_.endswith("bias"):
+                p.normal_(0, 0.2)
+    img8 = torch.rand(8, 3, size, size, generator=g) * 2 - 1
+    with torch.no_grad():
+        out["disc.pred8"] = np_(disc(img8))
+    out["disc.img8"] = np_(img8)
+    real = (torch.rand(4, 3, size, size, generator=g) * 2 - 1).requires_grad_(True)
+    pred = disc(real)
+    with gf.no_weight_gradients():
+        (grad_real,) = torch.autograd.grad(outputs=pred.sum(), inputs=real, create_graph=True)
+    r1 = grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+    disc.zero_grad()
+    (10.0 / 2 * r1 * 16 + 0 * pred[0]).backward()
+    out["disc.size"] = np.array(size)
+    out["disc.real"], out["disc.pred"], out["disc.grad_real"], out["disc.r1"] = np_(real), np_(pred), np_(grad_real), np_(r1)
+    keys = [k for k, _ in disc.named_parameters()]
+    out["disc.param_keys"] = np.array(keys)
+    out["disc.sd_keys"] = np.array(list(disc.state_dict().keys()))
+    out["disc.sd_sums"] = np.array([float(v.double().sum()) for v in disc.state_dict().values()])
+    out["disc.grad_absmax"] = np.array([float(p.grad.abs().max()) for _, p in disc.named_parameters()])
+    out["disc.grad_sum"] = np.array([float(p.grad.double().sum()) for _, p in disc.named_parameters()])
+    for k_, p in disc.named_parameters():          # full gradients of the small / structurally distinct parameters
+        if p.numel() <= 40000 or k_ in ("encoder_convs.1.skip.0.weight",):
+            out[f"disc.grad.{k_}"] = np_(p.grad)
+    np.savez_compressed(os.path.join(OUT, "gradfix.npz"), **out)
+    print("gradfix:", len(names), "conv cases; discriminator pred", np_(pred).ravel(), "r1", float(r1))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["upfirdn2d", "fused_act", "modconv", "layers", "networks"]
+    which = sys.argv[1:] or ["upfirdn2d", "fused_act", "modconv", "layers", "networks", "gradfix"]
     for w in which:
         globals()[f"gen_{w}"]()

@@ -1,0 +1,148 @@
+"""GPU parity of the conv2d_gradfix closed set and of its consumers (Discriminator, R1) against outputs of the reference
+itself (tests/golden/gradfix.npz, written by tests/golden/make_golden.py::gen_gradfix from /root/reference).
+
+Every member of the set — forward, transposed, weight gradient, and their second-order compositions
+(op/conv2d_gradfix.py:134-223) — runs on the tcgen05 kernels; tolerance is north_star's bf16 bound: max-abs <= 1e-2 of the
+reference's dynamic range and PSNR > 45 dB for first-order results, 3e-2 of the peak for second-order ones (two chained
+bf16 convolutions)."""
+import ast
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from vspbfr_b200.op import conv2d_gradfix as gf
+from vspbfr_b200.restorenet import Discriminator
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+G = load_golden("gradfix")
+
+
+def psnr(got, want):
+    peak = float(want.max() - want.min())
+    mse = float(((got - want) ** 2).mean())
+    return 10 * math.log10(peak * peak / max(mse, 1e-30))
+
+
+def check(got, want_np, what, tol=1e-2, need_psnr=45.0):
+    want = torch.from_numpy(np.asarray(want_np)).to(got.device)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    peak = max(float(want.max() - want.min()), 1e-12)
+    err = float((got - want).abs().max())
+    assert err <= tol * peak, f"{what}: max-abs {err} > {tol} * {peak}"
+    if need_psnr:
+        assert psnr(got, want) > need_psnr, f"{what}: psnr {psnr(got, want)}"
+
+
+def _case(name):
+    t = lambda k: torch.from_numpy(G[f"{name}.{k}"]).to(DEV)
+    x, w, go = t("x").requires_grad_(True), t("w").requires_grad_(True), t("go").requires_grad_(True)
+    b = t("b").requires_grad_(True) if f"{name}.b" in G.files else None
+    kw = ast.literal_eval(str(G[f"{name}.kw"]))
+    fn = gf.conv_transpose2d if bool(G[f"{name}.transposed"]) else gf.conv2d
+    return x, w, b, go, fn, kw
+
+
+@pytest.mark.parametrize("name", [str(n) for n in G["names"]])
+def test_closed_set_first_and_second_order(name):
+    x, w, b, go, fn, kw = _case(name)
+    y = fn(x, w, b, **kw)
+    check(y, G[f"{name}.y"], "y")
+    ins = [x, w] + ([b] if b is not None else [])
+    grads = torch.autograd.grad(y, ins, go, create_graph=True)
+    check(grads[0], G[f"{name}.gx"], "gx")
+    check(grads[1], G[f"{name}.gw"], "gw")
+    if b is not None:
+        check(grads[2], G[f"{name}.gb"], "gb", tol=1e-4, need_psnr=0)
+    # second order: d(|gx|^2)/d(w, go) goes through ConvOp's backward twice; d(|gw|^2)/d(x, go) through WeightGradOp.backward
+    ggw, ggo = torch.autograd.grad(grads[0].pow(2).sum(), [w, go], retain_graph=True)
+    check(ggw, G[f"{name}.ggw_from_x"], "ggw_from_x", tol=3e-2, need_psnr=40.0)
+    check(ggo, G[f"{name}.ggo_from_x"], "ggo_from_x", tol=3e-2, need_psnr=40.0)
+    ggx, ggo2 = torch.autograd.grad(grads[1].pow(2).sum(), [x, go], retain_graph=True)
+    check(ggx, G[f"{name}.ggx_from_w"], "ggx_from_w", tol=3e-2, need_psnr=40.0)
+    check(ggo2, G[f"{name}.ggo_from_w"], "ggo_from_w", tol=3e-2, need_psnr=40.0)
+
+
+def test_no_weight_gradients_skips_the_weight_gradient():
+    """restoration_train.py:66-73: inside the block only d/d(input) is produced; outside it both are."""
+    x, w, b, go, fn, kw = _case("c3_s1_p1")
+    y = fn(x, w, b, **kw)
+    with gf.no_weight_gradients():
+        assert gf.weight_gradients_disabled
+        gx, gw = torch.autograd.grad(y, [x, w], go, retain_graph=True, allow_unused=True)
+    assert gw is None and gx is not None
+    assert not gf.weight_gradients_disabled
+    gx2, gw2 = torch.autograd.grad(y, [x, w], go)
+    assert gw2 is not None
+    torch.testing.assert_close(gx, gx2, rtol=0, atol=0)
+
+
+def test_disabled_flag_uses_plain_torch_ops():
+    """``enabled = False`` is the reference's switch to plain ``F.conv2d`` (op/conv2d_gradfix.py:8, :34-42)."""
+    x, w, b, go, fn, kw = _case("c3_s1_p1")
+    gf.enabled = False
+    try:
+        y = fn(x, w, b, **kw)
+    finally:
+        gf.enabled = True
+    torch.testing.assert_close(y, torch.from_numpy(G["c3_s1_p1.y"]).to(DEV), rtol=1e-4, atol=1e-4)
+
+
+def test_unsupported_configuration_raises():
+    x = torch.randn(1, 8, 16, 16, device=DEV)
+    with pytest.raises(RuntimeError):
+        gf.conv2d(x, torch.randn(8, 8, 5, 5, device=DEV))              # 25 taps
+    with pytest.raises(RuntimeError):
+        gf.conv2d(x, torch.randn(8, 8, 3, 3, device=DEV), stride=3)
+
+
+def _golden_discriminator():
+    torch.manual_seed(4242)
+    d = Discriminator(int(G["disc.size"]))
+    with torch.no_grad():
+        for n_, p in d.named_parameters():
+            if n_.endswith("bias"):
+                p.normal_(0, 0.2)
+    sd = d.state_dict()
+    assert list(sd.keys()) == [str(k) for k in G["disc.sd_keys"]]
+    np.testing.assert_allclose([float(v.double().sum()) for v in sd.values()], G["disc.sd_sums"], rtol=1e-6, atol=1e-6)
+    return d.to(DEV)
+
+
+def test_discriminator_forward_matches_reference():
+    """Discriminator.forward incl. minibatch-stddev with two groups (models/RestoreNet.py:1244-1265) at batch 8."""
+    d = _golden_discriminator()
+    with torch.no_grad():
+        pred = d(torch.from_numpy(G["disc.img8"]).to(DEV))
+    want = torch.from_numpy(G["disc.pred8"]).to(DEV)
+    assert float((pred - want).abs().max()) <= 1e-2 * float(want.abs().max())
+
+
+def test_r1_step_matches_reference():
+    """The R1 regularisation step (restoration_train.py:66-73, :200-216): d(score)/d(image) with create_graph inside
+    no_weight_gradients(), then the penalty's backward into every Discriminator parameter — all on the closed set."""
+    d = _golden_discriminator()
+    real = torch.from_numpy(G["disc.real"]).to(DEV).requires_grad_(True)
+    pred = d(real)
+    with gf.no_weight_gradients():
+        (grad_real,) = torch.autograd.grad(outputs=pred.sum(), inputs=real, create_graph=True)
+    r1 = grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+    d.zero_grad()
+    (10.0 / 2 * r1 * 16 + 0 * pred[0]).backward()
+    want_pred = torch.from_numpy(G["disc.pred"]).to(DEV)
+    assert float((pred - want_pred).abs().max()) <= 1e-2 * float(want_pred.abs().max())
+    check(grad_real, G["disc.grad_real"], "grad_real", tol=2e-2, need_psnr=40.0)
+    assert abs(float(r1) - float(G["disc.r1"])) <= 3e-2 * float(G["disc.r1"])
+    keys = [str(k) for k in G["disc.param_keys"]]
+    params = dict(d.named_parameters())
+    for k, absmax in zip(keys, G["disc.grad_absmax"]):
+        g = params[k].grad
+        assert g is not None, k
+        assert abs(float(g.abs().max()) - absmax) <= 0.1 * absmax + 1e-9, (k, float(g.abs().max()), absmax)
+        if f"disc.grad.{k}" in G.files:
+            want = torch.from_numpy(G[f"disc.grad.{k}"]).to(DEV)
+            err = float((g - want).abs().max())
+            assert err <= 5e-2 * float(want.abs().max()) + 1e-9, (k, err, float(want.abs().max()))

@@ -163,3 +163,50 @@ def test_c_oracle_agrees_with_numpy_oracle_on_random_modes():
         got = bc.upfirdn2d_c(x, k, up, down, pad)
         assert got.shape == want.shape, (x.shape, k.shape, up, down, pad)
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_conv_oracle_matches_reference_closed_set():
+    """conv2d_ref (= F.conv2d, what conv2d_gradfix reduces to on the CPU) and its autograd against the reference's own
+    outputs and first-/second-order gradients (tests/golden/gradfix.npz)."""
+    import ast
+
+    import torch.nn.functional as F
+
+    g = load_golden("gradfix")
+    for name in [str(n) for n in g["names"]]:
+        t = lambda k: torch.from_numpy(g[f"{name}.{k}"])
+        x, w, go = t("x").requires_grad_(True), t("w").requires_grad_(True), t("go").requires_grad_(True)
+        b = t("b") if f"{name}.b" in g.files else None
+        kw = ast.literal_eval(str(g[f"{name}.kw"]))
+        y = F.conv_transpose2d(x, w, b, **kw) if bool(g[f"{name}.transposed"]) else oracle.conv2d_ref(x, w, b, **kw)
+        np.testing.assert_allclose(y.detach().numpy(), g[f"{name}.y"], rtol=1e-5, atol=1e-5)
+        gx, gw = torch.autograd.grad(y, [x, w], go, create_graph=True)
+        np.testing.assert_allclose(gx.detach().numpy(), g[f"{name}.gx"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(gw.detach().numpy(), g[f"{name}.gw"], rtol=1e-4, atol=1e-4)
+        (ggw,) = torch.autograd.grad(gx.pow(2).sum(), [w], retain_graph=True)
+        np.testing.assert_allclose(ggw.numpy(), g[f"{name}.ggw_from_x"], rtol=1e-4, atol=1e-4)
+
+
+def test_discriminator_oracle_matches_reference():
+    """discriminator_ref / r1_step_ref against the reference's Discriminator forward and R1 step."""
+    from vspbfr_b200.restorenet import Discriminator
+
+    g = load_golden("gradfix")
+    torch.manual_seed(4242)
+    d = Discriminator(int(g["disc.size"]))
+    with torch.no_grad():
+        for n_, p in d.named_parameters():
+            if n_.endswith("bias"):
+                p.normal_(0, 0.2)
+    sd = d.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["disc.sd_keys"]]
+    np.testing.assert_allclose([float(v.double().sum()) for v in sd.values()], g["disc.sd_sums"], rtol=1e-6, atol=1e-6)
+    with torch.no_grad():
+        pred8 = oracle.discriminator_ref(sd, torch.from_numpy(g["disc.img8"]))
+    np.testing.assert_allclose(pred8.numpy(), g["disc.pred8"], rtol=1e-5, atol=1e-5)
+    pred, grad_real, r1, grads = oracle.r1_step_ref(sd, torch.from_numpy(g["disc.real"]))
+    np.testing.assert_allclose(pred.numpy(), g["disc.pred"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(grad_real.numpy(), g["disc.grad_real"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(float(r1), float(g["disc.r1"]), rtol=1e-5)
+    for k, absmax in zip([str(k) for k in g["disc.param_keys"]], g["disc.grad_absmax"]):
+        np.testing.assert_allclose(float(grads[k].abs().max()), absmax, rtol=1e-3, atol=1e-9)

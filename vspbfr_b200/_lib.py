@@ -10,6 +10,7 @@ type through TORCH_CHECK, op/upfirdn2d.cpp:9-15).
 from __future__ import annotations
 
 import ctypes
+import fcntl
 import os
 import shutil
 import subprocess
@@ -59,7 +60,14 @@ def _stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every .cu under csrc/ into libvsp_b200.so for sm_100a (cross-compiles without a GPU)."""
-    with _lock:
+    if not force and not _stale():
+        return LIB_PATH
+    build_dir = os.path.join(_HERE, "build")
+    os.makedirs(build_dir, exist_ok=True)
+    # one builder at a time across threads AND processes (every torchrun rank calls load() on a stale checkout): the
+    # losers of the race wait on the file lock, then find the library fresh and return
+    with _lock, open(os.path.join(build_dir, ".lock"), "w") as lock_file:
+        fcntl.flock(lock_file, fcntl.LOCK_EX)
         if not force and not _stale():
             return LIB_PATH
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -67,8 +75,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("vspbfr_b200: nvcc not found and libvsp_b200.so is missing or stale")
         objs = []
         procs = []
-        build_dir = os.path.join(_HERE, "build")
-        os.makedirs(build_dir, exist_ok=True)
         compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
         for src in _sources():
             obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
@@ -86,7 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             log.append(out)
             if p.returncode != 0:
                 raise RuntimeError(f"vspbfr_b200: nvcc failed on {src}:\n{out}")
-        tmp = LIB_PATH + ".tmp"
+        tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
         cmd = [nvcc, "--shared", "-o", tmp, *objs, "-lcudart_static", "-ldl", "-lpthread", "-lrt"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
@@ -188,8 +194,8 @@ SIGNATURES = {
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "vsp_modconv_weight_style_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                              c_int64, c_int64, c_int64, c_int, c_float, c_void_p]),
+    "vsp_nchw_f32_to_nhwc_bf16_dot": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
+    "vsp_nhwc_bf16_to_nchw_f32_dot": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
 }
 
 

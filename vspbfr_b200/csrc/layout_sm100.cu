@@ -95,6 +95,129 @@ nhwc_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, float *__restrict__ y, 
   }
 }
 
+// ---- vectorised forms of the two conversions above (hw % 4 == 0, 16-byte aligned tensors): a block moves a tile of
+// 64 channels x 128 pixels.  The NCHW side is touched with 128-bit accesses (a warp covers 512 contiguous bytes of one
+// plane, 8 loads per thread in flight), the NHWC side with 32 contiguous bytes per lane (two 8-channel vectors = one full
+// sector); the shared tile [channel][pixel] has a pitch of 132 floats, which makes the 128-bit accesses of the NCHW side and
+// the pixel-per-lane accesses of the NHWC side both conflict free.  Optional fused reductions for the backward passes of
+// the modulated convolution (they ride on data the conversion already has in registers):
+//   DOT: dot_nc[n,c] += sum_p x[n,c,p] * other[n,c,p]     (`other` in the NCHW fp32 layout; x UNSCALED)
+constexpr int kTileC = 64, kTileP = 128, kPitch = 132;
+
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_v4_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc, const float *__restrict__ other,
+                       __nv_bfloat16 *__restrict__ y, float *__restrict__ dot_nc, long long c, long long hw,
+                       long long c_pad) {
+  __shared__ __align__(16) float tile[kTileC * kPitch];
+  const long long n = blockIdx.z;
+  const long long c0 = (long long)blockIdx.y * kTileC, p0 = (long long)blockIdx.x * kTileP;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  {
+    const long long pp = p0 + 4 * lane;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long cc = c0 + wrp + 8 * i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cc < c && pp < hw) v[i] = ld_stream_f4(reinterpret_cast<const float4 *>(x + (n * c + cc) * hw + pp));
+    }
+    if (DOT) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long cc = c0 + wrp + 8 * i;
+        float acc = 0.f;
+        if (cc < c && pp < hw) {
+          const float4 o = ld_stream_f4(reinterpret_cast<const float4 *>(other + (n * c + cc) * hw + pp));
+          acc = fmaf(v[i].x, o.x, fmaf(v[i].y, o.y, fmaf(v[i].z, o.z, v[i].w * o.w)));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0 && cc < c) atomicAdd(dot_nc + n * c + cc, acc);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cl = wrp + 8 * i;
+      float4 o = v[i];
+      if (scale_nc != nullptr && c0 + cl < c) {
+        const float sc = __ldg(scale_nc + n * c + c0 + cl);
+        o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+      }
+      *reinterpret_cast<float4 *>(&tile[cl * kPitch + 4 * lane]) = o;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int pl = threadIdx.x & (kTileP - 1), q = (threadIdx.x >> 7) + 2 * i;   // pixel, 16-channel group
+    const long long pp = p0 + pl, cc = c0 + 16 * q;
+    if (pp >= hw || cc >= c_pad) continue;
+    uint4 o[2];
+    __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      oh[j] = __floats2bfloat162_rn(tile[(16 * q + 2 * j) * kPitch + pl], tile[(16 * q + 2 * j + 1) * kPitch + pl]);
+    uint4 *dst = reinterpret_cast<uint4 *>(y + (n * hw + pp) * c_pad + cc);
+    dst[0] = o[0];
+    if (cc + 8 < c_pad) dst[1] = o[1];
+  }
+}
+
+//   y[n,c,p] = x[n,p,c] * scale_nc[n,c]   and, when DOT,   dot_nc[n,c] += sum_p x[n,p,c] * other[n,c,p]   (x UNSCALED)
+template <bool DOT>
+__global__ void __launch_bounds__(kThreads)
+nhwc_to_nchw_v4_kernel(const __nv_bfloat16 *__restrict__ x, const float *__restrict__ scale_nc,
+                       const float *__restrict__ other, float *__restrict__ y, float *__restrict__ dot_nc, long long c,
+                       long long hw, long long c_pad) {
+  __shared__ __align__(16) float tile[kTileC * kPitch];
+  const long long n = blockIdx.z;
+  const long long c0 = (long long)blockIdx.y * kTileC, p0 = (long long)blockIdx.x * kTileP;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int pl = threadIdx.x & (kTileP - 1), q = (threadIdx.x >> 7) + 2 * i;
+    const long long pp = p0 + pl, cc = c0 + 16 * q;
+    uint4 v[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (pp < hw && cc < c_pad) {
+      const uint4 *src = reinterpret_cast<const uint4 *>(x + (n * hw + pp) * c_pad + cc);
+      v[0] = __ldg(src);
+      if (cc + 8 < c_pad) v[1] = __ldg(src + 1);
+    }
+    const __nv_bfloat162 *vh = reinterpret_cast<const __nv_bfloat162 *>(v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = __bfloat1622float2(vh[j]);
+      tile[(16 * q + 2 * j) * kPitch + pl] = f.x;
+      tile[(16 * q + 2 * j + 1) * kPitch + pl] = f.y;
+    }
+  }
+  __syncthreads();
+  const long long pp = p0 + 4 * lane;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int cl = wrp + 8 * i;
+    const long long cc = c0 + cl;
+    if (cc >= c) continue;                                // warp-uniform
+    float acc = 0.f;
+    if (pp < hw) {
+      float4 v = *reinterpret_cast<const float4 *>(&tile[cl * kPitch + 4 * lane]);
+      if (DOT) {
+        const float4 o = ld_stream_f4(reinterpret_cast<const float4 *>(other + (n * c + cc) * hw + pp));
+        acc = fmaf(v.x, o.x, fmaf(v.y, o.y, fmaf(v.z, o.z, v.w * o.w)));
+      }
+      if (scale_nc != nullptr) {
+        const float sc = __ldg(scale_nc + n * c + cc);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      }
+      st_stream_f4(reinterpret_cast<float4 *>(y + (n * c + cc) * hw + pp), v);
+    }
+    if (DOT) {
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(dot_nc + n * c + cc, acc);
+    }
+  }
+}
+
 // ---- NCHW fp32 -> NCHW bf16 with a per-plane scale
 __global__ void __launch_bounds__(kThreads)
 nchw_cast_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc,
@@ -273,111 +396,90 @@ pack_weights_vec_kernel(const float *__restrict__ w, const float *__restrict__ s
   }
 }
 
-// Per-sample raw weight gradients arrive tap-major: G[b][t][o][i] (what wgrad_sm100.cu writes).
-// ---- c[b,o] = demod^2 * sum_{i,t} m*G   (one warp per (b,o))
-__global__ void __launch_bounds__(kThreads)
-demod_corr_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
-                  const float *__restrict__ demod, float *__restrict__ corr, long long batch,
-                  long long cout, long long cin, int taps, float wscale) {
-  const long long warp = (blockIdx.x * (long long)kThreads + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= batch * cout) return;
-  const long long b = warp / cout, o = warp % cout;
-  float acc = 0.f;
-  for (int t = 0; t < taps; ++t) {
-    const float *gr = gw + ((b * taps + t) * cout + o) * cin;
-    for (long long i = lane; i < cin; i += 32) {
-      const float m = wscale * w[(o * cin + i) * taps + t] * __ldg(s + b * cin + i);
-      acc = fmaf(m, gr[i], acc);
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const float d = demod[warp];
-    corr[warp] = d * d * acc;
-  }
-}
-
-// ---- dW[o,i,t] = wscale * sum_b s[b,i] * (G - corr[b,o]*m)     (thread per (t,o,i), G order)
-__global__ void __launch_bounds__(kThreads)
-dweight_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
-               const float *__restrict__ corr, float *__restrict__ dw, long long batch, long long cout,
-               long long cin, int taps, float wscale) {
-  const long long e = blockIdx.x * (long long)kThreads + threadIdx.x;
-  const long long per = cout * cin * taps;
-  if (e >= per) return;
-  const long long i = e % cin, o = (e / cin) % cout;
-  const int t = (int)(e / (cin * cout));
-  const long long we = (o * cin + i) * taps + t;
-  const float wv = w[we];
-  float acc = 0.f;
-  for (long long b = 0; b < batch; ++b) {
-    const float sv = s ? __ldg(s + b * cin + i) : 1.f;
-    float dm = gw[b * per + e];
-    if (corr) dm -= __ldg(corr + b * cout + o) * (wscale * wv * sv);
-    acc = fmaf(sv, dm, acc);
-  }
-  dw[we] = wscale * acc;
-}
-
-// ---- ds[b,i] = wscale * sum_{o,t} W[o,i,t] * (G - corr[b,o]*m); grid (i tiles, o chunks, b)
-__global__ void __launch_bounds__(kThreads)
-dstyle_kernel(const float *__restrict__ gw, const float *__restrict__ w, const float *__restrict__ s,
-              const float *__restrict__ corr, float *__restrict__ ds, long long cout, long long cin,
-              int taps, float wscale, long long o_chunk) {
-  const long long b = blockIdx.z;
-  const long long i = blockIdx.x * (long long)kThreads + threadIdx.x;
-  if (i >= cin) return;
-  const long long o_lo = blockIdx.y * o_chunk;
-  const long long o_hi = min(o_lo + o_chunk, cout);
-  const float sv = __ldg(s + b * cin + i);
-  float acc = 0.f;
-  for (long long o = o_lo; o < o_hi; ++o) {
-    const float c = corr ? __ldg(corr + b * cout + o) : 0.f;
-    const float *wr = w + (o * cin + i) * taps;
-    for (int t = 0; t < taps; ++t) {
-      const float wv = wr[t];
-      const float g = gw[((b * taps + t) * cout + o) * cin + i];
-      acc = fmaf(wv, g - c * (wscale * wv * sv), acc);
-    }
-  }
-  atomicAdd(ds + b * cin + i, wscale * acc);
-}
-
 }  // namespace
 }  // namespace vsp
 
 using namespace vsp;
 
-extern "C" int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y, int64_t n,
-                                         int64_t c, int64_t hw, int64_t c_pad, void *stream_) {
+namespace vsp {
+namespace {
+inline bool vec4_ok(const void *a, const void *b, const void *c, long long hw, long long c_pad) {
+  return hw % 4 == 0 && c_pad % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
+}
+}  // namespace
+}  // namespace vsp
+
+extern "C" int vsp_nchw_f32_to_nhwc_bf16_dot(const float *x, const float *scale_nc, const float *other, void *y,
+                                             float *dot_nc, int64_t n, int64_t c, int64_t hw, int64_t c_pad,
+                                             void *stream_) {
+  using namespace vsp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VSP_REQUIRE(n >= 0 && c >= 0 && hw >= 0 && c_pad >= c && c_pad % 2 == 0, "nchw->nhwc: bad geometry");
+  VSP_REQUIRE((other == nullptr) == (dot_nc == nullptr), "nchw->nhwc: `other` and `dot_nc` go together");
+  if (dot_nc != nullptr && n * c > 0) VSP_CUDA(cudaMemsetAsync(dot_nc, 0, sizeof(float) * n * c, stream));
   if (n == 0 || c_pad == 0 || hw == 0) return 0;
   VSP_REQUIRE(x && y, "nchw->nhwc: null pointer");
   VSP_REQUIRE(n <= 65535 && ceil_div64(c_pad, 64) <= 65535, "nchw->nhwc: batch/channel extent too large");
-  if (c_pad == 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+  if (dot_nc == nullptr && c_pad == 8 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     const long long total = n * hw;
     long long nb = ceil_div64(total, kThreads);
     if (nb > (long long)num_sms() * 32) nb = (long long)num_sms() * 32;
     nchw_to_nhwc8_kernel<<<(unsigned)nb, kThreads, 0, stream>>>(x, scale_nc, static_cast<uint4 *>(y), (int)c, hw, total);
     return check_launch("nchw_to_nhwc8_kernel");
   }
+  if (vec4_ok(x, y, other, hw, c_pad)) {
+    dim3 grid((unsigned)ceil_div64(hw, kTileP), (unsigned)ceil_div64(c_pad, kTileC), (unsigned)n);
+    if (dot_nc != nullptr)
+      nchw_to_nhwc_v4_kernel<true><<<grid, kThreads, 0, stream>>>(x, scale_nc, other, static_cast<__nv_bfloat16 *>(y),
+                                                                   dot_nc, c, hw, c_pad);
+    else
+      nchw_to_nhwc_v4_kernel<false><<<grid, kThreads, 0, stream>>>(x, scale_nc, nullptr, static_cast<__nv_bfloat16 *>(y),
+                                                                    nullptr, c, hw, c_pad);
+    return check_launch("nchw_to_nhwc_v4_kernel");
+  }
+  VSP_REQUIRE(dot_nc == nullptr, "nchw->nhwc: the fused dot needs hw %% 4 == 0 and 16-byte aligned tensors");
   dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
   nchw_to_nhwc_kernel<<<grid, kThreads, 0, stream>>>(x, scale_nc, static_cast<__nv_bfloat16 *>(y), c, hw, c_pad);
   return check_launch("nchw_to_nhwc_kernel");
 }
 
-extern "C" int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y, int64_t n, int64_t c, int64_t hw,
-                                         int64_t c_pad, void *stream_) {
+extern "C" int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y, int64_t n,
+                                         int64_t c, int64_t hw, int64_t c_pad, void *stream_) {
+  return vsp_nchw_f32_to_nhwc_bf16_dot(x, scale_nc, nullptr, y, nullptr, n, c, hw, c_pad, stream_);
+}
+
+extern "C" int vsp_nhwc_bf16_to_nchw_f32_dot(const void *x, const float *scale_nc, const float *other, float *y,
+                                             float *dot_nc, int64_t n, int64_t c, int64_t hw, int64_t c_pad,
+                                             void *stream_) {
+  using namespace vsp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VSP_REQUIRE(n >= 0 && c >= 0 && hw >= 0 && c_pad >= c && c_pad % 2 == 0, "nhwc->nchw: bad geometry");
+  VSP_REQUIRE((other == nullptr) == (dot_nc == nullptr), "nhwc->nchw: `other` and `dot_nc` go together");
+  if (dot_nc != nullptr && n * c > 0) VSP_CUDA(cudaMemsetAsync(dot_nc, 0, sizeof(float) * n * c, stream));
   if (n == 0 || c == 0 || hw == 0) return 0;
   VSP_REQUIRE(x && y, "nhwc->nchw: null pointer");
   VSP_REQUIRE(n <= 65535 && ceil_div64(c_pad, 64) <= 65535, "nhwc->nchw: batch/channel extent too large");
+  if (vec4_ok(x, y, other, hw, c_pad)) {
+    dim3 grid((unsigned)ceil_div64(hw, kTileP), (unsigned)ceil_div64(c_pad, kTileC), (unsigned)n);
+    if (dot_nc != nullptr)
+      nhwc_to_nchw_v4_kernel<true><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), scale_nc, other,
+                                                                   y, dot_nc, c, hw, c_pad);
+    else
+      nhwc_to_nchw_v4_kernel<false><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), scale_nc,
+                                                                    nullptr, y, nullptr, c, hw, c_pad);
+    return check_launch("nhwc_to_nchw_v4_kernel");
+  }
+  VSP_REQUIRE(dot_nc == nullptr && scale_nc == nullptr,
+              "nhwc->nchw: the fused scale / dot needs hw %% 4 == 0 and 16-byte aligned tensors");
   dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
   nhwc_to_nchw_kernel<<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16 *>(x), y, c, hw, c_pad);
   return check_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y, int64_t n, int64_t c, int64_t hw,
+                                         int64_t c_pad, void *stream_) {
+  return vsp_nhwc_bf16_to_nchw_f32_dot(x, nullptr, nullptr, y, nullptr, n, c, hw, c_pad, stream_);
 }
 
 extern "C" int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void *y, int64_t planes,
@@ -452,40 +554,6 @@ extern "C" int vsp_weight_sumsq_f32(const float *w, float *wsq, int64_t cout, in
   VSP_REQUIRE(w && wsq && cout >= 1 && cin >= 1 && taps >= 1, "weight_sumsq: bad arguments");
   weight_sumsq_kernel<<<(unsigned)ceil_div64(cout * cin, kThreads), kThreads, 0, stream>>>(w, wsq, cout * cin, taps);
   return check_launch("weight_sumsq_kernel");
-}
-
-extern "C" int vsp_modconv_weight_style_grad(const float *gw, const float *w, const float *s,
-                                             const float *demod, float *dw, float *ds, int64_t batch,
-                                             int64_t cout, int64_t cin, int taps, float wscale,
-                                             void *stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  VSP_REQUIRE(batch >= 1 && cout >= 1 && cin >= 1 && taps >= 1, "weight_style_grad: bad geometry");
-  VSP_REQUIRE(gw && w && s, "weight_style_grad: null pointer");
-  VSP_REQUIRE(batch <= 65535, "weight_style_grad: batch too large");
-  float *corr = nullptr;
-  if (demod) {
-    // scratch for corr[b,o]: stream-ordered allocation, freed on the same stream
-    VSP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&corr), sizeof(float) * batch * cout, stream));
-    demod_corr_kernel<<<(unsigned)ceil_div64(batch * cout * 32, kThreads), kThreads, 0, stream>>>(
-        gw, w, s, demod, corr, batch, cout, cin, taps, wscale);
-    if (int rc = check_launch("demod_corr_kernel")) return rc;
-  }
-  if (dw) {
-    dweight_kernel<<<(unsigned)ceil_div64(cout * cin * taps, kThreads), kThreads, 0, stream>>>(
-        gw, w, s, corr, dw, batch, cout, cin, taps, wscale);
-    if (int rc = check_launch("dweight_kernel")) return rc;
-  }
-  if (ds) {
-    VSP_CUDA(cudaMemsetAsync(ds, 0, sizeof(float) * batch * cin, stream));
-    long long chunks = 32;
-    if (chunks > cout) chunks = cout;
-    const long long o_chunk = ceil_div64(cout, chunks);
-    dim3 grid((unsigned)ceil_div64(cin, kThreads), (unsigned)ceil_div64(cout, o_chunk), (unsigned)batch);
-    dstyle_kernel<<<grid, kThreads, 0, stream>>>(gw, w, s, corr, ds, cout, cin, taps, wscale, o_chunk);
-    if (int rc = check_launch("dstyle_kernel")) return rc;
-  }
-  if (corr) VSP_CUDA(cudaFreeAsync(corr, stream));
-  return 0;
 }
 
 // ---- weight gradient of a 1x1 convolution with very few input channels (the RGB-side layers: LargeConvLayer 3->16,

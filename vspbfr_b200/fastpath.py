@@ -176,6 +176,20 @@ def _bank_clear():
     _demod_ctx.clear()
 
 
+def _clears_banks(fn):
+    """The per-pass modulation / demodulation tables are module state: drop them when a forward ends OR raises midway, so a
+    failed pass can never leak its styles into the next one."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        try:
+            return fn(*a, **k)
+        finally:
+            _bank_clear()
+    return wrapped
+
+
 def _conv_wsq(conv):
     """Cached sum_t W^2 [Cout, Cin] of a ModulatedConv2d (style-independent part of its demodulation)."""
     return _cached(conv, "wsq", [conv.weight], lambda: mc.weight_sumsq(
@@ -554,6 +568,7 @@ def _as_nhwc(t):
 
 
 @torch.no_grad()
+@_clears_banks
 def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_index=None, truncation=1,
                         truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
     """``Restoration_net.forward`` (models/RestoreNet.py:968-1046) as a fused pipeline.
@@ -612,6 +627,7 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
 
 
 @torch.no_grad()
+@_clears_banks
 def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_latent=None, input_is_latent=False,
                       noise=None, randomize_noise=True, return_features=True, features_nchw=False, pool_image=False):
     """Style decoder ``Generator.forward`` (e4e/models/stylegan2/model.py:475-552) fused.

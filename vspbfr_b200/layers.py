@@ -18,7 +18,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .op import FusedLeakyReLU, conv2d_gradfix, fused_leaky_relu, upfirdn2d
-from .op.modconv import modulated_conv2d
+from .op.modconv import modulate_input, modulated_conv2d
 
 
 def make_kernel(k):
@@ -150,12 +150,13 @@ class _ModulatedBase(nn.Module):
         self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
         self.demodulate = demodulate
 
-    def _conv(self, input, s):
+    def _conv(self, input, s, xs=None):
+        """``xs``: ``modulate_input(input, s)`` when the caller shares it between branches (stride-1 form only)."""
         if self.upsample:
-            return self.blur(modulated_conv2d(input, self.weight, s, self.demodulate, "up", self.dilation))
+            return self.blur(modulated_conv2d(input, self.weight, s, self.demodulate, "up", self.dilation, eps=self.eps))
         if self.downsample:
-            return modulated_conv2d(self.blur(input), self.weight, s, self.demodulate, "down", self.dilation)
-        return modulated_conv2d(input, self.weight, s, self.demodulate, "same", self.dilation)
+            return modulated_conv2d(self.blur(input), self.weight, s, self.demodulate, "down", self.dilation, eps=self.eps)
+        return modulated_conv2d(input, self.weight, s, self.demodulate, "same", self.dilation, xs=xs, eps=self.eps)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "
@@ -294,7 +295,10 @@ class SMART_layer(nn.Module):
 
     def _branches(self, input, style):
         s = self.modulation(style)
-        return [branch(input, s) for branch in self.ModulatedConv2ds]
+        if any(b.upsample or b.downsample for b in self.ModulatedConv2ds):
+            return [branch(input, s) for branch in self.ModulatedConv2ds]
+        xs = modulate_input(input, s)           # the four branches read the same modulated activation: convert it once
+        return [branch._conv(input, s, xs=xs) for branch in self.ModulatedConv2ds]
 
     def forward(self, input, style, noise=None):
         out = self.noise(self.fusion(torch.cat(self._branches(input, style), dim=1)), noise=noise)

@@ -1,139 +1,121 @@
-"""conv2d_gradfix — convolution with arbitrarily-high-order gradients through a CLOSED set of ops.
+"""conv2d_gradfix — convolutions whose gradients of any order stay inside a closed set of tcgen05 ops.
 
-Mirrors /root/reference/op/conv2d_gradfix.py: same module-level API (``conv2d``,
-``conv_transpose2d``, ``no_weight_gradients()``, ``enabled``, ``weight_gradients_disabled``) and
-the same autograd structure (:134-223): forward conv, input-gradient = the transposed op with
-``calc_output_padding`` (:122-132), weight-gradient = a dedicated op whose own backward closes
-the set.  The reference's custom path is dead on torch >= 1.9 (``could_use_op`` :78-92 falls back
-to plain ``F.conv2d``, and ``no_weight_gradients`` becomes a no-op); here it is live again.
+Public surface of /root/reference/op/conv2d_gradfix.py: ``conv2d`` (:22-42), ``conv_transpose2d`` (:45-75),
+``no_weight_gradients()`` (:12-19), the flags ``enabled`` (:8) and ``weight_gradients_disabled`` (:9).  The reference's
+custom path is dead on torch >= 1.9 (``could_use_op`` :78-92 falls back to ``F.conv2d``, so ``no_weight_gradients`` does
+nothing there); here it is live, and every member of the set runs on this repo's kernels (``_plainconv``):
 
-Backends for the three primitive ops (fprop / dgrad / wgrad):
-  * ``"tcgen05"`` — the bf16 implicit-GEMM kernels of this repo (csrc/conv_sm100.cu,
-    csrc/wgrad_sm100.cu) for the shapes they cover (see ``_tc_supported``);
-  * ``"aten"``    — ATen/cuDNN fp32 for everything else (tiny channel counts such as Cin=3,
-    exotic strides).  This is the library baseline, not a CPU fallback: CPU tensors raise.
+    ConvOp(spec)          y  = conv(x, w)          forward or transposed, described by a ``ConvSpec``
+      d/dx                dx = ConvOp(spec^T)(dy, w)           the transposed op, output padding chosen to restore x's extent
+      d/dw                dw = WeightGradOp(spec)(dy, x)       skipped inside ``no_weight_gradients()``
+    WeightGradOp(spec)    dw = wgrad(dy, x)
+      d/d(dy)             ConvOp(spec)(x, ddw)                 linear in w: the same conv with the incoming cotangent as weight
+      d/dx                ConvOp(spec^T)(dy, ddw)
+
+so R1 / path-length double backward (restoration_train.py:66-73, :200-216) never leaves the set.  Two autograd Functions
+take the spec as an argument; there is no per-configuration class factory or cache.
 """
 from __future__ import annotations
 
 import contextlib
 
 import torch
-from torch import autograd
 from torch.nn import functional as F
 
-enabled = True
+from ._plainconv import ConvSpec, conv_forward, conv_weight_grad
+
+enabled = True                      # False: plain torch.nn.functional ops (what the reference does on torch >= 1.9)
 weight_gradients_disabled = False
-backend = "tcgen05"  # or "aten"
 
 
 @contextlib.contextmanager
 def no_weight_gradients():
-    """op/conv2d_gradfix.py:12-19."""
+    """Skip weight gradients inside the block (R1: only d(score)/d(image) is wanted, restoration_train.py:66-73)."""
     global weight_gradients_disabled
-    old = weight_gradients_disabled
-    weight_gradients_disabled = True
+    saved, weight_gradients_disabled = weight_gradients_disabled, True
     try:
         yield
     finally:
-        weight_gradients_disabled = old
+        weight_gradients_disabled = saved
 
 
-def _tuple(xs, ndim=2):
-    return tuple(xs) if isinstance(xs, (tuple, list)) else (xs,) * ndim
+def _pair(v):
+    if isinstance(v, (tuple, list)):
+        if len(v) != 2:
+            raise ValueError(f"conv2d_gradfix: expected an int or a pair, got {v!r}")
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
 
 
-def _check(input):
+def _require_cuda(input):
     if input.device.type != "cuda":
         raise RuntimeError("conv2d_gradfix: input must be a CUDA tensor (vspbfr_b200 has no CPU path)")
 
 
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
-    """op/conv2d_gradfix.py:22-42."""
-    _check(input)
+    _require_cuda(input)
     if not enabled:
         return F.conv2d(input, weight, bias, stride, padding, dilation, groups)
-    return conv2d_gradfix(False, weight.shape, stride, padding, 0, dilation, groups).apply(input, weight, bias)
+    spec = ConvSpec(False, _pair(stride), _pair(padding), (0, 0), _pair(dilation), int(groups))
+    return ConvOp.apply(input, weight, bias, spec)
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
-    """op/conv2d_gradfix.py:45-75."""
-    _check(input)
+    _require_cuda(input)
     if not enabled:
         return F.conv_transpose2d(input, weight, bias, stride, padding, output_padding, groups, dilation)
-    return conv2d_gradfix(True, weight.shape, stride, padding, output_padding, dilation, groups).apply(
-        input, weight, bias)
+    spec = ConvSpec(True, _pair(stride), _pair(padding), _pair(output_padding), _pair(dilation), int(groups))
+    return ConvOp.apply(input, weight, bias, spec)
 
 
-conv2d_gradfix_cache = dict()
+def _adjoint(spec: ConvSpec, x_shape, y_shape, k_shape) -> ConvSpec:
+    """Spec of the op mapping a cotangent of y back to x's extent.  For a forward conv that is the transposed op whose
+    ``output_padding`` makes up for the rows the strided forward never reached (op/conv2d_gradfix.py:122-132); for a
+    transposed conv it is the plain forward conv."""
+    if spec.transpose:
+        return spec._replace(transpose=False, output_padding=(0, 0))
+    extra = tuple(x_shape[2 + a] - ((y_shape[2 + a] - 1) * spec.stride[a] - 2 * spec.padding[a]
+                                    + spec.dilation[a] * (k_shape[2 + a] - 1) + 1) for a in range(2))
+    return spec._replace(transpose=True, output_padding=extra)
 
 
-def conv2d_gradfix(transpose, weight_shape, stride, padding, output_padding, dilation, groups):
-    """Factory of the closed autograd set, cached per configuration (op/conv2d_gradfix.py:104-227)."""
-    ndim = 2
-    weight_shape = tuple(weight_shape)
-    stride = _tuple(stride)
-    padding = _tuple(padding)
-    output_padding = _tuple(output_padding)
-    dilation = _tuple(dilation)
-    key = (transpose, weight_shape, stride, padding, output_padding, dilation, groups)
-    if key in conv2d_gradfix_cache:
-        return conv2d_gradfix_cache[key]
+class ConvOp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, weight, bias, spec):
+        ctx.spec = spec
+        ctx.save_for_backward(input, weight)
+        return conv_forward(input, weight, bias, spec)
 
-    common = dict(stride=stride, padding=padding, dilation=dilation, groups=groups)
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weight = ctx.saved_tensors
+        spec = ctx.spec
+        want_x, want_w, want_b = ctx.needs_input_grad[:3]
+        dx = dw = db = None
+        if want_x:
+            dx = ConvOp.apply(grad_output, weight, None, _adjoint(spec, input.shape, grad_output.shape, weight.shape))
+        if want_w and not weight_gradients_disabled:
+            dw = WeightGradOp.apply(grad_output, input, spec, tuple(weight.shape))
+        if want_b:
+            db = grad_output.sum((0, 2, 3))
+        return dx, dw, db, None
 
-    def calc_output_padding(input_shape, output_shape):
-        if transpose:
-            return [0, 0]
-        return [input_shape[i + 2] - (output_shape[i + 2] - 1) * stride[i] - (1 - 2 * padding[i])
-                - dilation[i] * (weight_shape[i + 2] - 1) for i in range(ndim)]
 
-    class Conv2d(autograd.Function):
-        @staticmethod
-        def forward(ctx, input, weight, bias):
-            from . import _conv_backend as cb
+class WeightGradOp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grad_output, input, spec, weight_shape):
+        ctx.spec, ctx.weight_shape = spec, weight_shape
+        ctx.save_for_backward(grad_output, input)
+        return conv_weight_grad(grad_output, input, weight_shape, spec)
 
-            if not transpose:
-                out = cb.fprop(input, weight, bias, **common)
-            else:
-                out = cb.fprop_transposed(input, weight, bias, output_padding=output_padding, **common)
-            ctx.save_for_backward(input, weight)
-            return out
-
-        @staticmethod
-        def backward(ctx, grad_output):
-            input, weight = ctx.saved_tensors
-            grad_input = grad_weight = grad_bias = None
-            if ctx.needs_input_grad[0]:
-                p = calc_output_padding(input.shape, grad_output.shape)
-                grad_input = conv2d_gradfix(not transpose, weight_shape, output_padding=p, **common).apply(
-                    grad_output, weight, None)
-            if ctx.needs_input_grad[1] and not weight_gradients_disabled:
-                grad_weight = Conv2dGradWeight.apply(grad_output, input)
-            if ctx.needs_input_grad[2]:
-                grad_bias = grad_output.sum((0, 2, 3))
-            return grad_input, grad_weight, grad_bias
-
-    class Conv2dGradWeight(autograd.Function):
-        @staticmethod
-        def forward(ctx, grad_output, input):
-            from . import _conv_backend as cb
-
-            grad_weight = cb.wgrad(grad_output, input, weight_shape, transpose=transpose,
-                                   output_padding=output_padding, **common)
-            ctx.save_for_backward(grad_output, input)
-            return grad_weight
-
-        @staticmethod
-        def backward(ctx, grad_grad_weight):
-            grad_output, input = ctx.saved_tensors
-            grad_grad_output = grad_grad_input = None
-            if ctx.needs_input_grad[0]:
-                grad_grad_output = Conv2d.apply(input, grad_grad_weight, None)
-            if ctx.needs_input_grad[1]:
-                p = calc_output_padding(input.shape, grad_output.shape)
-                grad_grad_input = conv2d_gradfix(not transpose, weight_shape, output_padding=p, **common).apply(
-                    grad_output, grad_grad_weight, None)
-            return grad_grad_output, grad_grad_input
-
-    conv2d_gradfix_cache[key] = Conv2d
-    return Conv2d
+    @staticmethod
+    def backward(ctx, grad_grad_weight):
+        grad_output, input = ctx.saved_tensors
+        spec = ctx.spec
+        gg_out = gg_in = None
+        if ctx.needs_input_grad[0]:
+            gg_out = ConvOp.apply(input, grad_grad_weight, None, spec)
+        if ctx.needs_input_grad[1]:
+            gg_in = ConvOp.apply(grad_output, grad_grad_weight, None,
+                                 _adjoint(spec, input.shape, grad_output.shape, ctx.weight_shape))
+        return gg_out, gg_in, None, None

@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import ctypes
 import math
-import weakref
 
 import torch
 from torch.autograd import Function
@@ -75,45 +74,55 @@ def _prof(name, flops, fn, detail="", nbytes=0.0):
 # thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------------
 
-_nhwc_memo = [None]     # (weakref to the source tensor, its _version, c_pad, converted tensor) of the latest plain conversion
-
-
-def nchw_to_nhwc_bf16(x, scale_nc=None, c_pad=None):
+def nchw_to_nhwc_bf16(x, scale_nc=None, c_pad=None, dot_with=None):
     """[N,C,H,W] fp32 -> [N,H,W,c_pad] bf16 (optionally * scale_nc[n,c]); extra channels are zero.
-
-    The latest un-scaled conversion is memoised on the identity and version of its source: the four dilated branches of a
-    SMART layer (models/RestoreNet.py:229-233) convert the same input in forward and again in backward — a quarter of the
-    ~500 layout conversions of a training iteration."""
+    ``dot_with`` (same shape as x): additionally returns dot[n,c] = sum_p x[n,c,p] * dot_with[n,c,p] (x unscaled) from the
+    same pass — the demodulation gradient sum_p dy*y rides on the conversion of dy."""
     n, c, h, w = x.shape
     c_pad = c_pad or _round_up(c, 8)
-    memo = _nhwc_memo[0]
-    if (scale_nc is None and memo is not None and memo[0]() is x and memo[1] == x._version and memo[2] == c_pad
-            and not torch.cuda.is_current_stream_capturing()):
-        return memo[3]
     xc = x.contiguous()
     y = torch.empty((n, h, w, c_pad), dtype=torch.bfloat16, device=x.device)
+    dot = None
+    if dot_with is not None:
+        if (h * w) % 4 or c_pad == 8 or (xc.data_ptr() | dot_with.data_ptr()) & 15:     # shapes the fused reduction does not cover
+            dot, dot_with = (xc * dot_with).sum((2, 3)), None
+        else:
+            dot_with = dot_with.contiguous()
+            dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
     if y.numel():
         with torch.cuda.device(x.device):
-            rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16(ptr(xc), ptr(scale_nc), ptr(y), n, c, h * w, c_pad, stream_ptr())
+            rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16_dot(ptr(xc), ptr(scale_nc), ptr(dot_with), ptr(y),
+                                                           ptr(dot) if dot_with is not None else None, n, c, h * w, c_pad,
+                                                           stream_ptr())
         _lib.check(rc, "nchw_f32_to_nhwc_bf16")
-    if scale_nc is None and not torch.cuda.is_current_stream_capturing():
-        try:
-            _nhwc_memo[0] = (weakref.ref(x), x._version, c_pad, y)
-        except TypeError:
-            _nhwc_memo[0] = None
-    return y
+    return y if dot is None else (y, dot)
 
 
-def nhwc_bf16_to_nchw(x, c=None):
-    """[N,H,W,c_pad] bf16 -> [N,c,H,W] fp32."""
+def nhwc_bf16_to_nchw(x, c=None, scale_nc=None, dot_with=None):
+    """[N,H,W,c_pad] bf16 -> [N,c,H,W] fp32, optionally * scale_nc[n,c]; ``dot_with`` [N,c,H,W] fp32 additionally
+    returns dot[n,c] = sum_p x[n,p,c] * dot_with[n,c,p] (x unscaled) — the style gradient sum_p x*d(x*s)."""
     n, h, w, c_pad = x.shape
     c = c or c_pad
     y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    fused = (h * w) % 4 == 0 and c_pad % 8 == 0
+    if not fused and (scale_nc is not None or dot_with is not None):
+        y = nhwc_bf16_to_nchw(x, c)
+        dot = (y * dot_with).sum((2, 3)) if dot_with is not None else None
+        if scale_nc is not None:
+            y = y * scale_nc.reshape(n, c, 1, 1)
+        return y if dot_with is None else (y, dot)
+    dot = None
+    if dot_with is not None:
+        dot_with = dot_with.contiguous()
+        dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    if scale_nc is not None:
+        scale_nc = scale_nc.contiguous()
     if y.numel():
         with torch.cuda.device(x.device):
-            rc = _lib.load().vsp_nhwc_bf16_to_nchw_f32(ptr(x.contiguous()), ptr(y), n, c, h * w, c_pad, stream_ptr())
+            rc = _lib.load().vsp_nhwc_bf16_to_nchw_f32_dot(ptr(x.contiguous()), ptr(scale_nc), ptr(dot_with), ptr(y), ptr(dot),
+                                                           n, c, h * w, c_pad, stream_ptr())
         _lib.check(rc, "nhwc_bf16_to_nchw_f32")
-    return y
+    return y if dot_with is None else (y, dot)
 
 
 def nchw_to_bf16(x, scale_nc=None):
@@ -380,193 +389,209 @@ def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
     return gw
 
 
-def weight_style_grad(gw, weight, style, demod, wscale, want_dw=True, want_ds=True):
-    b, taps, cout, cin = gw.shape
-    dw = torch.empty((cout, cin, taps), dtype=torch.float32, device=gw.device) if want_dw else None
-    ds = torch.empty((b, cin), dtype=torch.float32, device=gw.device) if want_ds else None
-    with torch.cuda.device(gw.device):
-        rc = _lib.load().vsp_modconv_weight_style_grad(ptr(gw), ptr(weight.contiguous()), ptr(style.contiguous()),
-                                                       ptr(demod), ptr(dw), ptr(ds), b, cout, cin, taps, wscale,
-                                                       stream_ptr())
-    _lib.check(rc, "modconv_weight_style_grad")
-    return dw, ds
-
-
-# ----------------------------------------------------------------------------------------------
-# plain convolution primitives for conv2d_gradfix (NCHW fp32 boundary)
-# ----------------------------------------------------------------------------------------------
-
-def plain_conv_supported(input, weight_shape, stride, padding, dilation, groups, transpose):
-    """The tcgen05 path covers square stride-1/2 convs with <= 16 taps; groups == 1, or the
-    reference's grouped form (input [1, B*Cin, H, W], groups == B)."""
-    if input.dtype != torch.float32 or input.ndim != 4:
-        return False
-    if transpose:
-        return False  # transposed fprop of conv2d_gradfix goes through ATen for now (see DESIGN.md)
-    cout_total, cin_g, kh, kw = weight_shape
-    if kh * kw > 16 or stride[0] != stride[1] or stride[0] not in (1, 2):
-        return False
-    if padding[0] != padding[1] or dilation[0] != dilation[1]:
-        return False
-    if groups != 1 and input.shape[0] != 1:
-        return False
-    if cin_g < 8 or input.shape[2] < 1:
-        return False
-    return True
-
-
-def plain_conv_fprop(input, weight, bias, stride, padding, dilation, groups):
-    n, c_total, h, w = input.shape
-    cout_total, cin, kh, kw = weight.shape
-    cout = cout_total // groups
-    if groups == 1:
-        x = nchw_to_nhwc_bf16(input)
-        wq, _ = pack_weights(weight)
-        epi = make_epilogue(bias=bias) if bias is not None else None
-        return conv_fprop(x, wq, cout, kh, kw, stride[0], padding[0], dilation[0], epi=epi)
-    # grouped form of the modulated conv: [1, B*Cin, H, W] x [B*Cout, Cin, k, k]
-    x = nchw_to_nhwc_bf16(input.reshape(groups, cin, h, w))
-    wq = weight.reshape(groups, cout, cin, kh * kw).permute(0, 3, 1, 2)
-    k_pad = _round_up(cin, 8)
-    wq_p = torch.zeros((groups, kh * kw, cout, k_pad), dtype=torch.bfloat16, device=input.device)
-    wq_p[..., :cin] = wq.to(torch.bfloat16)
-    out = conv_fprop(x, wq_p, cout, kh, kw, stride[0], padding[0], dilation[0])
-    out = out.reshape(1, groups * cout, out.shape[2], out.shape[3])
-    if bias is not None:
-        out = out + bias.reshape(1, -1, 1, 1)
+def conv_transposed(x_nhwc, wq, cout, kh, kw, stride, pad=(0, 0), dil=(1, 1), out_pad=(0, 0), out=None, epi=None,
+                    out_nhwc=False):
+    """General transposed convolution (``F.conv_transpose2d`` semantics) without a zero-stuffed intermediate:
+    out[y, x] = sum over taps (i, j) and input pixels (a, b) with y = a*stride - pad + i*dil of x[a, b] * w[i, j].
+    One gather launch per output parity class (stride^2 classes); class (pa, pb) owns the output pixels
+    (A*stride + pa, B*stride + pb) and reads x[A + (pa + pad - i*dil)/stride] for the taps where that is an integer.
+    x_nhwc [B,H,W,K] bf16, wq [G,kh*kw,n_pad,K] (n = output channels) -> [B,cout,FH,FW] fp32 NCHW (or NHWC bf16) with
+    FH = (H-1)*stride - 2*pad + dil*(kh-1) + out_pad + 1."""
+    b, h, w, _ = x_nhwc.shape
+    s = stride
+    (ph, pw), (dh, dw), (oph, opw) = pad, dil, out_pad
+    fh = (h - 1) * s - 2 * ph + dh * (kh - 1) + oph + 1
+    fw = (w - 1) * s - 2 * pw + dw * (kw - 1) + opw + 1
+    if out is None:
+        out = (torch.zeros((b, max(fh, 0), max(fw, 0), _round_up(cout, 8)), dtype=torch.bfloat16, device=x_nhwc.device)
+               if out_nhwc else torch.empty((b, cout, max(fh, 0), max(fw, 0)), dtype=torch.float32, device=x_nhwc.device))
+    if out.numel() == 0:
+        return out
+    classes = []
+    for pa in range(s):
+        for pb in range(s):
+            taps = [(i, j) for i in range(kh) for j in range(kw)
+                    if (pa + ph - i * dh) % s == 0 and (pb + pw - j * dw) % s == 0]
+            rows, cols = (fh - pa + s - 1) // s, (fw - pb + s - 1) // s
+            if rows > 0 and cols > 0:
+                classes.append((pa, pb, taps, rows, cols))
+    if any(not c[2] for c in classes):
+        out.zero_()                                  # a class without taps (e.g. 1x1 stride 2) stays zero
+    for pa, pb, taps, rows, cols in classes:
+        if taps:
+            conv_gather(x_nhwc, wq, cout, [i * kw + j for i, j in taps], [(pa + ph - i * dh) // s for i, j in taps],
+                        [(pb + pw - j * dw) // s for i, j in taps], 1, (rows, cols), full_hw=(fh, fw), os_=s,
+                        oo=(pa, pb), out=out, epi=epi, out_nhwc=out_nhwc)
     return out
 
 
-def plain_conv_dgrad(*a, **k):  # pragma: no cover - routed to ATen by plain_conv_supported
-    raise RuntimeError("plain_conv_dgrad: not routed to tcgen05")
-
-
-def plain_conv_wgrad(grad_output, input, weight_shape, stride, padding, dilation, groups):
-    """Returns None when the wgrad kernel does not cover the shape (caller uses ATen)."""
-    return None
-
-
 # ----------------------------------------------------------------------------------------------
-# the modulated convolution (NCHW fp32 boundary, fused tcgen05 path)
+# the modulated convolution (NCHW fp32 boundary): modulation in the producer, demodulation in the epilogue
 # ----------------------------------------------------------------------------------------------
+#
+#   y[b] = d[b,o] * conv(x[b] * s[b,i], wscale * W)         d[b,o] = rsqrt(wscale^2 * sum_i s[b,i]^2 * sum_t W[o,i,t]^2 + eps)
+#
+# is the reference's un-fused branch (models/RestoreNet.py:481-508) and algebraically its fused one (:510-553).  Nothing
+# per-sample is ever materialised: the style scales the ACTIVATION inside the NCHW fp32 -> NHWC bf16 conversion the
+# tensor-core path needs anyway (`ModulateInput`), the GEMM runs on ONE shared bf16 weight tensor (`SharedWeightConv`:
+# samples may share an M tile, the weight gradient is one batch-summed GEMM), demodulation is a row scale in the epilogue,
+# and `demod_coefs` is plain (twice differentiable) tensor algebra on [B,Cin] x [Cin,Cout], so autograd supplies the
+# demodulation terms of dW and ds.  The style gradient needs no per-sample weight gradient either:
+# ds[b,i] = sum_p x[b,i,p] * dxs[b,i,p], a reduction fused into the conversion of the incoming gradient.
 
-def _modconv_reference_form(x, weight, s, demodulate, mode, dilation, eps=1e-8):
-    """The reference's own formulation (models/RestoreNet.py:510-553: materialised per-sample
-    weights + grouped conv through conv2d_gradfix).  Differentiable to any order; used for the
-    double-backward path (create_graph=True) of ModulatedConv2dFunction."""
-    from . import conv2d_gradfix
-
-    b, cin, h, w_ = x.shape
-    _, cout, _, k, _ = weight.shape
-    wscale = 1.0 / math.sqrt(cin * k * k)
-    wm = wscale * weight * s.reshape(b, 1, cin, 1, 1)
-    if demodulate:
-        d = torch.rsqrt(wm.pow(2).sum([2, 3, 4]) + eps)
-        wm = wm * d.reshape(b, cout, 1, 1, 1)
-    xin = x.reshape(1, b * cin, h, w_)
-    if mode == "up":
-        wt = wm.transpose(1, 2).reshape(b * cin, cout, k, k)
-        out = conv2d_gradfix.conv_transpose2d(xin, wt, padding=0, stride=2, groups=b, dilation=dilation)
-    elif mode == "down":
-        out = conv2d_gradfix.conv2d(xin, wm.reshape(b * cout, cin, k, k), padding=0, stride=2, groups=b,
-                                    dilation=dilation)
-    else:
-        out = conv2d_gradfix.conv2d(xin, wm.reshape(b * cout, cin, k, k), padding=((k - 1) * dilation) // 2,
-                                    groups=b, dilation=dilation)
-    return out.reshape(b, cout, out.shape[2], out.shape[3])
+def _taps(k):
+    return [(i, j) for i in range(k) for j in range(k)]
 
 
-class ModulatedConv2dFunction(Function):
-    """y[b] = demod[b] * conv(x[b], wscale * W * s[b]) on tcgen05 (bf16 operands, fp32 accumulate).
+def demod_coefs(weight, s, wscale, eps=1e-8):
+    """d[b,o] (models/RestoreNet.py:513-516) from the style-independent sum_t W^2; differentiable in W and s."""
+    wsq = weight.reshape(weight.shape[-4], weight.shape[-3], -1).square().sum(-1)          # [Cout, Cin]
+    return torch.rsqrt((wscale * wscale) * (s.square() @ wsq.t()) + eps)
 
-    mode: "same" (stride 1, padding (k-1)*dil/2), "down" (stride 2, padding 0 — the caller blurs
-    first), "up" (transposed stride 2, padding 0 — the caller blurs afterwards).
-    First-order backward runs on the same kernels (dgrad = gather conv with transposed weights,
-    wgrad = pixel-K GEMM, style/weight gradients incl. the demodulation term); when autograd asks
-    for a differentiable backward (create_graph=True) it switches to the reference formulation
-    through conv2d_gradfix, which is closed under differentiation.
-    """
+
+class ModulateInput(Function):
+    """xs = bf16(x * s[b,i]) in NHWC (s None: plain layout conversion).  Backward turns the NHWC bf16 gradient of xs
+    into dx = dxs * s (NCHW fp32) and ds = sum_p x * dxs in one pass."""
 
     @staticmethod
-    def forward(ctx, x, weight, s, demodulate, mode, dilation):
-        b, cin, h, w_ = x.shape
-        _, cout, cin_w, k, _ = weight.shape
-        if cin_w != cin or s.shape != (b, cin):
-            raise RuntimeError(f"modulated_conv2d: shape mismatch x{tuple(x.shape)} w{tuple(weight.shape)} s{tuple(s.shape)}")
+    def forward(ctx, x, s):
         if x.device.type != "cuda":
             raise RuntimeError("modulated_conv2d: input must be a CUDA tensor (vspbfr_b200 has no CPU path)")
+        ctx.save_for_backward(x, s)
+        return nchw_to_nhwc_bf16(x, scale_nc=s.contiguous() if s is not None else None)
+
+    @staticmethod
+    def backward(ctx, dxs):
+        x, s = ctx.saved_tensors
+        c = x.shape[1]
+        if torch.is_grad_enabled():                      # double backward: plain tensor algebra
+            g = dxs[..., :c].permute(0, 3, 1, 2).float()
+            if s is None:
+                return g, None
+            return g * s[:, :, None, None], (g * x).sum((2, 3)) if ctx.needs_input_grad[1] else None
+        if s is None:
+            return nhwc_bf16_to_nchw(dxs, c), None
+        if ctx.needs_input_grad[1]:
+            dx, ds = nhwc_bf16_to_nchw(dxs, c, scale_nc=s, dot_with=x)
+            return (dx if ctx.needs_input_grad[0] else None), ds
+        return nhwc_bf16_to_nchw(dxs, c, scale_nc=s), None
+
+
+def _shared_conv_reference(xs, weight, d, mode, dilation, cin):
+    """SharedWeightConv out of conv2d_gradfix ops (differentiable to any order) — the double-backward route."""
+    from . import conv2d_gradfix
+
+    cout, _, k, _ = weight.shape
+    xf = xs[..., :cin].permute(0, 3, 1, 2).float()
+    w = weight * (1.0 / math.sqrt(cin * k * k))
+    if mode == "up":
+        z = conv2d_gradfix.conv_transpose2d(xf, w.transpose(0, 1), stride=2, padding=0, dilation=dilation)
+    elif mode == "down":
+        z = conv2d_gradfix.conv2d(xf, w, stride=2, padding=0, dilation=dilation)
+    else:
+        z = conv2d_gradfix.conv2d(xf, w, padding=((k - 1) * dilation) // 2, dilation=dilation)
+    return z if d is None else z * d[:, :, None, None]
+
+
+class SharedWeightConv(Function):
+    """y = d[b,o] * conv(xs, wscale * W) on tcgen05: xs [B,H,W,Cin_pad] bf16 NHWC, W [Cout,Cin,k,k] fp32 (shared by the
+    batch), d [B,Cout] fp32 or None -> y [B,Cout,OH,OW] fp32 NCHW.
+    mode: "same" (stride 1, padding (k-1)*dil/2), "down" (stride 2, padding 0), "up" (transposed, stride 2, padding 0).
+    Backward: dz = d * dy (fused into the NHWC conversion of dy together with sum_p dy*y, which gives dL/dd = that / d);
+    dxs = the adjoint convolution of dz (NHWC bf16 out); dW = wscale * the batch-summed pixel-K GEMM of dz and xs."""
+
+    @staticmethod
+    def forward(ctx, xs, weight, d, mode, dilation):
+        cout, cin, k, _ = weight.shape
         wscale = 1.0 / math.sqrt(cin * k * k)
-        w4 = weight.reshape(cout, cin, k, k)
-        xq = nchw_to_nhwc_bf16(x)
-        # demodulation from sum_t W^2 (one well-parallelised pass over the weights + a [B,Cout] pass over it) instead of the
-        # warp-per-(b,o) walk over all of W (52 us per call at 512x512x9, 165 calls per training iteration)
-        wq, d = pack_weights(w4, s, wscale=wscale, want_demod=demodulate, wsq=weight_sumsq(w4) if demodulate else None)
-        epi = make_epilogue(row_scale=d) if demodulate else None
+        wq, _ = pack_weights(weight, wscale=wscale)
+        if wq.shape[3] != xs.shape[3]:
+            raise RuntimeError(f"modulated_conv2d: activation has {xs.shape[3]} channels, weight expects {wq.shape[3]}")
+        epi = make_epilogue(row_scale=d.contiguous()) if d is not None else None
         if mode == "up":
-            if dilation != 1:
-                raise RuntimeError("modulated_conv2d: dilated transposed convolution is not supported")
-            out = conv_transpose_s2(xq, wq, cout, k, k, epi=epi)
+            out = conv_transposed(xs, wq, cout, k, k, 2, dil=(dilation, dilation), epi=epi)
         elif mode == "down":
-            out = conv_fprop(xq, wq, cout, k, k, 2, 0, dilation, epi=epi)
+            out = conv_fprop(xs, wq, cout, k, k, 2, 0, dilation, epi=epi)
         else:
-            out = conv_fprop(xq, wq, cout, k, k, 1, ((k - 1) * dilation) // 2, dilation, epi=epi)
-        ctx.save_for_backward(x, weight, s, d if demodulate else None)
-        ctx.cfg = (demodulate, mode, dilation, wscale)
+            out = conv_fprop(xs, wq, cout, k, k, 1, ((k - 1) * dilation) // 2, dilation, epi=epi)
+        ctx.save_for_backward(xs, weight, d, out if d is not None else None)
+        ctx.cfg = (mode, dilation, wscale)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, s, d = ctx.saved_tensors
-        demodulate, mode, dilation, wscale = ctx.cfg
+        xs, weight, d, y = ctx.saved_tensors
+        mode, dilation, wscale = ctx.cfg
+        cout, cin, k, _ = weight.shape
+        need_x, need_w, need_d = ctx.needs_input_grad[:3]
         if torch.is_grad_enabled():
-            # differentiable backward requested (double backward): closed-set formulation
             with torch.enable_grad():
-                y = _modconv_reference_form(x, weight, s, demodulate, mode, dilation)
-                need = [t for t, n in zip((x, weight, s), ctx.needs_input_grad[:3]) if n]
-                grads = list(torch.autograd.grad(y, need, dy, create_graph=True, allow_unused=True))
-            out = []
-            for n in ctx.needs_input_grad[:3]:
-                out.append(grads.pop(0) if n else None)
-            return (*out, None, None, None)
+                out = _shared_conv_reference(xs, weight, d, mode, dilation, cin)
+                wanted = [t for t, n in zip((xs, weight, d), (need_x, need_w, need_d)) if n]
+                grads = list(torch.autograd.grad(out, wanted, dy, create_graph=True, allow_unused=True))
+            res = [grads.pop(0) if n else None for n in (need_x, need_w, need_d)]
+            if res[0] is not None and res[0].dtype != xs.dtype:
+                res[0] = res[0].to(xs.dtype)
+            return (*res, None, None)
 
-        b, cin, h, w_ = x.shape
-        _, cout, _, k, _ = weight.shape
-        w4 = weight.reshape(cout, cin, k, k)
+        b, h, w_, _ = xs.shape
         pad = ((k - 1) * dilation) // 2
-        dzq = nchw_to_nhwc_bf16(dy, scale_nc=d)           # dz = demod * dy, channels-last bf16
-        taps = [(i, j) for i in range(k) for j in range(k)]
-        dx = dw = ds = None
-        if ctx.needs_input_grad[0]:
-            wq_t, _ = pack_weights(w4, s, wscale=wscale, transpose=True)
+        dxs = dw = dd = None
+        if d is not None:
+            dzq, dot = nchw_to_nhwc_bf16(dy, scale_nc=d, dot_with=y)       # dz = d * dy ; dot = sum_p dy * y
+            if need_d:
+                dd = dot / d
+        else:
+            dzq = nchw_to_nhwc_bf16(dy)
+        taps = _taps(k)
+        if need_x:
+            wq_t, _ = pack_weights(weight, wscale=wscale, transpose=True)   # n = Cin, k = Cout
+            cpad = xs.shape[3]
             if mode == "same":
-                dx = conv_gather(dzq, wq_t, cin, [i * k + j for i, j in taps], [pad - i * dilation for i, j in taps],
-                                 [pad - j * dilation for i, j in taps], 1, (h, w_))
+                dxs = conv_gather(dzq, wq_t, cin, [i * k + j for i, j in taps], [pad - i * dilation for i, j in taps],
+                                  [pad - j * dilation for i, j in taps], 1, (h, w_), out_nhwc=True,
+                                  out=_nhwc_out(b, h, w_, cin, cpad, xs.device))
             elif mode == "down":
-                dx = conv_transpose_s2(dzq, wq_t, cin, k, k)
-                if dx.shape[2] != h or dx.shape[3] != w_:   # even-sized inputs lose their last row/col to stride 2
-                    full = torch.zeros_like(x)
-                    full[:, :, :dx.shape[2], :dx.shape[3]] = dx[:, :, :h, :w_]
-                    dx = full
+                reach = dilation * (k - 1) + 1
+                dxs = conv_transposed(dzq, wq_t, cin, k, k, 2, dil=(dilation, dilation), out_nhwc=True,
+                                      out_pad=(h - ((dy.shape[2] - 1) * 2 + reach), w_ - ((dy.shape[3] - 1) * 2 + reach)),
+                                      out=_nhwc_out(b, h, w_, cin, cpad, xs.device))
             else:
-                dx = conv_fprop(dzq, wq_t, cin, k, k, 2, 0, 1)
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            xq = nchw_to_nhwc_bf16(x)
+                dxs = conv_fprop(dzq, wq_t, cin, k, k, 2, 0, dilation, out_nhwc=True,
+                                 out=_nhwc_out(b, h, w_, cin, cpad, xs.device))
+        if need_w:
             if mode == "up":
-                # y[2p+t] += x[p] w[t]  =>  G[t,o,i] = sum_p x[p,i] dz[2p+t,o]: roles swapped, then transposed
-                gw = conv_wgrad(xq, dzq, b, k, k, 2, 0, 1).transpose(2, 3).contiguous()
+                # y[2p + t*dil] += xs[p] w[t]  =>  G[t,o,i] = sum_p xs[p,i] dz[2p + t*dil, o]: roles swapped, then transposed
+                gw = conv_wgrad(xs, dzq, 1, k, k, 2, 0, dilation).transpose(2, 3)
             elif mode == "down":
-                gw = conv_wgrad(dzq, xq, b, k, k, 2, 0, dilation)
+                gw = conv_wgrad(dzq, xs, 1, k, k, 2, 0, dilation)
             else:
-                gw = conv_wgrad(dzq, xq, b, k, k, 1, pad, dilation)
-            gw = gw[:, :, :cout, :cin]
-            if gw.shape[2] != cout or not gw.is_contiguous():
-                gw = gw.contiguous()
-            dw, ds = weight_style_grad(gw, w4, s, d, wscale, ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-            if dw is not None:
-                dw = dw.reshape(weight.shape)
-        return dx, dw, ds, None, None, None
+                gw = conv_wgrad(dzq, xs, 1, k, k, 1, pad, dilation)
+            dw = (gw[0, :, :cout, :cin].permute(1, 2, 0) * wscale).reshape(weight.shape)
+        return dxs, dw, dd, None, None
 
 
-def modulated_conv2d(x, weight, s, demodulate=True, mode="same", dilation=1):
-    """x [B,Cin,H,W] fp32, weight [1,Cout,Cin,k,k], s [B,Cin] (already through ``modulation``)."""
-    return ModulatedConv2dFunction.apply(x, weight, s, demodulate, mode, dilation)
+def _nhwc_out(b, h, w, c, c_pad, device):
+    """NHWC bf16 gradient buffer; padding channels (c..c_pad) must read as zero."""
+    if c_pad == c:
+        return torch.empty((b, h, w, c_pad), dtype=torch.bfloat16, device=device)
+    return torch.zeros((b, h, w, c_pad), dtype=torch.bfloat16, device=device)
+
+
+def modulate_input(x, s=None):
+    """x [B,C,H,W] fp32 (* s [B,C]) -> NHWC bf16 activation shared by every convolution that consumes x with this style
+    (the four dilated branches of a SMART layer convert their common input once)."""
+    return ModulateInput.apply(x, s)
+
+
+def modulated_conv2d(x, weight, s, demodulate=True, mode="same", dilation=1, xs=None, eps=1e-8):
+    """x [B,Cin,H,W] fp32, weight [1,Cout,Cin,k,k], s [B,Cin] (already through ``modulation``) -> [B,Cout,OH,OW] fp32.
+    ``xs``: the result of ``modulate_input(x, s)`` when the caller shares it between several convolutions."""
+    _, cout, cin, k, _ = weight.shape
+    if xs is None:
+        if x.shape[1] != cin or s.shape != (x.shape[0], cin):
+            raise RuntimeError(f"modulated_conv2d: shape mismatch x{tuple(x.shape)} w{tuple(weight.shape)} s{tuple(s.shape)}")
+        xs = modulate_input(x, s)
+    w4 = weight.reshape(cout, cin, k, k)
+    d = demod_coefs(w4, s, 1.0 / math.sqrt(cin * k * k), eps) if demodulate else None
+    return SharedWeightConv.apply(xs, w4, d, mode, dilation)
