@@ -355,7 +355,7 @@ int vsp_torgb_pool2_nhwc_bf16(const void *x, const float *w, const float *s, con
 
 /*
  * Weight gradient as a bf16 GEMM on tcgen05 (K = pixels):
- *   gw[g, t, o, i] = sum_{p in sample(s) of group g} dy[b,p,o] * x[b, p*stride + t*dil - pad, i]
+ *   gw[g, t, o, i] = sum_{p in sample(s) of group g} dy[b,p,o] * x[b, p*stride + t*dil - pad, i]   (pad / dil per axis)
  * Replaces aten::cudnn_convolution_backward_weight, op/conv2d_gradfix.py:177-199.
  *   dy [batch, out_h, out_w, cout] bf16 NHWC, x [batch, in_h, in_w, cin] bf16 NHWC
  *   (cin, cout multiples of 8); both operands are consumed channel-contiguous (MN-major UMMA).
@@ -365,7 +365,8 @@ int vsp_torgb_pool2_nhwc_bf16(const void *x, const float *w, const float *s, con
 int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw,
                           int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
                           int64_t cin, int64_t cout, int64_t out_h, int64_t out_w,
-                          int kh, int kw, int stride, int pad, int dil, void *stream);
+                          int kh, int kw, int stride, int pad_h, int pad_w, int dil_h, int dil_w,
+                          void *stream);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,40 @@ from .upfirdn2d_ref import upfirdn2d_native_port
 SQRT2 = math.sqrt(2.0)
 
 
+class _RoundBf16(torch.autograd.Function):
+    """Round to bf16 in the forward AND round the cotangent in the backward — what a bf16-operand GEMM does to both passes."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().to(g.dtype)
+
+
+_emulate_bf16 = False
+
+
+def _conv2d(x, w, bias=None, **kw):
+    if _emulate_bf16:
+        x, w = _RoundBf16.apply(x), _RoundBf16.apply(w)
+    return F.conv2d(x, w, bias, **kw)
+
+
+class bf16_operands:
+    """``with bf16_operands():`` the oracle's convolutions take bf16-rounded operands (fp32 accumulation) — the precision
+    floor of ANY bf16 tensor-core implementation of the same network, used by the GPU tests to size their tolerances."""
+
+    def __enter__(self):
+        global _emulate_bf16
+        self._saved, _emulate_bf16 = _emulate_bf16, True
+
+    def __exit__(self, *exc):
+        global _emulate_bf16
+        _emulate_bf16 = self._saved
+
+
 def _blur(x, pad):
     k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=x.dtype)
     k = torch.outer(k, k)
@@ -42,7 +76,7 @@ def _conv_layer(sd, p, x, k, downsample=False, activate=True):
     w = sd[f"{p}{i}.weight"]
     scale = 1.0 / math.sqrt(w.shape[1] * k * k)
     bias = sd.get(f"{p}{i}.bias")
-    x = F.conv2d(x, w * scale, bias, stride=2 if downsample else 1, padding=0 if downsample else k // 2)
+    x = _conv2d(x, w * scale, bias, stride=2 if downsample else 1, padding=0 if downsample else k // 2)
     if activate:
         x = _lrelu(x, sd.get(f"{p}{i + 1}.bias"))
     return x

@@ -27,7 +27,8 @@ class Policy:
     term (hi + lo) for that operand, i.e. a 2-pass / 3-pass tensor-core product."""
 
     def __init__(self, w=True, x=True, store=True, stages=None, split_w=False, split_x=False, split_stages=None,
-                 fp32_store_stages=None):
+                 fp32_store_stages=None, w_fp16=False):
+        self.w_fp16 = w_fp16            # weight operand in fp16 (11-bit significand) instead of bf16 (8-bit)
         self.w, self.x, self.store, self.stages = w, x, store, stages
         self.split_w, self.split_x, self.split_stages = split_w, split_x, split_stages
         self.fp32_store_stages = fp32_store_stages or set()
@@ -47,6 +48,8 @@ class Policy:
         return hi
 
     def qw(self, t):
+        if self.w_fp16 and self.w and self._on():
+            return t.half().float()
         return self._r(t, self.split_w and self._split()) if (self.w and self._on()) else t
 
     def qx(self, t):
@@ -222,6 +225,15 @@ POLICIES.update({
     "all_le64_exact": lambda: Policy(split_w=True, split_x=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32, 64])),
     "enc_le128_exact": lambda: Policy(split_w=True, split_x=True, split_stages=_lv(["enc"], [4, 8, 16, 32, 64, 128])),
     "enc_exact": lambda: Policy(split_w=True, split_x=True, split_stages={"enc"}),
+    "fp16_w": lambda: Policy(w_fp16=True),
+    "fp16_w_enc_split_x": lambda: Policy(w_fp16=True, split_x=True, split_stages={"enc"}),
+    "fp16_w_le32_split_x": lambda: Policy(w_fp16=True, split_x=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32])),
+    "enc_split_w": lambda: Policy(split_w=True, split_stages={"enc"}),
+    "enc_le64_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc"], [4, 8, 16, 32, 64])),
+    "enc_le32_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc"], [4, 8, 16, 32])),
+    "le32_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32])),
+    "le64_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32, 64])),
+    "le128_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32, 64, 128])),
 })
 
 

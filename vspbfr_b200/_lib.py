@@ -193,7 +193,7 @@ SIGNATURES = {
                                           c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vsp_conv2d_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
-                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vsp_nchw_f32_to_nhwc_bf16_dot": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
     "vsp_nhwc_bf16_to_nchw_f32_dot": (c_int, [c_void_p] * 5 + [c_int64] * 4 + [c_void_p]),
 }

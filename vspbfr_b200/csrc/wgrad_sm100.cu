@@ -291,8 +291,8 @@ inline int next_pow2(int v) {
 
 extern "C" int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw, int64_t batch, int64_t groups,
                                      int64_t in_h, int64_t in_w, int64_t cin, int64_t cout, int64_t out_h,
-                                     int64_t out_w, int kh, int kw, int stride, int pad, int dil,
-                                     void *stream_) {
+                                     int64_t out_w, int kh, int kw, int stride, int pad_h, int pad_w, int dil_h,
+                                     int dil_w, void *stream_) {
   using namespace vsp;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   VSP_REQUIRE(batch >= 1 && (groups == 1 || groups == batch), "wgrad: groups must be 1 or batch");
@@ -312,8 +312,8 @@ extern "C" int vsp_conv2d_wgrad_bf16(const void *dy, const void *x, float *gw, i
   p.out_h = (int)out_h; p.out_w = (int)out_w; p.stride = stride; p.ntaps = kh * kw;
   for (int i = 0; i < kh; ++i)
     for (int j = 0; j < kw; ++j) {
-      p.tap_dy[i * kw + j] = i * dil - pad;
-      p.tap_dx[i * kw + j] = j * dil - pad;
+      p.tap_dy[i * kw + j] = i * dil_h - pad_h;
+      p.tap_dx[i * kw + j] = j * dil_w - pad_w;
     }
   p.kwb = next_pow2((int)out_w) < kPixK ? next_pow2((int)out_w) : kPixK;
   p.khb = kPixK / p.kwb;

@@ -139,15 +139,13 @@ def conv_weight_grad(grad_output, input, weight_shape, spec: ConvSpec):
         sampled, pixels = input, grad_output
     kh, kw = weight_shape[2], weight_shape[3]
     _check(spec, kh, kw)
-    if spec.padding[0] != spec.padding[1] or spec.dilation[0] != spec.dilation[1]:
-        raise RuntimeError("conv2d_gradfix: weight gradient needs equal padding / dilation on both axes")
-    g, s, p, d = spec.groups, spec.stride[0], spec.padding[0], spec.dilation[0]
+    g, s, p, d = spec.groups, spec.stride[0], tuple(spec.padding), tuple(spec.dilation)
     n = input.shape[0]
     c_pix, c_smp = pixels.shape[1] // g, sampled.shape[1] // g      # gw rows / columns per group
     gw_total = torch.zeros(weight_shape, dtype=torch.float32, device=input.device) if (g > 1 and n > 1) else None
     if grad_output.numel() == 0 or input.numel() == 0:
         return torch.zeros(weight_shape, dtype=torch.float32, device=input.device)
-    small = (not spec.transpose and g == 1 and kh == 1 and kw == 1 and c_smp <= 8 and s == 1 and p == 0
+    small = (not spec.transpose and g == 1 and kh == 1 and kw == 1 and c_smp <= 8 and s == 1 and p == (0, 0)
              and (input.shape[2] * input.shape[3]) % 4 == 0 and n <= 65535)
     if small:
         # RGB-side 1x1 layers (3 -> 16, 3 -> 64): a streaming reduction beats a GEMM whose N is 8 padded columns

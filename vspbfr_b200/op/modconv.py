@@ -377,14 +377,16 @@ def conv_up2_fused(x_nhwc, wq, cout, epi=None, out=None, co_off=0):
 
 
 def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
-    """gw[g,t,o,i] = sum_p dy[b,p,o] x[b, p*stride + t*dil - pad, i] (tap-major); groups == batch or 1.
+    """gw[g,t,o,i] = sum_p dy[b,p,o] x[b, p*stride + t*dil - pad, i] (tap-major); groups == batch or 1; ``pad`` / ``dil``
+    are ints or per-axis (h, w) pairs.
     dy_nhwc [B,OH,OW,Cout_pad] bf16, x_nhwc [B,H,W,Cin_pad] bf16 -> [groups, kh*kw, Cout_pad, Cin_pad] fp32."""
     b, oh, ow, cout = dy_nhwc.shape
     _, h, w, cin = x_nhwc.shape
     gw = torch.empty((groups, kh * kw, cout, cin), dtype=torch.float32, device=dy_nhwc.device)
+    (ph, pw), (dh, dw) = (pad if isinstance(pad, tuple) else (pad, pad)), (dil if isinstance(dil, tuple) else (dil, dil))
     with torch.cuda.device(dy_nhwc.device):
         rc = _lib.load().vsp_conv2d_wgrad_bf16(ptr(dy_nhwc), ptr(x_nhwc), ptr(gw), b, groups, h, w, cin, cout,
-                                               oh, ow, kh, kw, stride, pad, dil, stream_ptr())
+                                               oh, ow, kh, kw, stride, ph, pw, dh, dw, stream_ptr())
     _lib.check(rc, "conv2d_wgrad_bf16")
     return gw
 
