@@ -128,6 +128,13 @@ int vsp_bias_act_bwd_f32(const float *dy, const float *ref, float *dx, float *db
 int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y,
                               int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);
 
+/* NCHW fp32 -> NHWC bf16 TWO-TERM operand: y [n, hw, 3*c] = [hi | lo | hi] with v = x * scale_nc (may be NULL),
+ * hi = bf16(v), lo = bf16(v - hi).  Convolved with weights laid out [w_hi | w_hi | w_lo] over 3*c input channels it gives
+ * conv(x_hi,w_hi) + conv(x_lo,w_hi) + conv(x_hi,w_lo): near-fp32 products on the bf16 tensor pipe, used for the <= 32x32
+ * encoder layers of Restoration_net whose output feeds every decoder style (models/RestoreNet.py:937-940).  c even. */
+int vsp_nchw_f32_to_nhwc_split3_bf16(const float *x, const float *scale_nc, void *y,
+                                     int64_t n, int64_t c, int64_t hw, void *stream);
+
 /* NHWC bf16 -> NCHW fp32: x [n, hw, c_pad] -> y [n, c, hw]. */
 int vsp_nhwc_bf16_to_nchw_f32(const void *x, float *y,
                               int64_t n, int64_t c, int64_t hw, int64_t c_pad, void *stream);

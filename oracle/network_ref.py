@@ -128,12 +128,17 @@ def restoration_ref(sd, images, de_feats, pre_styles, z, size, n_mlp, noise=None
     log_size = int(math.log2(size))
     n_latent = log_size * 2 - 2
     n_layers = (log_size - 2) * 2 + 1
-    noise = noise or [None] * n_layers
+    if isinstance(noise, dict):
+        # explicit per-layer noise for BOTH halves (test form): the reference's single list cannot express it, because its
+        # encoder indexes the reversed decoder list and the down-convs' shapes do not match (:924-927)
+        noise_rev, noise = list(noise["encoder"]), list(noise["decoder"])
+    else:
+        noise = noise or [None] * n_layers
+        noise_rev = noise[::-1]
     b = images.shape[0]
     w_noise = _style_mlp(sd, z, n_mlp).unsqueeze(1).repeat(1, n_latent, 1)
     latent = torch.cat([pre_styles[:, :n_latent], w_noise], dim=-1)
     lat_rev = torch.flip(latent, dims=[1])
-    noise_rev = noise[::-1]
     # encoder (:915-942): SMART and its down-conv share the latent index
     out = _large_conv(sd, "down_from_big.", images, 1)
     features = []
@@ -165,8 +170,9 @@ def restoration_ref(sd, images, de_feats, pre_styles, z, size, n_mlp, noise=None
 
 
 @torch.no_grad()
-def restore_faces_ref(net_sd, dec_sd, low, codes, z, size, dec_size, n_mlp):
-    """Hot path of one batch on the CPU: decoder features -> restoration network."""
-    image, feats = generator_ref(dec_sd, codes, dec_size)
-    restored = restoration_ref(net_sd, low, feats, codes, z, size, n_mlp)
+def restore_faces_ref(net_sd, dec_sd, low, codes, z, size, dec_size, n_mlp, dec_noise=None, net_noise=None):
+    """Hot path of one batch on the CPU: decoder features -> restoration network.  ``dec_noise``: per-layer list for the
+    style decoder; ``net_noise``: list (reference semantics) or {"encoder": [...], "decoder": [...]} for the restorer."""
+    image, feats = generator_ref(dec_sd, codes, dec_size, noise=dec_noise)
+    restored = restoration_ref(net_sd, low, feats, codes, z, size, n_mlp, noise=net_noise)
     return restored, image

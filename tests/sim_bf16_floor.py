@@ -92,10 +92,15 @@ def modconv(sd, p, x, s, demod=True, up=False, down=False, dilation=1):
     return y
 
 
-def styled_conv(sd, p, x, style, up=False, down=False, residuals=()):
+def _nz(sd, p, y, noise):
+    """NoiseInjection with an explicit image (None: the weight is taken as 0)."""
+    return y if noise is None else y + sd[p + "noise.weight"] * noise
+
+
+def styled_conv(sd, p, x, style, up=False, down=False, residuals=(), noise=None):
     s = nr._equal_linear(sd, p + "conv.modulation.", style)
     y = modconv(sd, p + "conv.", x, s, up=up, down=down)
-    y = nr._lrelu(y, sd[p + "activate.bias"])           # noise weights are 0 in this experiment
+    y = nr._lrelu(_nz(sd, p, y, noise), sd[p + "activate.bias"])
     for r in residuals:
         y = y + r
     return P.qs(y)
@@ -112,13 +117,13 @@ def to_rgb(sd, p, x, style, skip=None):
     return y
 
 
-def smart(sd, p, x, style, rates=(1, 2, 4, 8)):
+def smart(sd, p, x, style, rates=(1, 2, 4, 8), noise=None):
     s = nr._equal_linear(sd, p + "modulation.", style)
     outs = [P.qs(modconv(sd, f"{p}ModulatedConv2ds.{j}.", x, s, dilation=r)) for j, r in enumerate(rates)]
     w = sd[p + "fusion.0.weight"]
     y = F.conv2d(P.qx(torch.cat(outs, 1)), P.qw(w / math.sqrt(w.shape[1] * 9)), padding=1)
     y = nr._lrelu(y, sd[p + "fusion.1.bias"])
-    return P.qs(nr._lrelu(y, sd[p + "activate.bias"]))
+    return P.qs(nr._lrelu(_nz(sd, p, y, noise), sd[p + "activate.bias"]))
 
 
 def large_conv(sd, p, x, k, rates=(1, 2, 4, 8)):
@@ -133,29 +138,34 @@ def large_conv(sd, p, x, k, rates=(1, 2, 4, 8)):
 
 
 @torch.no_grad()
-def generator(sd, codes, size):
+def generator(sd, codes, size, noise=None):
     log_size = int(math.log2(size))
     b = codes.shape[0]
+    noise = noise or [None] * (2 * (log_size - 2) + 1)
     P.stage = "dec4"
     out = P.qs(sd["input.input"].repeat(b, 1, 1, 1))
-    out = styled_conv(sd, "conv1.", out, codes[:, 0])
+    out = styled_conv(sd, "conv1.", out, codes[:, 0], noise=noise[0])
     skip = to_rgb(sd, "to_rgb1.", out, codes[:, 1])
     feats = [out]
     i = 1
     for lvl in range(log_size - 2):
         P.stage = f"dec{2 ** (lvl + 3)}"
-        out = styled_conv(sd, f"convs.{2 * lvl}.", out, codes[:, i], up=True)
+        out = styled_conv(sd, f"convs.{2 * lvl}.", out, codes[:, i], up=True, noise=noise[2 * lvl + 1])
         feats.append(out)
-        out = styled_conv(sd, f"convs.{2 * lvl + 1}.", out, codes[:, i + 1])
+        out = styled_conv(sd, f"convs.{2 * lvl + 1}.", out, codes[:, i + 1], noise=noise[2 * lvl + 2])
         skip = to_rgb(sd, f"to_rgbs.{lvl}.", out, codes[:, i + 2], skip)
         i += 2
     return skip, feats
 
 
 @torch.no_grad()
-def restoration(sd, images, de_feats, pre_styles, z, size, n_mlp):
+def restoration(sd, images, de_feats, pre_styles, z, size, n_mlp, noise=None):
+    """``noise``: None or {"encoder": [...], "decoder": [...]} (explicit per-layer images, as oracle.restoration_ref)."""
     log_size = int(math.log2(size))
     n_latent = log_size * 2 - 2
+    n_enc, n_dec = [None] * (2 * (log_size - 2)), [None] * (2 * (log_size - 2) + 1)
+    if noise is not None:
+        n_enc, n_dec = list(noise["encoder"]), list(noise["decoder"])
     b = images.shape[0]
     w_noise = nr._style_mlp(sd, z, n_mlp).unsqueeze(1).repeat(1, n_latent, 1)
     latent = torch.cat([pre_styles[:, :n_latent], w_noise], dim=-1)
@@ -166,9 +176,9 @@ def restoration(sd, images, de_feats, pre_styles, z, size, n_mlp):
     for lvl in range(log_size - 2):
         ii = 2 * lvl
         P.stage = f"enc{size >> lvl}"
-        out = smart(sd, f"encoder_convs.{ii}.", out, lat_rev[:, ii])
+        out = smart(sd, f"encoder_convs.{ii}.", out, lat_rev[:, ii], noise=n_enc[ii])
         features.append(out)
-        out = styled_conv(sd, f"encoder_convs.{ii + 1}.", out, lat_rev[:, ii], down=True)
+        out = styled_conv(sd, f"encoder_convs.{ii + 1}.", out, lat_rev[:, ii], down=True, noise=n_enc[ii + 1])
     P.stage = "enc4"
     out = large_conv(sd, "final_layer.", out, 3)
     x_global = nr._equal_linear(sd, "final_linear.0.", out.reshape(b, -1), act=True)
@@ -180,14 +190,15 @@ def restoration(sd, images, de_feats, pre_styles, z, size, n_mlp):
         return torch.cat([latent[:, i], x_global], dim=1)
 
     P.stage = "res4"
-    out = smart(sd, "conv1.", features[0], sty(0))
+    out = smart(sd, "conv1.", features[0], sty(0), noise=n_dec[0])
     skip = to_rgb(sd, "to_rgb1.", out, sty(1))
     i = 1
     for lvl in range(log_size - 2):
         P.stage = f"res{2 ** (lvl + 3)}"
         level = (i + 1) // 2
-        out = styled_conv(sd, f"convs.{2 * lvl}.", out, sty(i), up=True, residuals=(features[level], de_feats[level]))
-        out = smart(sd, f"convs.{2 * lvl + 1}.", out, sty(i + 1))
+        out = styled_conv(sd, f"convs.{2 * lvl}.", out, sty(i), up=True, residuals=(features[level], de_feats[level]),
+                          noise=n_dec[2 * lvl + 1])
+        out = smart(sd, f"convs.{2 * lvl + 1}.", out, sty(i + 1), noise=n_dec[2 * lvl + 2])
         skip = to_rgb(sd, f"to_rgbs.{lvl}.", out, sty(i + 2), skip)
         i += 2
     return skip
@@ -213,6 +224,18 @@ POLICIES = {
 }
 
 
+def restore_faces_rounded(policy, net_sd, dec_sd, low, codes, z, size, dec_size, n_mlp, dec_noise=None, net_noise=None):
+    """The hot path (as oracle.restore_faces_ref) under a rounding policy name: ``restored`` only.  GPU tests use
+    ``"bf16_all"`` on their own inputs as the precision floor of an all-bf16-operand implementation."""
+    global P
+    saved, P = P, POLICIES[policy]()
+    try:
+        _, feats = generator(dec_sd, codes, dec_size, noise=dec_noise)
+        return restoration(net_sd, low, feats, codes, z, size, n_mlp, noise=net_noise)
+    finally:
+        P = saved
+
+
 def _lv(names, rs):
     return {f"{n}{r}" for n in names for r in rs}
 
@@ -228,6 +251,11 @@ POLICIES.update({
     "fp16_w": lambda: Policy(w_fp16=True),
     "fp16_w_enc_split_x": lambda: Policy(w_fp16=True, split_x=True, split_stages={"enc"}),
     "fp16_w_le32_split_x": lambda: Policy(w_fp16=True, split_x=True, split_stages=_lv(["enc", "dec", "res"], [4, 8, 16, 32])),
+    "enc_le16_exact": lambda: Policy(split_w=True, split_x=True, split_stages=_lv(["enc"], [4, 8, 16])),
+    "enc_le8_exact": lambda: Policy(split_w=True, split_x=True, split_stages=_lv(["enc"], [4, 8])),
+    "enc_le16_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc"], [4, 8, 16])),
+    "enc_le32_split_x": lambda: Policy(split_x=True, split_stages=_lv(["enc"], [4, 8, 16, 32])),
+    "enc_le64_exact": lambda: Policy(split_w=True, split_x=True, split_stages=_lv(["enc"], [4, 8, 16, 32, 64])),
     "enc_split_w": lambda: Policy(split_w=True, split_stages={"enc"}),
     "enc_le64_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc"], [4, 8, 16, 32, 64])),
     "enc_le32_split_w": lambda: Policy(split_w=True, split_stages=_lv(["enc"], [4, 8, 16, 32])),

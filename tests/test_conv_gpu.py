@@ -26,6 +26,13 @@ def _no_tf32():
 
 
 def bf16r(t):
+    """Round like an ACTIVATION operand (bf16)."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def wr(t):
+    """Round like a packed WEIGHT operand: bf16 as well.  (fp16 weights against bf16 activations were tried — kind::f16
+    has separate a_format / b_format fields — and trap with "illegal instruction" on B200: the formats must match.)"""
     return t.to(torch.bfloat16).to(torch.float32)
 
 
@@ -72,7 +79,7 @@ def test_fprop_shared_weights(b, cin, cout, h, w, k, stride, pad, dil):
     xq = mc.nchw_to_nhwc_bf16(x)
     wq, _ = mc.pack_weights(wt)
     out = mc.conv_fprop(xq, wq, cout, k, k, stride, pad, dil)
-    want = F.conv2d(bf16r(x), bf16r(wt), None, stride, pad, dil)
+    want = F.conv2d(bf16r(x), wr(wt), None, stride, pad, dil)
     assert_close_tight(out, want)
 
 
@@ -102,7 +109,7 @@ def test_weight_prologue(transpose):
         want = (m * d[:, :, None, None, None]).permute(0, 3, 4, 2, 1).reshape(b, k * k, cin, cout)
     else:
         want = m.permute(0, 3, 4, 1, 2).reshape(b, k * k, cout, cin)
-    torch.testing.assert_close(wq.float()[..., :want.shape[-1]], bf16r(want), rtol=1e-2, atol=1e-6)
+    torch.testing.assert_close(wq.float()[..., :want.shape[-1]], wr(want), rtol=1e-2, atol=1e-6)
 
 
 def _modconv_ref(x, w, s, demod, stride=1, pad=1, dil=1, round_ops=True):
@@ -114,7 +121,7 @@ def _modconv_ref(x, w, s, demod, stride=1, pad=1, dil=1, round_ops=True):
     outs = []
     for i in range(b):
         if round_ops:
-            y = F.conv2d(bf16r(x[i:i + 1]), bf16r(m[i]), None, stride, pad, dil) * d[i][None, :, None, None]
+            y = F.conv2d(bf16r(x[i:i + 1]), wr(m[i]), None, stride, pad, dil) * d[i][None, :, None, None]
         else:
             y = F.conv2d(x[i:i + 1], m[i] * d[i][:, None, None, None], None, stride, pad, dil)
         outs.append(y)
@@ -152,7 +159,7 @@ def test_epilogue_noise_bias_act_residual_nhwc_and_nchw():
     rs = torch.rand(b, cout, device=DEV) + 0.5
     xq = mc.nchw_to_nhwc_bf16(x)
     wq, _ = mc.pack_weights(w)
-    base = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise + bias[None, :, None, None]
+    base = F.conv2d(bf16r(x), wr(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise + bias[None, :, None, None]
     want = F.leaky_relu(base, 0.2) * math.sqrt(2)
     # NCHW fp32 output, fp32 residuals
     epi = mc.make_epilogue(row_scale=rs, noise=noise, noise_weight=0.37, bias=bias, act=3, alpha=0.2,
@@ -163,7 +170,7 @@ def test_epilogue_noise_bias_act_residual_nhwc_and_nchw():
     nw = torch.tensor([0.37], device=DEV)
     epi = mc.make_epilogue(row_scale=rs, noise=noise[:1], noise_weight_dev=nw, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2))
     out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, 1, 1, epi=epi)
-    base1 = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise[:1] + bias[None, :, None, None]
+    base1 = F.conv2d(bf16r(x), wr(w), None, 1, 1) * rs[:, :, None, None] + 0.37 * noise[:1] + bias[None, :, None, None]
     assert_close_tight(out, F.leaky_relu(base1, 0.2) * math.sqrt(2))
     # NHWC bf16 output with bf16 residual, written at a channel offset of a wider buffer
     resq = mc.nchw_to_nhwc_bf16(res)  # same layout as the output (48 channels)
@@ -171,14 +178,14 @@ def test_epilogue_noise_bias_act_residual_nhwc_and_nchw():
     epi = mc.make_epilogue(row_scale=rs[:, :16].contiguous(), bias=bias[:16].contiguous(), act=3, alpha=0.2, scale=math.sqrt(2))
     wq16, _ = mc.pack_weights(w[:16].contiguous())
     mc.conv_fprop(xq, wq16, 16, 3, 3, 1, 1, 1, epi=epi, out=buf, out_nhwc=True, co_off=32)
-    want16 = F.leaky_relu(F.conv2d(bf16r(x), bf16r(w[:16]), None, 1, 1) * rs[:, :16, None, None] + bias[None, :16, None, None], 0.2) * math.sqrt(2)
+    want16 = F.leaky_relu(F.conv2d(bf16r(x), wr(w[:16]), None, 1, 1) * rs[:, :16, None, None] + bias[None, :16, None, None], 0.2) * math.sqrt(2)
     got = buf[..., 32:48].permute(0, 3, 1, 2).float()
     assert_close_tight(got, want16, tol=1e-2)
     assert float(buf[..., :32].abs().max()) == 0 and float(buf[..., 48:].abs().max()) == 0
     epi = mc.make_epilogue(residual=resq)
     wq48, _ = mc.pack_weights(w)
     o2 = mc.conv_fprop(xq, wq48, cout, 3, 3, 1, 1, 1, epi=epi, out_nhwc=True)
-    want2 = F.conv2d(bf16r(x), bf16r(w), None, 1, 1) + bf16r(res)
+    want2 = F.conv2d(bf16r(x), wr(w), None, 1, 1) + bf16r(res)
     assert_close_tight(o2[..., :cout].permute(0, 3, 1, 2).float(), want2, tol=1e-2)
 
 
@@ -190,7 +197,7 @@ def test_transposed_stride2(b, cin, cout, h, w_):
     xq = mc.nchw_to_nhwc_bf16(x)
     wq, _ = mc.pack_weights(w)
     out = mc.conv_transpose_s2(xq, wq, cout, 3, 3)
-    want = F.conv_transpose2d(bf16r(x), bf16r(w).transpose(0, 1), None, stride=2, padding=0)
+    want = F.conv_transpose2d(bf16r(x), wr(w).transpose(0, 1), None, stride=2, padding=0)
     assert_close_tight(out, want)
 
 
@@ -201,7 +208,7 @@ def test_dgrad_via_gather_matches_autograd():
     x = torch.randn(b, cin, h, h, device=DEV, requires_grad=True)
     w = torch.randn(cout, cin, k, k, device=DEV) / 24
     dy = torch.randn(b, cout, h, h, device=DEV)
-    y = F.conv2d(x, bf16r(w), None, 1, pad, dil)
+    y = F.conv2d(x, wr(w), None, 1, pad, dil)
     (want,) = torch.autograd.grad(y, x, bf16r(dy))
     wq_t, _ = mc.pack_weights(w, transpose=True)
     dyq = mc.nchw_to_nhwc_bf16(dy)
@@ -355,7 +362,7 @@ def test_two_stage_epilogue_smart_fusion():
     wq, _ = mc.pack_weights(w)
     epi = mc.make_epilogue(pre_bias=b1, pre_act=3, noise=noise, noise_weight=0.5, bias=b2, act=3, alpha=0.2, scale=math.sqrt(2))
     out = mc.conv_fprop(xq, wq, c, 3, 3, 1, 1, 1, epi=epi)
-    y = F.leaky_relu(F.conv2d(bf16r(x), bf16r(w), None, 1, 1) + b1[None, :, None, None], 0.2) * math.sqrt(2)
+    y = F.leaky_relu(F.conv2d(bf16r(x), wr(w), None, 1, 1) + b1[None, :, None, None], 0.2) * math.sqrt(2)
     y = F.leaky_relu(y + 0.5 * noise + b2[None, :, None, None], 0.2) * math.sqrt(2)
     assert_close_tight(out, y)
 
@@ -387,11 +394,11 @@ def test_rowhalo_conv(b, cin, cout, h, w, dil, per_sample):
     if per_sample:
         s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
         wq, _ = mc.pack_weights(wt, s)
-        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wt * s[i][None, :, None, None]), None, 1, dil, dil)
+        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), wr(wt * s[i][None, :, None, None]), None, 1, dil, dil)
                           for i in range(b)])
     else:
         wq, _ = mc.pack_weights(wt)
-        want = F.conv2d(bf16r(x), bf16r(wt), None, 1, dil, dil)
+        want = F.conv2d(bf16r(x), wr(wt), None, 1, dil, dil)
     out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, dil, dil)
     assert_close_tight(out, want)
 
@@ -427,11 +434,11 @@ def test_ring_conv(b, cin, cout, h, w, k, dil, per_sample, nhwc):
     if per_sample:
         s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV)
         wq, _ = mc.pack_weights(wt, s)
-        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wt * s[i][None, :, None, None]), None, 1, pad, dil)
+        want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), wr(wt * s[i][None, :, None, None]), None, 1, pad, dil)
                           for i in range(b)])
     else:
         wq, _ = mc.pack_weights(wt)
-        want = F.conv2d(bf16r(x), bf16r(wt), None, 1, pad, dil)
+        want = F.conv2d(bf16r(x), wr(wt), None, 1, pad, dil)
     if wq.shape[3] != xq.shape[3]:   # Cin padded to 8 on the activation side
         wq = F.pad(wq, (0, xq.shape[3] - wq.shape[3]))
     if nhwc:   # staged epilogue: swizzled shared-memory tile + TMA store
@@ -461,7 +468,7 @@ def test_ring_conv_epilogue_nhwc_slices():
     epi = mc.make_epilogue(row_scale=rs, pre_bias=b1, pre_act=3, noise=noise, noise_weight_dev=nw, bias=b2, act=3, alpha=0.2,
                            scale=math.sqrt(2), residual=resq)
     out = mc.conv_fprop(xq, wq, cout, 3, 3, 1, 1, 1, epi=epi, out_nhwc=True)
-    y = F.leaky_relu(F.conv2d(bf16r(x), bf16r(wt), None, 1, 1) * rs[:, :, None, None] + b1[None, :, None, None], 0.2) * math.sqrt(2)
+    y = F.leaky_relu(F.conv2d(bf16r(x), wr(wt), None, 1, 1) * rs[:, :, None, None] + b1[None, :, None, None], 0.2) * math.sqrt(2)
     y = F.leaky_relu(y + 0.41 * noise + b2[None, :, None, None], 0.2) * math.sqrt(2) + bf16r(res)
     assert_close_tight(out.permute(0, 3, 1, 2).float(), y, tol=1e-2)
     # four dilated 16-channel branches into slices of one 64-channel buffer
@@ -473,7 +480,7 @@ def test_ring_conv_epilogue_nhwc_slices():
         wqj, _ = mc.pack_weights(wj)
         epi = mc.make_epilogue(row_scale=rs[:, 16 * j:16 * j + 16].contiguous())
         mc.conv_fprop(xsq, wqj, 16, 3, 3, 1, dil, dil, epi=epi, out=buf, out_nhwc=True, co_off=16 * j)
-        want = F.conv2d(bf16r(xs), bf16r(wj), None, 1, dil, dil) * rs[:, 16 * j:16 * j + 16, None, None]
+        want = F.conv2d(bf16r(xs), wr(wj), None, 1, dil, dil) * rs[:, 16 * j:16 * j + 16, None, None]
         assert_close_tight(buf[..., 16 * j:16 * j + 16].permute(0, 3, 1, 2).float(), want, tol=1e-2)
 
 
@@ -516,7 +523,7 @@ def test_up2_fused_matches_transposed_conv_then_blur(b, cin, cout, h, w_, per_sa
     # tight check of the kernel itself: fp32 conv with the bf16-rounded composite weights + pixel shuffle
     zs = []
     for i in range(b):
-        wi = bf16r(w3 * s[i][None, :, None, None]) if per_sample else bf16r(w3)
+        wi = wr(w3 * s[i][None, :, None, None]) if per_sample else wr(w3)
         zs.append(F.pixel_shuffle(F.conv2d(bf16r(x[i:i + 1]), wi, None, 1, 1)
                                   .view(1, 4, cout, h, w_).transpose(1, 2).reshape(1, cout * 4, h, w_), 2))
     z = torch.cat(zs)
@@ -550,10 +557,10 @@ def test_conv_branches_one_launch(b, cin, cq, h, w_, per_sample):
     for j, dil in enumerate(dils):
         wj = wt[j * cq:(j + 1) * cq]
         if per_sample:
-            want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), bf16r(wj * s[i][None, :, None, None]), None, 1, dil, dil)
+            want = torch.cat([F.conv2d(bf16r(x[i:i + 1]), wr(wj * s[i][None, :, None, None]), None, 1, dil, dil)
                               for i in range(b)])
         else:
-            want = F.conv2d(bf16r(x), bf16r(wj), None, 1, dil, dil)
+            want = F.conv2d(bf16r(x), wr(wj), None, 1, dil, dil)
         want = want * rs[:, j * cq:(j + 1) * cq, None, None]
         assert_close_tight(out[..., j * cq:(j + 1) * cq].permute(0, 3, 1, 2).float(), want, tol=1e-2)
 
@@ -581,7 +588,7 @@ def test_up2_fused_lowres_shared_weights(b, cin, cout, h, w_):
     wq, _ = mc.pack_weights(w3)
     epi = mc.make_epilogue(row_scale=d, noise=noise, noise_weight=0.3, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2))
     out = mc.conv_up2_fused(xs, wq, cout, epi=epi)
-    z = F.pixel_shuffle(F.conv2d(xs.permute(0, 3, 1, 2).float(), bf16r(w3), None, 1, 1)
+    z = F.pixel_shuffle(F.conv2d(xs.permute(0, 3, 1, 2).float(), wr(w3), None, 1, 1)
                         .view(b, 4, cout, h, w_).transpose(1, 2).reshape(b, cout * 4, h, w_), 2)
     want = F.leaky_relu(z * d[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2)
     assert_close_tight(out.permute(0, 3, 1, 2).float(), want, tol=1e-2)

@@ -289,15 +289,142 @@ def test_full_size_hot_path_matches_cpu_oracle():
     got, got_img = fp.restore_faces(net, dec, low.to(DEV), codes.to(DEV), [z.to(DEV)])
     want_img = torch.nn.functional.adaptive_avg_pool2d(want_img, (512, 512)) if want_img.shape[-1] != 512 else want_img
     check_bf16(got_img.cpu(), want_img, "decoder image @512 (pooled)")
-    # The restorer output goes through ~45 bf16 layers of a RANDOM-INIT network (dynamic range ~700, i.e. the network
-    # amplifies): its max-abs error is a chaotic function of rounding order — measured 1.05e-2 .. 2.0e-2 of the range
-    # (PSNR 50.2 .. 53.5 dB) across permutations of the kernel paths (tests/dbg_fullsize.py with VSP_NO_* flags), with
-    # no spatial structure.  PSNR is the robust criterion here; max-abs is bounded at 3e-2 of the range.
-    got, want = got.cpu(), want
+    # north_star bound on the restorer output as well.  An all-bf16 pipeline cannot meet it on this random-init (amplifying,
+    # dynamic range ~700) network: the CPU oracle with bf16-rounded operands and stores (tests/sim_bf16_floor.py) sits at
+    # 1.4e-2 for this seed, and half of that comes from the encoder's <= 32x32 layers, whose error reaches every decoder
+    # modulation through x_global.  Those layers run with two-term (hi + lo) operands (fastpath.smart_layer_split):
+    # measured 0.77e-2 of the range / 57.7 dB here, 1.06e-2 / 55.6 dB when only the <= 16x16 ones do, 1.5e-2 / 51.5 dB
+    # with VSP_NO_SPLIT_LOWRES=1.
+    check_bf16(got.cpu(), want, "restored @512")
+
+
+def _explicit_noise(net, dec, batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    dsh, nsh = fp.noise_shapes(net, dec, batch)
+    return ([torch.randn(sh, generator=g) for sh in dsh],
+            {k: [torch.randn(sh, generator=g) for sh in v] for k, v in nsh.items()})
+
+
+def _set_noise_weights(mods, value):
+    with torch.no_grad():
+        for m in mods:
+            for name, p in m.named_parameters():
+                if name.endswith("noise.weight"):
+                    p.fill_(value)
+
+
+def test_bench_configuration_matches_cpu_oracle():
+    """The configuration bench.py times — micro-batch 32, one CUDA-graph replay pair per micro-batch
+    (fastpath.GraphedRestorer), every NoiseInjection weight 0.05 — against the fp32 CPU oracle, with EXPLICIT noise images
+    fed to both sides (the graph's static noise buffers; the oracle's per-layer lists).  Samples 0, 13 and 31 of the
+    micro-batch are checked (images are independent; the oracle needs ~2 s per image).
+
+    Tolerance: north_star's (max-abs <= 1e-2 of the range, PSNR > 45 dB) wherever a bf16-operand implementation CAN meet
+    it.  On this seed it cannot: the CPU oracle re-run with every conv operand and activation store rounded to bf16 and
+    fp32 accumulation (tests/sim_bf16_floor.py, policy "bf16_all" — the floor of ANY all-bf16 pipeline, computed below on
+    the same inputs) is itself at 2.6e-2 / 46 dB; making the whole encoder exact in that experiment still leaves 1.1e-2.
+    The fused pipeline must beat that floor (it measures 1.8e-2: the two-term low-resolution encoder layers) and keep the
+    PSNR bound."""
+    import oracle
+    import sim_bf16_floor as sim
+    torch.manual_seed(0)
+    net = Restoration_net(512, 512, 8, channel_multiplier=2).eval()
+    dec = Generator(1024, 512, 8, channel_multiplier=2).eval()
+    _set_noise_weights((net, dec), 0.05)
+    micro, pick = 32, [0, 13, 31]
+    g = torch.Generator().manual_seed(101)
+    low = torch.rand(micro, 3, 512, 512, generator=g) * 2 - 1
+    codes = torch.randn(micro, 18, 512, generator=g)
+    z = torch.randn(micro, 512, generator=g)
+    dec_noise, net_noise = _explicit_noise(net, dec, micro, 102)
+    sel = lambda t: t[pick]
+    with torch.no_grad():
+        want, want_img = oracle.restore_faces_ref(
+            net.state_dict(), dec.state_dict(), sel(low), sel(codes), sel(z), 512, 1024, 8,
+            dec_noise=[sel(t) for t in dec_noise], net_noise={k: [sel(t) for t in v] for k, v in net_noise.items()})
+    net, dec = net.to(DEV), dec.to(DEV)
+    graphed = fp.GraphedRestorer(net, dec, micro, device=DEV, explicit_noise=True)
+    graphed.set_noise(dec_noise, net_noise)
+    got, got_img = graphed(low.to(DEV), codes.to(DEV), z.to(DEV))
+    want_img = torch.nn.functional.avg_pool2d(want_img, 2)
+    check_bf16(got_img[pick].cpu(), want_img, "decoder image @512 (pooled), micro-batch 32, graph, noise 0.05")
+    cpu_sd = lambda m: {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        floor = sim.restore_faces_rounded(
+            "bf16_all", cpu_sd(net), cpu_sd(dec), sel(low), sel(codes), sel(z), 512, 1024, 8,
+            dec_noise=[sel(t) for t in dec_noise], net_noise={k: [sel(t) for t in v] for k, v in net_noise.items()})
     peak = float(want.max() - want.min())
-    err = float((got - want).abs().max())
-    assert psnr(got, want) > 45.0, f"restored @512: psnr {psnr(got, want)}"
-    assert err <= 3e-2 * peak, f"restored @512: max-abs {err} > 3e-2 * {peak}"
+    floor_err = float((floor - want).abs().max()) / peak
+    err = float((got[pick].cpu() - want).abs().max()) / peak
+    print(f"bench configuration: max-abs {err:.3e} of range, all-bf16 floor {floor_err:.3e}, psnr {psnr(got[pick].cpu(), want):.1f} dB")
+    assert err <= max(1e-2, floor_err), f"restored @512, micro-batch 32, graph, noise 0.05: {err} vs floor {floor_err}"
+    assert psnr(got[pick].cpu(), want) > 45.0
+    # the noise path is live: the same replay with other noise images gives another result
+    dec_noise2, net_noise2 = _explicit_noise(net, dec, micro, 103)
+    graphed.set_noise(dec_noise2, net_noise2)
+    got2, _ = graphed(low.to(DEV), codes.to(DEV), z.to(DEV))
+    assert float((got2 - got).abs().max()) > 1e-3 * float(want.max() - want.min())
+
+
+def _shard_worker(rank, world, port, q):
+    """One rank of the 2-process shard-equality test: both processes share cuda:0 (the test box has one GPU); rendezvous
+    and the gather of the result run over gloo — the hot path itself has no collective."""
+    import os as _os
+    import torch.distributed as dist
+    from vspbfr_b200 import sharding
+    _os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net, dec = _build_nets()
+        low, codes, z = _shard_job()
+        lo, hi = sharding.shard_range(low.shape[0], rank, world)
+        out = torch.empty(hi - lo, *low.shape[1:]).pin_memory()
+        sharding.restore_from_host(net, dec, low[lo:hi].pin_memory(), codes[lo:hi].pin_memory(), z[lo:hi].pin_memory(), out,
+                                   micro=2, device=DEV)
+        torch.cuda.synchronize()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lo, hi, out.numpy()))
+        if rank == 0:
+            q.put(gathered)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _shard_job():
+    g = torch.Generator().manual_seed(77)
+    n, size = 8, int(NET["size"])
+    return (torch.rand(n, 3, size, size, generator=g) * 2 - 1, torch.randn(n, 18, 512, generator=g),
+            torch.randn(n, 512, generator=g))
+
+
+def test_two_rank_shards_concatenate_to_the_single_rank_result():
+    """Batch-shard equality (SURVEY §8 e): two processes restoring rows [0,4) and [4,8) of a job return, concatenated, the
+    bits one process returns for the whole job (same micro-batch size; noise weights 0 -> deterministic)."""
+    import socket
+    import torch.multiprocessing as mp
+    from vspbfr_b200 import sharding
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    gathered = q.get(timeout=600)
+    for p_ in procs:
+        p_.join(timeout=120)
+        assert p_.exitcode == 0
+    net, dec = _build_nets()
+    low, codes, z = _shard_job()
+    want = torch.empty_like(low).pin_memory()
+    sharding.restore_from_host(net, dec, low.pin_memory(), codes.pin_memory(), z.pin_memory(), want, micro=2, device=DEV)
+    torch.cuda.synchronize()
+    assert [(lo, hi) for lo, hi, _ in gathered] == [(0, 4), (4, 8)]
+    got = np.concatenate([part for _, _, part in gathered], 0)
+    np.testing.assert_array_equal(got, want.numpy())
 
 
 @pytest.mark.parametrize("c,h", [(32, 64), (64, 32), (8, 20), (16, 24), (128, 12), (32, 130)])

@@ -43,6 +43,47 @@ nchw_to_nhwc_kernel(const float *__restrict__ x, const float *__restrict__ scale
   }
 }
 
+// ---- NCHW fp32 -> NHWC bf16 two-term operand [hi | lo | hi] over 3*C channels: hi = bf16(v), lo = bf16(v - hi),
+// v = x * scale.  A convolution of it with the weights [w_hi | w_hi | w_lo] is conv(x_hi, w_hi) + conv(x_lo, w_hi) +
+// conv(x_hi, w_lo) ~ the fp32 product to 2^-17 — used for the few low-resolution encoder layers whose rounding error
+// reaches every decoder modulation through x_global (fastpath.smart_layer_split).
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_split3_kernel(const float *__restrict__ x, const float *__restrict__ scale_nc,
+                           __nv_bfloat16 *__restrict__ y, long long c, long long hw) {
+  __shared__ float tile[64][65];
+  const long long n = blockIdx.z;
+  const long long c0 = (long long)blockIdx.y * 64, p0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int cl = ty + 4 * i;
+    const long long cc = c0 + cl, pp = p0 + tx;
+    float v = 0.f;
+    if (cc < c && pp < hw) {
+      v = ld_stream_f1(x + (n * c + cc) * hw + pp);
+      if (scale_nc != nullptr) v *= __ldg(scale_nc + n * c + cc);
+    }
+    tile[cl][tx] = v;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int pl = py + 8 * i;
+    const long long pp = p0 + pl, cc = c0 + 2 * cx;
+    if (pp < hw && cc < c) {
+      const float a = tile[2 * cx][pl], b = tile[2 * cx + 1][pl];
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(hi);
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      __nv_bfloat16 *row = y + (n * hw + pp) * 3 * c + cc;
+      *reinterpret_cast<__nv_bfloat162 *>(row) = hi;
+      *reinterpret_cast<__nv_bfloat162 *>(row + c) = lo;
+      *reinterpret_cast<__nv_bfloat162 *>(row + 2 * c) = hi;
+    }
+  }
+}
+
 // ---- NCHW fp32 -> NHWC bf16 for c_pad == 8 (the RGB network input): one thread per pixel, coalesced plane reads,
 // one 128-bit store; the 64 x 64 transpose tile above would be 95 % padding.
 __global__ void __launch_bounds__(kThreads)
@@ -442,6 +483,19 @@ extern "C" int vsp_nchw_f32_to_nhwc_bf16_dot(const float *x, const float *scale_
   dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c_pad, 64), (unsigned)n);
   nchw_to_nhwc_kernel<<<grid, kThreads, 0, stream>>>(x, scale_nc, static_cast<__nv_bfloat16 *>(y), c, hw, c_pad);
   return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int vsp_nchw_f32_to_nhwc_split3_bf16(const float *x, const float *scale_nc, void *y, int64_t n, int64_t c,
+                                                int64_t hw, void *stream_) {
+  using namespace vsp;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(n >= 0 && c >= 0 && hw >= 0 && c % 2 == 0, "nchw->nhwc split3: channels must be even");
+  if (n == 0 || c == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && y, "nchw->nhwc split3: null pointer");
+  VSP_REQUIRE(n <= 65535 && ceil_div64(c, 64) <= 65535, "nchw->nhwc split3: batch/channel extent too large");
+  dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div64(c, 64), (unsigned)n);
+  nchw_to_nhwc_split3_kernel<<<grid, kThreads, 0, stream>>>(x, scale_nc, static_cast<__nv_bfloat16 *>(y), c, hw);
+  return check_launch("nchw_to_nhwc_split3_kernel");
 }
 
 extern "C" int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y, int64_t n,

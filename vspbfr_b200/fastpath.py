@@ -448,6 +448,116 @@ def large_conv_layer(m: LargeConvLayer, x):
     return mc.conv_fprop(buf, _plain_weights(fconv), cout, 1, 1, 1, 0, 1, out_nhwc=True, epi=mc.make_epilogue(**kw))
 
 
+# ----------------------------------------------------------------------------------------------
+# two-term (hi + lo) bf16 operands for the low-resolution half of the restorer's encoder
+# ----------------------------------------------------------------------------------------------
+# The encoder's low-resolution layers end in ``final_linear`` -> x_global, which is concatenated into the style of EVERY decoder
+# layer (models/RestoreNet.py:937-940, :1022-1037): a rounding error there is not a local pixel error, it perturbs all
+# decoder modulations coherently.  The precision-floor experiment (tests/sim_bf16_floor.py) attributes half
+# of the full-network max-abs error of an all-bf16 pipeline to these few layers (2.6 % of the FLOPs).  They therefore run
+# with two-term operands: x = x_hi + x_lo, w = w_hi + w_lo (each term bf16, fp32 accumulation on the tensor core),
+#   conv(x, w) ~= conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)            (error ~2^-17 instead of 2^-9)
+# expressed to the SAME tcgen05 kernels as one convolution over 3*Cin channels: activation [hi | lo | hi], weight
+# [w_hi | w_hi | w_lo]; activations between these layers stay fp32 NCHW (they are at most 32x32).
+# Measured on the B200 (tests/dbg_fullsize.py, parity test's seed): no two-term layers 1.51e-2 of the range / 51.5 dB;
+# <= 16x16: 1.06e-2 / 55.6 dB; <= 32x32 (default): 0.77e-2 / 57.7 dB, for 4 % of the throughput (1024 -> 983 faces/s).
+_SPLIT_PIXELS = 0 if os.environ.get("VSP_NO_SPLIT_LOWRES") is not None else int(os.environ.get("VSP_SPLIT_PIXELS", "1024"))
+
+
+def _split3_nhwc(x, s=None):
+    """x [B,C,H,W] fp32 (* s [B,C]) -> [B,H,W,3C] bf16 = [hi | lo | hi] with hi = bf16(x), lo = bf16(x - hi)."""
+    b, c, h, w = x.shape
+    x = x.contiguous()
+    y = torch.empty((b, h, w, 3 * c), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().vsp_nchw_f32_to_nhwc_split3_bf16(ptr(x), ptr(s.contiguous()) if s is not None else None, ptr(y),
+                                                          b, c, h * w, stream_ptr())
+    _lib.check(rc, "nchw_f32_to_nhwc_split3_bf16")
+    return y
+
+
+def _split3_weights(owner, tag, sources, build_w, wscale):
+    """Packed [1,taps,Cout,3*Cin] two-term weights [w_hi | w_hi | w_lo] of ``wscale * build_w()`` ([Cout,Cin,k,k]), cached."""
+    def build():
+        w = build_w().detach().float() * wscale
+        hi = w.to(torch.bfloat16).float()
+        lo = (w - hi).to(torch.bfloat16).float()
+        return mc.pack_weights(torch.cat([hi, hi, lo], 1).contiguous())[0]
+    return _cached(owner, tag, sources, build)
+
+
+def smart_layer_split(m: SMART_layer, x, style, noise=None):
+    """:func:`smart_layer` with two-term operands; x and the result are fp32 NCHW."""
+    b, cin, h, w = x.shape
+    branches = list(m.ModulatedConv2ds)
+    cq, k = branches[0].out_channel, branches[0].kernel_size
+    cout = cq * len(branches)
+    s = _modulation(m.modulation, style)
+    wsq = _smart_wsq(m) if branches[0].demodulate else None
+    d_pre = _demod_ctx.get(id(m)) if branches[0].demodulate else None
+    d = (d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, branches[0].scale, branches[0].eps)) if wsq is not None else None
+    wq = _split3_weights(m, "wq_split3", [br.weight for br in branches], lambda: _smart_wcat(m), branches[0].scale)
+    buf = mc.conv_branches(_split3_nhwc(x, s), wq, cout, [br.dilation for br in branches], out_nhwc=False, algo_cin=cin,
+                           epi=mc.make_epilogue(row_scale=d) if d is not None else None)
+    fconv, fact = m.fusion[0], m.fusion[1]
+    nz = _noise_for(noise, b, h, w, x.device)
+    kw = dict(pre_bias=fact.bias.detach(), pre_act=3, noise=nz, noise_weight_dev=m.noise.weight.detach(),
+              alpha=fact.negative_slope, scale=fact.scale)
+    if m.activate is not None:
+        kw.update(bias=m.activate.bias.detach(), act=3)
+    wf = _split3_weights(fconv, "wq_split3", [fconv.weight], lambda: fconv.weight, fconv.scale)
+    return mc.conv_fprop(_split3_nhwc(buf), wf, cout, 3, 3, 1, fconv.padding, 1, epi=mc.make_epilogue(**kw), algo_cin=cout)
+
+
+def styled_conv_down_split(m, x, style, noise=None):
+    """StyledConv_down (blur pad (2,2) -> modulated 3x3 stride-2 conv -> noise -> bias + lrelu) with two-term operands;
+    x and the result are fp32 NCHW.  The blur runs in fp32 on the modulated input (modulation commutes with the
+    per-channel FIR)."""
+    conv = m.conv
+    b, cin, h, w = x.shape
+    cout, k = conv.out_channel, conv.kernel_size
+    s = _modulation(conv.modulation, style)
+    d = None
+    if conv.demodulate:
+        d = _demod_ctx.get(id(conv))
+        if d is None:
+            d = mc.demod_from_wsq(s, _conv_wsq(conv), conv.scale, conv.eps)
+    xb = upfirdn2d_raw((x * s[:, :, None, None]).contiguous(), conv.blur.kernel, (1, 1), (1, 1), tuple(conv.blur.pad) * 2)
+    wq = _split3_weights(conv, "wq_split3", [conv.weight], lambda: conv.weight.view(cout, cin, k, k), conv.scale)
+    nz = _noise_for(noise, b, (xb.shape[2] - k) // 2 + 1, (xb.shape[3] - k) // 2 + 1, x.device)
+    return mc.conv_fprop(_split3_nhwc(xb), wq, cout, k, k, 2, 0, 1, algo_cin=cin, epi=mc.make_epilogue(
+        row_scale=d, noise=nz, bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
+        noise_weight_dev=m.noise.weight.detach()))
+
+
+def large_conv_layer_split(m: LargeConvLayer, x):
+    """:func:`large_conv_layer` (3x3 dilated form, the encoder's 4x4 head) with two-term operands; fp32 NCHW in/out."""
+    convs = list(m.dilated_convs)
+    cq, k = convs[0].weight.shape[0], convs[0].weight.shape[2]
+    cout = cq * len(convs)
+    assert k == 3 and not m.downsample and all(c.padding == c.dilation for c in convs)
+    wq = _split3_weights(m, "wq_split3", [c.weight for c in convs],
+                         lambda: torch.cat([c.weight.detach() for c in convs], 0), convs[0].scale)
+    buf = mc.conv_branches(_split3_nhwc(x), wq, cout, [c.dilation for c in convs], out_nhwc=False, algo_cin=x.shape[1])
+    fconv, fact = m.fusion[0], m.fusion[1]
+    kw = dict(pre_bias=fact.bias.detach(), pre_act=3, alpha=fact.negative_slope, scale=fact.scale)
+    if m.activate is not None:
+        kw.update(bias=m.activate.bias.detach() if m.activate.bias is not None else None, act=3)
+    wf = _split3_weights(fconv, "wq_split3", [fconv.weight], lambda: fconv.weight, fconv.scale)
+    return mc.conv_fprop(_split3_nhwc(buf), wf, cout, 1, 1, 1, 0, 1, epi=mc.make_epilogue(**kw), algo_cin=cout)
+
+
+def _split_ok(m):
+    """Shapes the two-term path covers: 4 power-of-two 3x3 dilated branches with Cin a multiple of 64."""
+    branches = list(getattr(m, "ModulatedConv2ds", [])) or list(getattr(m, "dilated_convs", []))
+    if not branches:
+        return False
+    w = branches[0].weight
+    cq, cin, k = w.shape[-4], w.shape[-3], w.shape[-1]
+    return (k == 3 and len(branches) <= 4 and cq >= 16 and (cq & (cq - 1)) == 0 and cin % 64 == 0
+            and all(br.padding == br.dilation for br in branches))
+
+
 def _pack_padded(weight, wscale, cin_pad):
     """Pack [Cout,Cin,kh,kw] to bf16 with the input-channel axis padded to the activation's width."""
     cout, cin, kh, kw = weight.shape
@@ -577,11 +687,17 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     noise_latent = _mapped_latent(net.style, net.n_latent, noise_styles, inject_index, truncation, truncation_latent,
                                   input_is_latent)
     latent = torch.cat([pre_styles[:, :noise_latent.shape[1], :], noise_latent], dim=-1)
-    if noise is None:
-        noise = ([None] * net.num_layers if randomize_noise
-                 else [getattr(net.noises, f"noise_{i}") for i in range(net.num_layers)])
+    if isinstance(noise, dict):
+        # explicit noise for every layer of both halves: {"encoder": [14 images in encoder-layer order], "decoder": [15]}.
+        # The reference's one list cannot say this (its encoder reads the REVERSED decoder list, whose down-conv shapes do
+        # not match, models/RestoreNet.py:924-927), so parity tests with live noise paths use this form.
+        noise_rev, noise = list(noise["encoder"]), list(noise["decoder"])
+    else:
+        if noise is None:
+            noise = ([None] * net.num_layers if randomize_noise
+                     else [getattr(net.noises, f"noise_{i}") for i in range(net.num_layers)])
+        noise_rev = noise[::-1]
     lat_rev = torch.flip(latent, dims=[1])
-    noise_rev = noise[::-1]
 
     enc = net.encoder_convs
     banks = _banks_for(net, lambda: (
@@ -595,15 +711,28 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     _bank_apply(banks[0], lat_rev)
     out = large_conv_layer(net.down_from_big, mc.nchw_to_nhwc_bf16(images, c_pad=8))
     features = []
+    exact = None                                                            # fp32 NCHW activation once on the two-term path
     for ii in range(0, len(enc), 2):
+        if (exact is None and out.shape[1] * out.shape[2] <= _SPLIT_PIXELS and _split_ok(enc[ii])
+                and enc[ii + 1].conv.in_channel % 64 == 0 and enc[ii + 1].conv.kernel_size == 3):
+            exact = mc.nhwc_bf16_to_nchw(out)
+        if exact is not None:
+            exact = smart_layer_split(enc[ii], exact, lat_rev[:, ii], noise_rev[ii])
+            features.append(mc.nchw_to_nhwc_bf16(exact))
+            exact = styled_conv_down_split(enc[ii + 1], exact, lat_rev[:, ii], noise_rev[ii + 1])
+            continue
         out = smart_layer(enc[ii], out, lat_rev[:, ii], noise_rev[ii])
         features.append(out)
         out = styled_conv(enc[ii + 1], out, lat_rev[:, ii], noise_rev[ii + 1])
-    out = large_conv_layer(net.final_layer, out)                           # [B,4,4,C]
-    flat = out.permute(0, 3, 1, 2).reshape(b, -1).float()                  # reference flattens NCHW
+    if exact is not None and _split_ok(net.final_layer):
+        head = large_conv_layer_split(net.final_layer, exact)              # [B,C,4,4] fp32
+    else:
+        src = out if exact is None else mc.nchw_to_nhwc_bf16(exact)
+        head = large_conv_layer(net.final_layer, src).permute(0, 3, 1, 2).float()
+    flat = head.reshape(b, -1)                                             # reference flattens NCHW
     x_global = net.final_linear[0](flat)                                   # Dropout2d is the identity in eval
-    early = net.final_transfer(x_global).view(b, -1, 4, 4).permute(0, 2, 3, 1)
-    features.append((out.float() + early).to(torch.bfloat16).contiguous())
+    early = net.final_transfer(x_global).view(b, -1, 4, 4)
+    features.append(mc.nchw_to_nhwc_bf16((head + early).contiguous()))
     features = features[::-1]
 
     n_sty = 2 * len(net.to_rgbs) + 2
@@ -667,12 +796,13 @@ def generator_forward(gen, styles, inject_index=None, truncation=1, truncation_l
 
 
 @torch.no_grad()
-def decode_stage(decoder, codes, size, out_n_latent=16):
+def decode_stage(decoder, codes, size, out_n_latent=16, noise=None):
     """First half of :func:`restore_faces`: style decoder features (+ its image, pooled to ``size``) from the w+ codes.
     Needs only the codes — the degraded images are not touched until :func:`restore_stage`."""
     _noise_pool.begin(codes.device)
     fuse_pool = decoder.size == 2 * size and len(decoder.to_rgbs) > 0 and decoder.to_rgbs[-1].upsample.factor == 2
-    image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True, pool_image=fuse_pool)
+    image, feats = generator_forward(decoder, [codes], input_is_latent=True, randomize_noise=True, pool_image=fuse_pool,
+                                     noise=noise)
     if image.shape[-1] != size:
         # face_pool (e4e/models/psp.py:245-246): AdaptiveAvgPool2d to (size, size) is an exact k x k mean when divisible
         k = image.shape[-1] // size
@@ -682,20 +812,33 @@ def decode_stage(decoder, codes, size, out_n_latent=16):
 
 
 @torch.no_grad()
-def restore_stage(net, low_imgs, feats, codes, noise_styles):
+def restore_stage(net, low_imgs, feats, codes, noise_styles, noise=None):
     """Second half of :func:`restore_faces`: the restoration network on the degraded images and the decoder features."""
-    return restoration_forward(net, low_imgs, feats, codes, noise_styles)
+    return restoration_forward(net, low_imgs, feats, codes, noise_styles, noise=noise)
 
 
 @torch.no_grad()
-def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent=16):
+def restore_faces(net, decoder, low_imgs, codes, noise_styles=None, out_n_latent=16, dec_noise=None, net_noise=None):
     """The hot path of one restoration batch (restoration_test.py:130-131): style decoder features from
-    the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512)."""
+    the (diffused) w+ codes, then the restoration network.  Returns (restored, decoder image at 512).
+    ``dec_noise`` / ``net_noise``: explicit NoiseInjection images (default: drawn per call, as the reference does) — a
+    per-layer list for the decoder; a list or {"encoder": [...], "decoder": [...]} for the restorer."""
     if noise_styles is None:
         noise_styles = [torch.randn(low_imgs.shape[0], net.style_dim, device=low_imgs.device)]
-    image, feats = decode_stage(decoder, codes, low_imgs.shape[-1], out_n_latent)
-    restored = restore_stage(net, low_imgs, feats, codes, noise_styles)
+    image, feats = decode_stage(decoder, codes, low_imgs.shape[-1], out_n_latent, noise=dec_noise)
+    restored = restore_stage(net, low_imgs, feats, codes, noise_styles, noise=net_noise)
     return restored, image
+
+
+def noise_shapes(net, decoder, batch):
+    """Shapes of every NoiseInjection image of one hot-path pass: (decoder list, {"encoder": [...], "decoder": [...]})."""
+    dec = [(batch, 1) + tuple(getattr(decoder.noises, f"noise_{i}").shape[2:]) for i in range(decoder.num_layers)]
+    rdec = [(batch, 1) + tuple(getattr(net.noises, f"noise_{i}").shape[2:]) for i in range(net.num_layers)]
+    renc, r = [], net.size
+    for _ in range(0, len(net.encoder_convs), 2):
+        renc += [(batch, 1, r, r), (batch, 1, r // 2, r // 2)]           # SMART layer at r, then its stride-2 conv
+        r //= 2
+    return dec, {"encoder": renc, "decoder": rdec}
 
 
 class GraphedRestorer:
@@ -711,7 +854,7 @@ class GraphedRestorer:
     ``micro`` rows; outputs are copies (the static output buffers are overwritten by the next replay) unless
     ``clone=False``."""
 
-    def __init__(self, net, decoder, micro, size=None, n_latent=None, device=None, warmup=2):
+    def __init__(self, net, decoder, micro, size=None, n_latent=None, device=None, warmup=2, explicit_noise=False):
         device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         size = size or net.size
         n_latent = n_latent or decoder.n_latent
@@ -719,11 +862,18 @@ class GraphedRestorer:
         self.low = torch.zeros(micro, 3, size, size, device=device)
         self.codes = torch.zeros(micro, n_latent, decoder.style_dim, device=device)
         self.z = torch.zeros(micro, net.style_dim, device=device)
+        # explicit_noise: the NoiseInjection images are static input buffers the caller fills (``dec_noise`` list,
+        # ``net_noise`` dict, see :func:`noise_shapes`) instead of per-replay draws — what parity tests compare against
+        self.dec_noise = self.net_noise = None
+        if explicit_noise:
+            dsh, nsh = noise_shapes(net, decoder, micro)
+            self.dec_noise = [torch.zeros(sh, device=device) for sh in dsh]
+            self.net_noise = {k: [torch.zeros(sh, device=device) for sh in v] for k, v in nsh.items()}
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                restore_faces(net, decoder, self.low, self.codes, [self.z])
+                restore_faces(net, decoder, self.low, self.codes, [self.z], dec_noise=self.dec_noise, net_noise=self.net_noise)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         # two graphs sharing one memory pool: the decoder half needs only the codes, so a caller that streams its inputs
@@ -732,10 +882,20 @@ class GraphedRestorer:
         self.graph_restore = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
-            self.image, feats = decode_stage(decoder, self.codes, size)
+            self.image, feats = decode_stage(decoder, self.codes, size, noise=self.dec_noise)
         with torch.cuda.graph(self.graph_restore, pool=self.graph.pool()):
-            self.restored = restore_stage(net, self.low, feats, self.codes, [self.z])
+            self.restored = restore_stage(net, self.low, feats, self.codes, [self.z], noise=self.net_noise)
         self.launches = _lib.launch_count() - n0          # sm_100a kernels of this library inside one replay of both
+
+    def set_noise(self, dec_noise, net_noise):
+        """Fill the static NoiseInjection buffers of an ``explicit_noise`` restorer (shapes: :func:`noise_shapes`)."""
+        if self.dec_noise is None:
+            raise RuntimeError("GraphedRestorer was captured without explicit_noise=True")
+        for dst, src in zip(self.dec_noise, dec_noise):
+            dst.copy_(src, non_blocking=True)
+        for key in ("encoder", "decoder"):
+            for dst, src in zip(self.net_noise[key], net_noise[key]):
+                dst.copy_(src, non_blocking=True)
 
     def __call__(self, low, codes, z, clone=True, before_low=None):
         """``before_low``: optional callable run after the decoder half has been enqueued and before ``low`` is read (e.g.

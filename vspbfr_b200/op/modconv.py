@@ -209,7 +209,8 @@ def _rows_per_tap(wq):
     return wq.shape[2]
 
 
-def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=None, out_nhwc=False, co_off=0):
+def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=None, out_nhwc=False, co_off=0,
+               algo_cin=None):
     """out = conv(x_nhwc, wq) (+ epilogue).  x_nhwc [B,H,W,Cin_pad] bf16, wq [G,taps,cout_pad,Cin_pad] bf16."""
     b, h, w, cin = x_nhwc.shape
     g, taps, _, k_pad = wq.shape
@@ -226,7 +227,8 @@ def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=N
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
     with torch.cuda.device(x_nhwc.device):
-        rc = _prof("conv_fprop", 2.0 * b * oh * ow * cout * cin * kh * kw, lambda: _lib.load().vsp_conv2d_fprop_bf16(
+        # algo_cin: channels of the layer this launch stands for when the operand carries extra terms (two-term operands)
+        rc = _prof("conv_fprop", 2.0 * b * oh * ow * cout * (algo_cin or cin) * kh * kw, lambda: _lib.load().vsp_conv2d_fprop_bf16(
             ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, stride, pad, dil, int(out_nhwc),
             ldo, co_off, ctypes.byref(e) if e is not None else None, stream_ptr()),
             detail=f"b{b} {cin}->{cout} k{kh} s{stride} d{dil} {h}x{w} g{g}",
@@ -314,7 +316,7 @@ def demod_from_wsq(s, wsq, wscale, eps=1e-8):
     return d
 
 
-def conv_branches(x_nhwc, wq, cout, dils, epi=None, out=None, out_nhwc=True, co_off=0):
+def conv_branches(x_nhwc, wq, cout, dils, epi=None, out=None, out_nhwc=True, co_off=0, algo_cin=None):
     """The dilated 3x3 branches of a SMART layer in one launch (vsp_conv2d_branches_bf16)."""
     b, h, w, cin = x_nhwc.shape
     g, taps, rows, k_pad = wq.shape
@@ -326,7 +328,7 @@ def conv_branches(x_nhwc, wq, cout, dils, epi=None, out=None, out_nhwc=True, co_
     e, keep = epi if epi is not None else (None, None)
     dl = _int_array(dils)
     with torch.cuda.device(x_nhwc.device):
-        rc = _prof("conv_branches", 2.0 * b * h * w * cout * cin * 9, lambda: _lib.load().vsp_conv2d_branches_bf16(
+        rc = _prof("conv_branches", 2.0 * b * h * w * cout * (algo_cin or cin) * 9, lambda: _lib.load().vsp_conv2d_branches_bf16(
             ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, len(dils), dl, int(out_nhwc), ldo, co_off,
             ctypes.byref(e) if e is not None else None, stream_ptr()),
             detail=f"b{b} {cin}->{cout} k3 x{len(dils)} branches {h}x{w} g{g}", nbytes=2.0 * b * h * w * (cin + cout))
