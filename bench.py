@@ -167,9 +167,14 @@ def main():
     ap.add_argument("--graph", type=int, default=GRAPH_DEFAULT,
                     help="1: replay one captured CUDA graph per micro-batch (fastpath.GraphedRestorer); 0: eager launches")
     ap.add_argument("--light", action="store_true", help="headline numbers only (skip roofline / pipeline / CPU legs)")
+    ap.add_argument("--workload", default="inference", choices=["inference", "train"],
+                    help="inference: BASELINE configs[3] (the headline, default); train: configs[4], one restoration_train.py "
+                         "iteration per step at batch 4/GPU under DDP")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch.distributed as dist
     from vspbfr_b200 import _lib, fastpath, sharding
@@ -324,9 +329,19 @@ def main():
         result["full_pipeline"] = full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev,
                                                  world * t_res / args.steps / TOTAL_IMAGES)
         result["roofline_config2"] = isolated_conv(mc, pk)
+        result["config2_module"] = config2_module(pk, dev)
+        result["config3_batch4"] = config3_batch4(net, dec, dev)
         result["hbm_roofline"] = isolated_upfirdn(upfirdn2d_raw, pk, dev)
         result["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(result))
+    if not args.light:
+        # BASELINE configs[4] next to the headline: every rank takes part (DDP all-reduce); rank 0 reports
+        del graphed
+        fastpath.clear_cache()
+        torch.cuda.empty_cache()
+        train = train_step_numbers(args, dev, world, rank, local, steps=3, warmup=2)
+        if rank == 0:
+            result["train_step"] = train
+            print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 
@@ -373,6 +388,252 @@ def full_pipeline(args, net, dec, low_d, z_d, micro, n_micro, world, dev, hot_s_
             "front_end": "e4e IR-SE50 encoder @256 (cuDNN, bf16 channels_last weights) + 4-step code diffuser (PyTorch, TF32 matmuls), random-init",
             "launch": "one CUDA graph replay per micro-batch (front end + hot path)" if graphed is not None else "eager launches",
             "note": "rank 0's shard only; the headline `value` starts from w+ codes"}
+
+
+def _event_time(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e-3 / iters
+
+
+def _graph_of(fn):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def config2_module(pk, dev):
+    """BASELINE configs[1] AS WRITTEN: ``ModulatedConv2d(512, 512, 3, style_dim=512)`` forward and forward+backward through
+    the module API — NCHW fp32 activations in and out, the modulation linear, demodulation vector, layout conversions and
+    weight packing all inside the timed region (next to ``roofline_config2``, which is the bare GEMM launch).  Rotating
+    input sets (6 x 134 MB > L2).  ``graph``: the same calls captured once and replayed (how the training step runs them);
+    ``eager``: issued from Python each time (host-bound: ~35 launches in ~0.5 ms of GPU time)."""
+    from vspbfr_b200.layers import ModulatedConv2d
+
+    torch.manual_seed(0)
+    b, c, h, sets = 8, 512, 64, 6
+    m = ModulatedConv2d(c, c, 3, 512).to(dev)
+    xs = [torch.randn(b, c, h, h, device=dev, requires_grad=True) for _ in range(sets)]
+    styles = [torch.randn(b, 512, device=dev, requires_grad=True) for _ in range(sets)]
+    dys = [torch.randn(b, c, h, h, device=dev) for _ in range(sets)]
+    params = list(m.parameters())
+
+    def fwd():
+        with torch.no_grad():
+            for x, st in zip(xs, styles):
+                m(x, st)
+
+    def fwdbwd():
+        for x, st, dy in zip(xs, styles, dys):
+            torch.autograd.grad(m(x, st), [x, st] + params, dy)
+
+    flops = 2.0 * b * c * c * 9 * h * h
+    out = {"workload": "ModulatedConv2d 3x3 demod 512->512, 64x64, batch 8, module API (NCHW fp32 in/out)",
+           "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (burst)", "unit": "TFLOP/s",
+           "timing": f"{sets} rotating input sets per measurement, CUDA events, 10 repetitions after warm-up"}
+    for name, fn, mult in (("fwd", fwd, 1), ("fwd_bwd", fwdbwd, 3)):
+        t_eager = _event_time(fn, 10) / sets
+        g = _graph_of(fn)
+        t_graph = _event_time(g.replay, 10) / sets
+        out[name] = {"us_graph": t_graph * 1e6, "us_eager": t_eager * 1e6,
+                     "achieved": mult * flops / t_graph / 1e12, "frac": mult * flops / t_graph / 1e12 / pk["bf16_tflops"],
+                     "algorithmic_gflop": mult * flops / 1e9}
+        del g
+    return out
+
+
+def config3_batch4(net, dec, dev):
+    """BASELINE configs[2]: restoration_test.py:125-131 at batch 4 on one GPU — e4e encoder + 4-step code diffuser, style
+    decoder, restoration network — per-stage CUDA-event times (eager launches) and the whole loop as one graph replay."""
+    from vspbfr_b200 import fastpath, frontend
+
+    torch.manual_seed(1)
+    b = 4
+    front = frontend.WPlusFrontEnd(frontend.Encoder4Editing(50, "ir_se"), n_latent=18).to(dev).eval().half_precision_()
+    ddpm = frontend.My_DDPM(frontend.Code_diffuser(timesteps=4), timesteps=4, linear_start=0.1, linear_end=0.99).to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    low = (torch.rand(b, 3, SIZE, SIZE, generator=g) * 2 - 1).to(dev)
+    z = torch.randn(b, STYLE_DIM, generator=g).to(dev)
+    with torch.no_grad():
+        codes = ddpm(condi_in=front(low), tf32=True)
+        _, feats = fastpath.decode_stage(dec, codes, SIZE)
+
+        def stage_front():
+            ddpm(condi_in=front(low), tf32=True)
+
+        def stage_decoder():
+            fastpath.decode_stage(dec, codes, SIZE)
+
+        def stage_restorer():
+            fastpath.restore_stage(net, low, feats, codes, [z])
+
+        def whole():
+            frontend.restore_pipeline(low, front, ddpm, dec, net, [z], tf32=True)
+
+        stages = {name: 1e3 * _event_time(fn, 5) for name, fn in (("front_end", stage_front), ("style_decoder", stage_decoder),
+                                                                   ("restoration_net", stage_restorer), ("whole_eager", whole))}
+        graphed = frontend.GraphedPipeline(front, ddpm, dec, net, b, device=dev)
+        t_graph = _event_time(lambda: graphed(low, z, clone=False), 10)
+    del graphed
+    return {"workload": "restoration_test.py:125-131, batch 4, 1 GPU (e4e IR-SE50 + 4-step diffuser + style decoder@1024 + "
+                        "Restoration_net@512), random-init",
+            "value": b / t_graph, "unit": UNIT, "ms_per_batch_graph": 1e3 * t_graph, "stage_ms_eager": stages,
+            "note": "eager stage times include host launch gaps at this batch size (a batch-4 pass is launch-bound); the graph "
+                    "replay is the GPU time of the same launches"}
+
+
+def _allreduce_probe(nbytes, dev, world):
+    """Stand-alone NCCL all-reduce of ``nbytes`` of fp32 in DDP-sized (25 MiB) buckets: (seconds, bus GB/s)."""
+    import torch.distributed as dist
+    if world == 1:
+        return 0.0, None
+    bucket = 25 * 2 ** 20 // 4
+    n = nbytes // 4
+    bufs = [torch.zeros(min(bucket, n - i), device=dev) for i in range(0, n, bucket)]
+    for _ in range(2):
+        for t in bufs:
+            dist.all_reduce(t)
+    torch.cuda.synchronize()
+    dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for t in bufs:
+        dist.all_reduce(t)
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    return sec, 2.0 * (world - 1) / world * nbytes / sec / 1e9
+
+
+def train_step_numbers(args, dev, world, rank, local, steps, warmup, batch=4):
+    """BASELINE configs[4]: ``steps`` iterations of vspbfr_b200.train_step.TrainStep (restoration_train.py:159-256: D
+    logistic + R1 double backward + G + EMA) at 512x512, batch 4 per GPU.  One GPU: the whole iteration replays as one
+    CUDA graph; N GPUs: DDP over NCCL (eager; DDP's bucketed all-reduce is not captured), timed with and without the
+    gradient all-reduce to expose its cost, plus a stand-alone all-reduce of the same bytes for the bus bandwidth."""
+    import torch.distributed as dist
+    from vspbfr_b200 import _lib
+    from vspbfr_b200.train_step import TrainStep
+
+    ts = TrainStep(SIZE, batch, dev, world=world, local_rank=local, rank=rank, capturable=(world == 1))
+    n0 = _lib.launch_count()
+    step = ts.capture(warmup) if world == 1 else ts.step
+    per_graph = ts.graph_launches if world == 1 else None
+
+    def timed(n, **kw):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            out = step(**kw)
+        e.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    for _ in range(max(warmup, 1)):
+        step()
+    n0 = _lib.launch_count()
+    t, (d_l, r1_l, g_l) = timed(steps)
+    launches = per_graph * steps if per_graph is not None else _lib.launch_count() - n0
+    # end to end: the step's batch arrives from pinned host memory and its losses are read back, every step
+    host = [x.cpu().pin_memory() for x in (ts.real_img, ts.low_img, ts.codes)]
+
+    inner = step
+
+    def step_e2e(**kw):
+        for dst, src in zip((ts.real_img, ts.low_img, ts.codes), host):
+            dst.copy_(src, non_blocking=True)
+        return [float(v) for v in inner(**kw)]
+
+    step = step_e2e
+    t_e2e = timed(steps)[0]
+    step = inner
+    t_nosync = timed(steps, sync=False)[0] if world > 1 else t
+    gb = ts.grad_bytes()
+    ar_s, bus = _allreduce_probe(gb["per_step"], dev, world)
+    res = {"metric": "train_images_per_sec_512", "value": world * batch * steps / t, "unit": "images/s", "n_gpus": world,
+           "batch_per_gpu": batch, "steps": steps, "ms_per_step": 1e3 * t / steps,
+           "ms_per_step_no_allreduce": 1e3 * t_nosync / steps, "allreduce_exposed_frac": max(0.0, 1 - t_nosync / t),
+           "allreduce": {"collective": "NCCL all-reduce of fp32 gradients in DDP buckets (25 MiB), during backward",
+                         "bytes_per_step": gb["per_step"], "generator_bytes": gb["generator"],
+                         "discriminator_bytes_x2": 2 * gb["discriminator"],
+                         "standalone_ms": 1e3 * ar_s, "bus_gbs": bus},
+           "launch": "one CUDA graph replay per iteration" if world == 1 else "eager launches under DistributedDataParallel",
+           "workload": "restoration_train.py:159-256 (D logistic + R1 double backward every iteration + G non-saturating + EMA), "
+                       "LPIPS / ArcFace weights 0 (pretrained nets unavailable), synthetic w+ codes for e4e + diffuser",
+           "e2e": {"value": world * batch * steps / t_e2e, "unit": "images/s",
+                   "h2d_bytes_per_step": world * sum(x.numel() * 4 for x in host), "d2h_bytes_per_step": world * 12},
+           "gpu_launches": int(launches) * world,
+           "losses": {"d": float(d_l), "r1": float(r1_l), "g": float(g_l)},
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    del ts
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_train(args):
+    """``--workload train``: the contract line for BASELINE configs[4]."""
+    import torch.distributed as dist
+    from vspbfr_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    _lib.load()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    res = train_step_numbers(args, dev, world, rank, local, steps=args.steps, warmup=max(args.warmup, 3))
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": res["workload"], "batch_per_gpu": res["batch_per_gpu"], "size": SIZE,
+                           "parallelism": f"DDP x{world} (NCCL all-reduce of gradients)", "launch": res["launch"],
+                           "l2": "activations of one iteration exceed L2 (> 10 GB)"},
+                "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clk, "train_step": res}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def conv_traffic(micro):

@@ -1,0 +1,131 @@
+"""GPU tests of the training step (BASELINE configs[4]): the iteration runs, every parameter is updated, and DDP's
+all-reduced gradients equal the single-process gradients of the concatenated batch ("DDP grads == single
+process").  The two ranks of the DDP test share cuda:0 (the test box has one GPU) and talk over gloo; NCCL carries the
+same all-reduce in ``bench.py --workload train --gpus N``."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vspbfr_b200.restorenet import Discriminator, Restoration_net
+from vspbfr_b200.stylegan2 import Generator
+from vspbfr_b200.train_step import TrainStep, d_logistic_loss, g_nonsaturating_loss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SIZE = 32
+
+
+def test_train_step_updates_every_parameter_and_replays_as_a_graph():
+    ts = TrainStep(SIZE, 2, DEV, capturable=True)
+    before = {k: v.detach().clone() for k, v in list(ts.g_module.named_parameters()) + list(ts.d_module.named_parameters())}
+    d, r1, g = ts.step()
+    assert all(torch.isfinite(v) for v in (d, r1, g))
+    after = dict(list(ts.g_module.named_parameters()) + list(ts.d_module.named_parameters()))
+    same = [k for k, v in before.items() if torch.equal(v, after[k])]
+    assert not same, f"parameters not updated: {same[:5]}"
+    replay = ts.capture()
+    assert ts.graph_launches > 100
+    snap = ts.g_module.conv1.fusion[0].weight.detach().clone()
+    d2, r12, g2 = replay()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v) for v in (d2, r12, g2))
+    assert not torch.equal(snap, ts.g_module.conv1.fusion[0].weight)          # the replay trains
+
+
+def _nets(seed=7):
+    torch.manual_seed(seed)
+    # eval(): the only train/eval difference in these networks is Restoration_net's Dropout2d(0.5) on the global code
+    # (models/RestoreNet.py:909), whose random mask would differ between the processes being compared
+    g = Restoration_net(SIZE, 512, 2, channel_multiplier=2).to(DEV).eval()
+    d = Discriminator(SIZE, channel_multiplier=2).to(DEV)
+    dec = Generator(SIZE * 2, 512, 2, channel_multiplier=2).to(DEV).eval()
+    return g, d, dec
+
+
+def _batch(n):
+    gen = torch.Generator().manual_seed(11)
+    return (torch.rand(n, 3, SIZE, SIZE, generator=gen) * 2 - 1, torch.rand(n, 3, SIZE, SIZE, generator=gen) * 2 - 1,
+            torch.randn(n, 18, 512, generator=gen), torch.randn(n, 512, generator=gen))
+
+
+def _losses_backward(g, d, dec, real, low, codes, z):
+    """G loss through D, and D's logistic loss: the two gradient sets DDP all-reduces."""
+    real, low, codes, z = (t.to(DEV) for t in (real, low, codes, z))
+    with torch.no_grad():
+        _, feats = dec([codes], input_is_latent=True, return_features=True)
+    restored = g(low, feats, codes, [z])
+    g_loss = g_nonsaturating_loss(d(restored))
+    d_loss = d_logistic_loss(d(real), d(restored.detach()))
+    g.zero_grad()
+    d.zero_grad()
+    # separate backward passes so each network's gradient comes from its own loss only
+    gg = torch.autograd.grad(g_loss, [p for p in g.parameters()], retain_graph=True)
+    d_loss.backward()
+    return gg
+
+
+def _ddp_worker(rank, world, port, per_rank, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, d, dec = _nets()
+        gd = torch.nn.parallel.DistributedDataParallel(g, broadcast_buffers=False)
+        dd = torch.nn.parallel.DistributedDataParallel(d, broadcast_buffers=False)
+        real, low, codes, z = _batch(world * per_rank)
+        # rank r owns rows r, r + world, ...: the single-process reference's minibatch-stddev groups (strided by batch/group,
+        # models/RestoreNet.py:1250-1258) then coincide with the per-rank batches
+        rows = slice(rank, None, world)
+        real, low, codes, z = (t[rows].to(DEV) for t in (real, low, codes, z))
+        with torch.no_grad():
+            _, feats = dec([codes], input_is_latent=True, return_features=True)
+        restored = gd(low, feats, codes, [z])
+        for p in d.parameters():
+            p.requires_grad_(False)
+        g_loss = g_nonsaturating_loss(d(restored))
+        gd.zero_grad()
+        g_loss.backward()                                    # DDP all-reduces (averages) G's gradients here
+        for p in d.parameters():
+            p.requires_grad_(True)
+        d_loss = d_logistic_loss(dd(real), dd(restored.detach()))
+        dd.zero_grad()
+        d_loss.backward()
+        torch.cuda.synchronize()
+        if rank == 0:
+            # numpy, not tensors: a tensor in a Queue travels as a shared-memory handle that dies with this process
+            q.put(({k: p.grad.cpu().numpy() for k, p in g.named_parameters()},
+                   {k: p.grad.cpu().numpy() for k, p in d.named_parameters()}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_gradients_equal_single_process_gradients():
+    world, per_rank = 2, 4
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, per_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    g_ddp, d_ddp = q.get(timeout=900)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g, d, dec = _nets()
+    gg = _losses_backward(g, d, dec, *_batch(world * per_rank))
+    # same arithmetic per sample; only the order of the batch reduction (split-K slices, atomics, all-reduce) differs
+    for (k, _), want in zip(g.named_parameters(), gg):
+        got = torch.from_numpy(g_ddp[k]).to(DEV)
+        scale = float(want.abs().max()) + 1e-12
+        assert float((got - want).abs().max()) <= 2e-2 * scale, (k, float((got - want).abs().max()), scale)
+    for k, p in d.named_parameters():
+        got, want = torch.from_numpy(d_ddp[k]).to(DEV), p.grad
+        scale = float(want.abs().max()) + 1e-12
+        assert float((got - want).abs().max()) <= 2e-2 * scale, (k, float((got - want).abs().max()), scale)

@@ -260,16 +260,22 @@ int launch_wgrad(WgradParams &p, const CUtensorMap &tdy, const void *x, int64_t 
   const long long base_tiles = (long long)p.groups * p.ntaps * p.tiles_m * p.tiles_n;
   const int samples = p.groups == 1 ? p.batch : 1;
   const long long kb_total = (long long)samples * p.kb_h * p.kb_w;
-  // split K until there are ~2 tiles per SM, keeping >= 8 k-blocks per slice
+  // split K: pick the slice count that minimises  waves x (k-blocks per slice + epilogue), where a wave is one tile per SM
+  // and the epilogue (TMEM -> registers -> fp32 stores / atomics of a 128 x BLOCK_N tile) costs about as much as 12
+  // k-blocks of MMAs.  The old rule (~2 tiles per SM) gave e.g. 360 tiles = 2.4 waves for 512 -> 512 at 64x64, batch 8;
+  // this one takes 144 tiles = one full wave (181 -> 150 us).  Slices keep >= 8 k-blocks.
   long long ks = 1;
-  const long long want = 2LL * num_sms();
-  if (base_tiles < want) {
-    ks = (want + base_tiles - 1) / base_tiles;
+  {
+    const long long sms = num_sms();
     const long long max_ks = kb_total / 8 > 0 ? kb_total / 8 : 1;
-    if (ks > max_ks) ks = max_ks;
-    // avoid empty slices
-    const long long per = (kb_total + ks - 1) / ks;
-    ks = (kb_total + per - 1) / per;
+    double best = 1e30;
+    for (long long c = 1; c <= max_ks && c <= 64; ++c) {
+      const long long per = (kb_total + c - 1) / c;
+      const long long slices = (kb_total + per - 1) / per;        // no empty slices
+      const long long waves = (base_tiles * slices + sms - 1) / sms;
+      const double cost = (double)waves * ((double)per + (slices > 1 ? 16.0 : 12.0));
+      if (cost < best - 1e-9) { best = cost; ks = slices; }
+    }
   }
   p.ksplit = (int)ks;
   p.total_tiles = base_tiles * ks;

@@ -152,11 +152,15 @@ class _ModulatedBase(nn.Module):
 
     def _conv(self, input, s, xs=None):
         """``xs``: ``modulate_input(input, s)`` when the caller shares it between branches (stride-1 form only)."""
+        cache = self.__dict__.setdefault("_derived", {})      # sum_t W^2 / packed weights, revalidated per call (not in state_dict)
         if self.upsample:
-            return self.blur(modulated_conv2d(input, self.weight, s, self.demodulate, "up", self.dilation, eps=self.eps))
+            return self.blur(modulated_conv2d(input, self.weight, s, self.demodulate, "up", self.dilation, eps=self.eps,
+                                              cache=cache))
         if self.downsample:
-            return modulated_conv2d(self.blur(input), self.weight, s, self.demodulate, "down", self.dilation, eps=self.eps)
-        return modulated_conv2d(input, self.weight, s, self.demodulate, "same", self.dilation, xs=xs, eps=self.eps)
+            return modulated_conv2d(self.blur(input), self.weight, s, self.demodulate, "down", self.dilation, eps=self.eps,
+                                    cache=cache)
+        return modulated_conv2d(input, self.weight, s, self.demodulate, "same", self.dilation, xs=xs, eps=self.eps,
+                                cache=cache)
 
     def __repr__(self):
         return (f"{self.__class__.__name__}({self.in_channel}, {self.out_channel}, {self.kernel_size}, "

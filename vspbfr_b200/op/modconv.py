@@ -447,10 +447,67 @@ def _taps(k):
     return [(i, j) for i in range(k) for j in range(k)]
 
 
-def demod_coefs(weight, s, wscale, eps=1e-8):
-    """d[b,o] (models/RestoreNet.py:513-516) from the style-independent sum_t W^2; differentiable in W and s."""
+def _demod_coefs_algebra(weight, s, wscale, eps=1e-8):
+    """d[b,o] as plain tensor algebra — differentiable to any order (the double-backward route)."""
     wsq = weight.reshape(weight.shape[-4], weight.shape[-3], -1).square().sum(-1)          # [Cout, Cin]
     return torch.rsqrt((wscale * wscale) * (s.square() @ wsq.t()) + eps)
+
+
+def _weight_derived(cache, weight, tag, build):
+    """A tensor derived from ``weight`` alone (sum_t W^2, packed bf16 forms), rebuilt only when the parameter changes
+    (``_version`` moves on every in-place update, i.e. every optimizer step; a new storage moves ``data_ptr``).
+    ``cache`` is a dict OWNED BY THE LAYER MODULE (it dies with the parameter, so a recycled address can never alias a stale
+    entry); None = no caching.  While a CUDA graph is being captured the tensor is always rebuilt, so the packing kernels
+    are part of the graph and a replay that follows an in-graph optimizer step never sees weights packed at capture time."""
+    if cache is None or torch.cuda.is_current_stream_capturing():
+        return build()
+    ver = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = build()
+    cache[tag] = (ver, val)
+    return val
+
+
+class DemodCoefs(Function):
+    """d[b,o] = rsqrt(wscale^2 * sum_i s[b,i]^2 * sum_t W[o,i,t]^2 + eps) (models/RestoreNet.py:513-516): one launch over the
+    cached sum_t W^2 instead of five library passes over the 9-tap weight.  First-order gradients in closed form; under
+    ``create_graph`` the backward re-derives them from the differentiable algebra."""
+
+    @staticmethod
+    def forward(ctx, weight, s, wscale, eps, cache):
+        w3 = weight.detach()
+        wsq = _weight_derived(cache, w3, "wsq", lambda: weight_sumsq(w3.contiguous()))
+        d = demod_from_wsq(s.detach(), wsq, wscale, eps)
+        ctx.save_for_backward(weight, s, d, wsq)
+        ctx.cfg = (wscale, eps)
+        return d
+
+    @staticmethod
+    def backward(ctx, gd):
+        weight, s, d, wsq = ctx.saved_tensors
+        wscale, eps = ctx.cfg
+        if torch.is_grad_enabled():
+            with torch.enable_grad():
+                dd = _demod_coefs_algebra(weight, s, wscale, eps)
+                wanted = [t for t, n in zip((weight, s), ctx.needs_input_grad[:2]) if n]
+                grads = list(torch.autograd.grad(dd, wanted, gd, create_graph=True, allow_unused=True))
+            return tuple(grads.pop(0) if n else None for n in ctx.needs_input_grad[:2]) + (None, None, None)
+        gq = (-0.5 * wscale * wscale) * gd * d * d * d                    # dL/d(sum_i s^2 wsq) [B, Cout]
+        gw = gs = None
+        if ctx.needs_input_grad[0]:
+            gw = (2.0 * (gq.t() @ s.square())).unsqueeze(-1).unsqueeze(-1) * weight        # [Cout, Cin, 1, 1] * W
+        if ctx.needs_input_grad[1]:
+            gs = 2.0 * s * (gq @ wsq)
+        return gw, gs, None, None, None
+
+
+def demod_coefs(weight, s, wscale, eps=1e-8, cache=None):
+    """d[b,o] (models/RestoreNet.py:513-516) from the style-independent sum_t W^2; differentiable in W and s."""
+    if weight.device.type != "cuda":
+        return _demod_coefs_algebra(weight, s, wscale, eps)
+    return DemodCoefs.apply(weight, s, wscale, eps, cache)
 
 
 class ModulateInput(Function):
@@ -505,10 +562,12 @@ class SharedWeightConv(Function):
     dxs = the adjoint convolution of dz (NHWC bf16 out); dW = wscale * the batch-summed pixel-K GEMM of dz and xs."""
 
     @staticmethod
-    def forward(ctx, xs, weight, d, mode, dilation):
+    def forward(ctx, xs, weight, d, mode, dilation, cache=None):
         cout, cin, k, _ = weight.shape
         wscale = 1.0 / math.sqrt(cin * k * k)
-        wq, _ = pack_weights(weight, wscale=wscale)
+        wd = weight.detach()
+        wq = _weight_derived(cache, wd, "wq", lambda: pack_weights(wd, wscale=wscale)[0])
+        ctx.cache = cache
         if wq.shape[3] != xs.shape[3]:
             raise RuntimeError(f"modulated_conv2d: activation has {xs.shape[3]} channels, weight expects {wq.shape[3]}")
         epi = make_epilogue(row_scale=d.contiguous()) if d is not None else None
@@ -536,7 +595,7 @@ class SharedWeightConv(Function):
             res = [grads.pop(0) if n else None for n in (need_x, need_w, need_d)]
             if res[0] is not None and res[0].dtype != xs.dtype:
                 res[0] = res[0].to(xs.dtype)
-            return (*res, None, None)
+            return (*res, None, None, None)
 
         b, h, w_, _ = xs.shape
         pad = ((k - 1) * dilation) // 2
@@ -549,7 +608,8 @@ class SharedWeightConv(Function):
             dzq = nchw_to_nhwc_bf16(dy)
         taps = _taps(k)
         if need_x:
-            wq_t, _ = pack_weights(weight, wscale=wscale, transpose=True)   # n = Cin, k = Cout
+            wd = weight.detach()
+            wq_t = _weight_derived(ctx.cache, wd, "wq_t", lambda: pack_weights(wd, wscale=wscale, transpose=True)[0])   # n = Cin, k = Cout
             cpad = xs.shape[3]
             if mode == "same":
                 dxs = conv_gather(dzq, wq_t, cin, [i * k + j for i, j in taps], [pad - i * dilation for i, j in taps],
@@ -572,7 +632,7 @@ class SharedWeightConv(Function):
             else:
                 gw = conv_wgrad(dzq, xs, 1, k, k, 1, pad, dilation)
             dw = (gw[0, :, :cout, :cin].permute(1, 2, 0) * wscale).reshape(weight.shape)
-        return dxs, dw, dd, None, None
+        return dxs, dw, dd, None, None, None
 
 
 def _nhwc_out(b, h, w, c, c_pad, device):
@@ -588,14 +648,16 @@ def modulate_input(x, s=None):
     return ModulateInput.apply(x, s)
 
 
-def modulated_conv2d(x, weight, s, demodulate=True, mode="same", dilation=1, xs=None, eps=1e-8):
+def modulated_conv2d(x, weight, s, demodulate=True, mode="same", dilation=1, xs=None, eps=1e-8, cache=None):
     """x [B,Cin,H,W] fp32, weight [1,Cout,Cin,k,k], s [B,Cin] (already through ``modulation``) -> [B,Cout,OH,OW] fp32.
-    ``xs``: the result of ``modulate_input(x, s)`` when the caller shares it between several convolutions."""
+    ``xs``: the result of ``modulate_input(x, s)`` when the caller shares it between several convolutions.
+    ``cache``: a dict owned by the calling layer for tensors derived from ``weight`` alone (sum_t W^2, packed bf16 weights),
+    revalidated against the parameter's version on every call."""
     _, cout, cin, k, _ = weight.shape
     if xs is None:
         if x.shape[1] != cin or s.shape != (x.shape[0], cin):
             raise RuntimeError(f"modulated_conv2d: shape mismatch x{tuple(x.shape)} w{tuple(weight.shape)} s{tuple(s.shape)}")
         xs = modulate_input(x, s)
     w4 = weight.reshape(cout, cin, k, k)
-    d = demod_coefs(w4, s, 1.0 / math.sqrt(cin * k * k), eps) if demodulate else None
-    return SharedWeightConv.apply(xs, w4, d, mode, dilation)
+    d = demod_coefs(w4, s, 1.0 / math.sqrt(cin * k * k), eps, cache) if demodulate else None
+    return SharedWeightConv.apply(xs, w4, d, mode, dilation, cache)

@@ -1,0 +1,160 @@
+"""One training iteration of the restoration GAN on the rebuilt layers (BASELINE.json configs[4]).
+
+Mirror of the loop body of /root/reference/restoration_train.py:159-256 — discriminator logistic step (:181-193), R1
+regulariser with its double backward through the Discriminator (:63-73, :200-216), generator non-saturating step
+(:220-250) and the EMA update (:46-51, :255) — with the loss helpers under the reference's own names
+(``d_logistic_loss`` :56-60, ``d_r1_loss`` :63-73, ``g_nonsaturating_loss`` :76-79, ``requires_grad`` :41-43,
+``accumulate`` :46-51).  The w+ codes stand in for the frozen e4e encoder + code diffuser (:166-167, outside the hot
+path); LPIPS / ArcFace terms need pretrained networks that cannot be downloaded and are off (their weights are 0, the
+``--percept_loss_weight 0 --id_loss_weight 0`` setting).  Data parallelism is the reference's: one process per GPU,
+``DistributedDataParallel`` around generator and discriminator (:431-445), gradients all-reduced by NCCL during backward.
+
+Every convolution of the step — forward, input gradient, weight gradient and the second-order terms of R1 — runs on the
+tcgen05 kernels through ``op.conv2d_gradfix`` / ``op.modconv``; there is no library convolution on this path.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+import torch.nn.functional as F
+from torch import autograd
+
+from .op import conv2d_gradfix
+from .restorenet import Discriminator, Restoration_net, mixing_noise
+from .stylegan2 import Generator
+
+
+def requires_grad(model, flag=True):
+    for p in model.parameters():
+        p.requires_grad = flag
+
+
+def accumulate(model1, model2, decay=0.999):
+    """EMA of ``model2``'s parameters into ``model1`` (one fused multi-tensor update instead of 2 launches per tensor)."""
+    p1, p2 = dict(model1.named_parameters()), dict(model2.named_parameters())
+    dst = [p1[k].data for k in p1]
+    src = [p2[k].data for k in p1]
+    torch._foreach_mul_(dst, decay)
+    torch._foreach_add_(dst, src, alpha=1 - decay)
+
+
+def d_logistic_loss(real_pred, fake_pred):
+    return F.softplus(-real_pred).mean() + F.softplus(fake_pred).mean()
+
+
+def d_r1_loss(real_pred, real_img):
+    with conv2d_gradfix.no_weight_gradients():
+        grad_real, = autograd.grad(outputs=real_pred.sum(), inputs=real_img, create_graph=True)
+    return grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
+
+
+def g_nonsaturating_loss(fake_pred):
+    return F.softplus(-fake_pred).mean()
+
+
+class TrainStep:
+    """Networks, optimizers and synthetic batch of one rank, and ``step()`` = one full iteration.
+
+    ``world`` > 1 wraps generator and discriminator in DistributedDataParallel over the already initialised default
+    process group.  ``capturable`` makes the Adam states device-resident so the whole iteration can be captured as one
+    CUDA graph (single GPU)."""
+
+    def __init__(self, size=512, batch=4, device="cuda", world=1, local_rank=0, rank=0, r1=10.0, d_reg_every=16,
+                 style_dim=512, n_mlp=8, mixing=0.9, capturable=False, seed=0):
+        self.size, self.batch, self.world, self.device = size, batch, world, torch.device(device)
+        self.r1, self.d_reg_every, self.style_dim, self.mixing = r1, d_reg_every, style_dim, mixing
+        dev = self.device
+        torch.manual_seed(seed)
+        self.g_module = Restoration_net(size, style_dim, n_mlp, channel_multiplier=2).to(dev)
+        self.g_ema = Restoration_net(size, style_dim, n_mlp, channel_multiplier=2).to(dev).eval()
+        self.g_ema.load_state_dict(self.g_module.state_dict())
+        self.d_module = Discriminator(size, channel_multiplier=2).to(dev)
+        self.decoder = Generator(max(size * 2, 16), style_dim, n_mlp, channel_multiplier=2).to(dev).eval()
+        self.generator, self.discriminator = self.g_module, self.d_module
+        if world > 1:
+            ddp = torch.nn.parallel.DistributedDataParallel
+            ids = [local_rank] if dev.type == "cuda" else None
+            self.generator = ddp(self.g_module, device_ids=ids, broadcast_buffers=False)
+            self.discriminator = ddp(self.d_module, device_ids=ids, broadcast_buffers=False)
+        g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)          # restoration_train.py:410-422
+        self.g_optim = torch.optim.Adam(self.generator.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio),
+                                        capturable=capturable)
+        self.d_optim = torch.optim.Adam(self.discriminator.parameters(), lr=0.002 * d_ratio, betas=(0.0, 0.99 ** d_ratio),
+                                        capturable=capturable)
+        g = torch.Generator(device="cpu").manual_seed(100 + rank)
+        self.real_img = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).to(dev)
+        self.low_img = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).to(dev)
+        self.codes = torch.randn(batch, 18, style_dim, generator=g).to(dev)
+
+    def grad_bytes(self):
+        """fp32 gradient bytes all-reduced per iteration: D twice (logistic + R1 steps), G once."""
+        n = lambda m: sum(p.numel() for p in m.parameters()) * 4
+        return {"generator": n(self.g_module), "discriminator": n(self.d_module), "per_step": n(self.g_module) + 2 * n(self.d_module)}
+
+    def _nosync(self, module, sync):
+        return module.no_sync() if (self.world > 1 and not sync) else contextlib.nullcontext()
+
+    def step(self, sync=True):
+        """One iteration; ``sync=False`` skips the gradient all-reduce (to measure its exposed cost)."""
+        dev = self.device
+        with torch.no_grad():
+            _, de_feats = self.decoder([self.codes], input_is_latent=True, return_features=True)
+        # ---- discriminator, logistic loss
+        requires_grad(self.generator, False)
+        requires_grad(self.discriminator, True)
+        noise = mixing_noise(self.batch, self.style_dim, self.mixing, dev)
+        with torch.no_grad():
+            restored = self.generator(self.low_img, de_feats, self.codes, noise)
+        with self._nosync(self.discriminator, sync):
+            d_loss = d_logistic_loss(self.discriminator(self.real_img), self.discriminator(restored.detach()))
+            self.discriminator.zero_grad()
+            d_loss.backward()
+        self.d_optim.step()
+        # ---- R1 (every iteration here: the double-backward path is what configs[4] is about; the reference runs it
+        # every d_reg_every-th iteration with the same weight)
+        tmp = self.real_img.detach().clone().requires_grad_(True)
+        with self._nosync(self.discriminator, sync):
+            real_pred = self.discriminator(tmp)
+            r1_loss = d_r1_loss(real_pred, tmp)
+            self.discriminator.zero_grad()
+            (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * real_pred[0]).backward()
+        self.d_optim.step()
+        # ---- generator, non-saturating loss
+        requires_grad(self.generator, True)
+        requires_grad(self.discriminator, False)
+        noise = mixing_noise(self.batch, self.style_dim, self.mixing, dev)
+        with self._nosync(self.generator, sync):
+            restored = self.generator(self.low_img, de_feats, self.codes, noise)
+            g_loss = g_nonsaturating_loss(self.discriminator(restored))
+            self.generator.zero_grad()
+            g_loss.backward()
+        self.g_optim.step()
+        accumulate(self.g_ema, self.g_module, 0.5 ** (32 / (10 * 1000)))
+        return d_loss.detach(), r1_loss.detach(), g_loss.detach()
+
+    def capture(self, warmup=3):
+        """The whole iteration as ONE CUDA graph (single GPU): returns ``replay() -> (d, r1, g)`` losses (static tensors)."""
+        if self.world != 1:
+            raise RuntimeError("whole-iteration capture is single-GPU (DDP's bucketed all-reduce is not captured)")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, warmup)):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.generator.zero_grad(set_to_none=True)
+        self.discriminator.zero_grad(set_to_none=True)
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            out = self.step()
+        self._graph = graph
+        self.graph_launches = _lib.launch_count() - n0          # this library's kernels inside one replay
+
+        def replay():
+            graph.replay()
+            return out
+        return replay
