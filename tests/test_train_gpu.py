@@ -1,6 +1,6 @@
 """GPU tests of the training step (BASELINE configs[4]): the iteration runs, every parameter is updated, and DDP's
-all-reduced gradients equal the single-process gradients of the concatenated batch ("DDP grads == single
-process").  The two ranks of the DDP test share cuda:0 (the test box has one GPU) and talk over gloo; NCCL carries the
+all-reduced gradients equal the average of the same shards' gradients computed in one process ("DDP grads ==
+single process").  The two ranks of the DDP test share cuda:0 (the test box has one GPU) and talk over gloo; NCCL carries the
 same all-reduce in ``bench.py --workload train --gpus N``."""
 import os
 import socket
@@ -118,14 +118,27 @@ def test_ddp_gradients_equal_single_process_gradients():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    # single process: the same two shards one after the other, gradients averaged (what DDP's all-reduce computes).  The
+    # shards are NOT fused into one batch of 8: the style MLP / modulation linears are library GEMMs whose fp32 summation
+    # order depends on the batch size (measured 1e-6), and this random-init network amplifies such differences through
+    # bf16 rounding flips to ~10 % of a gradient — a property of the network, not of the all-reduce under test.
+    # What remains between the two sides is the order of fp32 atomics (split-K weight gradients, bias reductions) followed by bf16 rounding of the next gradient: measured 2e-3, bound 1e-2.
     g, d, dec = _nets()
-    gg = _losses_backward(g, d, dec, *_batch(world * per_rank))
-    # same arithmetic per sample; only the order of the batch reduction (split-K slices, atomics, all-reduce) differs
-    for (k, _), want in zip(g.named_parameters(), gg):
-        got = torch.from_numpy(g_ddp[k]).to(DEV)
+    batch = _batch(world * per_rank)
+    g_sum, d_sum = None, None
+    for r in range(world):
+        shard = [t[r::world] for t in batch]
+        gg = _losses_backward(g, d, dec, *shard)
+        dgr = [p.grad.detach().clone() for p in d.parameters()]
+        g_sum = list(gg) if g_sum is None else [a + b for a, b in zip(g_sum, gg)]
+        d_sum = dgr if d_sum is None else [a + b for a, b in zip(d_sum, dgr)]
+    for (k, _), want in zip(g.named_parameters(), g_sum):
+        if k.endswith("noise.weight"):
+            continue        # its gradient is sum(dy * noise) with noise drawn per call from each process's own generator
+        got, want = torch.from_numpy(g_ddp[k]).to(DEV), want / world
         scale = float(want.abs().max()) + 1e-12
-        assert float((got - want).abs().max()) <= 2e-2 * scale, (k, float((got - want).abs().max()), scale)
-    for k, p in d.named_parameters():
-        got, want = torch.from_numpy(d_ddp[k]).to(DEV), p.grad
+        assert float((got - want).abs().max()) <= 1e-2 * scale, (k, float((got - want).abs().max()), scale)
+    for (k, _), want in zip(d.named_parameters(), d_sum):
+        got, want = torch.from_numpy(d_ddp[k]).to(DEV), want / world
         scale = float(want.abs().max()) + 1e-12
-        assert float((got - want).abs().max()) <= 2e-2 * scale, (k, float((got - want).abs().max()), scale)
+        assert float((got - want).abs().max()) <= 1e-2 * scale, (k, float((got - want).abs().max()), scale)
