@@ -525,15 +525,19 @@ def train_step_numbers(args, dev, world, rank, local, steps, warmup, batch=4):
     """BASELINE configs[4]: ``steps`` iterations of vspbfr_b200.train_step.TrainStep (restoration_train.py:159-256: D
     logistic + R1 double backward + G + EMA) at 512x512, batch 4 per GPU.  One GPU: the whole iteration replays as one
     CUDA graph; N GPUs: DDP over NCCL (eager; DDP's bucketed all-reduce is not captured), timed with and without the
-    gradient all-reduce to expose its cost, plus a stand-alone all-reduce of the same bytes for the bus bandwidth."""
+    gradient all-reduce to expose its cost, plus a stand-alone all-reduce of the same bytes for the bus bandwidth.
+    Several GPUs: the phases of the iteration replay as graphs and the flat gradient buffers are averaged by NCCL between
+    them (``VSP_TRAIN_REDUCE=ddp``: the reference's DistributedDataParallel, eager)."""
     import torch.distributed as dist
     from vspbfr_b200 import _lib
     from vspbfr_b200.train_step import TrainStep
 
-    ts = TrainStep(SIZE, batch, dev, world=world, local_rank=local, rank=rank, capturable=(world == 1))
+    reduce = os.environ.get("VSP_TRAIN_REDUCE", "flat")          # "flat": graph phases + one NCCL all-reduce per backward; "ddp": eager DDP
+    graphed = world == 1 or reduce == "flat"
+    ts = TrainStep(SIZE, batch, dev, world=world, local_rank=local, rank=rank, capturable=graphed, reduce=reduce)
     n0 = _lib.launch_count()
-    step = ts.capture(warmup) if world == 1 else ts.step
-    per_graph = ts.graph_launches if world == 1 else None
+    step = ts.capture(warmup) if graphed else ts.step
+    per_graph = ts.graph_launches if graphed else None
 
     def timed(n, **kw):
         if world > 1:
@@ -576,11 +580,14 @@ def train_step_numbers(args, dev, world, rank, local, steps, warmup, batch=4):
     res = {"metric": "train_images_per_sec_512", "value": world * batch * steps / t, "unit": "images/s", "n_gpus": world,
            "batch_per_gpu": batch, "steps": steps, "ms_per_step": 1e3 * t / steps,
            "ms_per_step_no_allreduce": 1e3 * t_nosync / steps, "allreduce_exposed_frac": max(0.0, 1 - t_nosync / t),
-           "allreduce": {"collective": "NCCL all-reduce of fp32 gradients in DDP buckets (25 MiB), during backward",
+           "allreduce": {"collective": ("one NCCL all-reduce (AVG) of the flat fp32 gradient buffer after each backward, between graph replays"
+                                        if reduce == "flat" else "NCCL all-reduce of fp32 gradients in DDP buckets (25 MiB), during backward"),
                          "bytes_per_step": gb["per_step"], "generator_bytes": gb["generator"],
                          "discriminator_bytes_x2": 2 * gb["discriminator"],
                          "standalone_ms": 1e3 * ar_s, "bus_gbs": bus},
-           "launch": "one CUDA graph replay per iteration" if world == 1 else "eager launches under DistributedDataParallel",
+           "launch": ("one CUDA graph replay per iteration" if world == 1 else
+                      "four CUDA graph replays per iteration (D / R1 / G / update phases), gradient all-reduce between them" if graphed
+                      else "eager launches under DistributedDataParallel"),
            "workload": "restoration_train.py:159-256 (D logistic + R1 double backward every iteration + G non-saturating + EMA), "
                        "LPIPS / ArcFace weights 0 (pretrained nets unavailable), synthetic w+ codes for e4e + diffuser",
            "e2e": {"value": world * batch * steps / t_e2e, "unit": "images/s",

@@ -36,6 +36,34 @@ def test_train_step_updates_every_parameter_and_replays_as_a_graph():
     assert not torch.equal(snap, ts.g_module.conv1.fusion[0].weight)          # the replay trains
 
 
+def test_flat_gradient_buffers_stay_attached_and_train():
+    """reduce="flat": every .grad is (and stays, after backward passes and optimizer steps) a view into the network's one
+    flat buffer — the thing the single NCCL all-reduce per backward operates on — and the graph replay trains."""
+    ts = TrainStep(SIZE, 2, DEV, capturable=True, reduce="flat")
+
+    def attached(module, flat):
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+        off = 0
+        for p in module.parameters():
+            assert p.grad is not None and p.grad.data_ptr() == lo + off * 4 and p.grad.data_ptr() < hi
+            off += p.numel()
+        assert off == flat.numel()
+
+    attached(ts.g_module, ts.flat_g)
+    attached(ts.d_module, ts.flat_d)
+    ts.step()
+    attached(ts.g_module, ts.flat_g)
+    attached(ts.d_module, ts.flat_d)
+    assert float(ts.flat_g.abs().sum()) > 0 and float(ts.flat_d.abs().sum()) > 0
+    replay = ts.capture()
+    snap = ts.d_module.final_linear[1].weight.detach().clone()
+    d, r1, g = replay()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v) for v in (d, r1, g))
+    assert not torch.equal(snap, ts.d_module.final_linear[1].weight)
+    attached(ts.g_module, ts.flat_g)
+
+
 def _nets(seed=7):
     torch.manual_seed(seed)
     # eval(): the only train/eval difference in these networks is Restoration_net's Dropout2d(0.5) on the global code

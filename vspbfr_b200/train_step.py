@@ -54,16 +54,25 @@ def g_nonsaturating_loss(fake_pred):
 
 
 class TrainStep:
-    """Networks, optimizers and synthetic batch of one rank, and ``step()`` = one full iteration.
+    """Networks, optimizers and synthetic batch of one rank; ``step()`` = one full iteration.
 
-    ``world`` > 1 wraps generator and discriminator in DistributedDataParallel over the already initialised default
-    process group.  ``capturable`` makes the Adam states device-resident so the whole iteration can be captured as one
-    CUDA graph (single GPU)."""
+    Gradient exchange across ``world`` ranks (the default process group must already be initialised):
+      * ``reduce="ddp"``  — the reference's way: generator and discriminator wrapped in DistributedDataParallel
+        (restoration_train.py:431-445), bucketed all-reduce overlapped with backward by the reducer's hooks; eager only.
+      * ``reduce="flat"`` — every parameter's ``.grad`` is a view into one flat fp32 buffer per network, averaged with ONE
+        NCCL all-reduce per backward (D logistic, D R1, G: 116 + 116 + 450 MB over NVLink) between the phases of the
+        iteration.  The phases hold no collective, so each replays as a CUDA graph (``capture()``): the eager iteration is
+        bound by the host (~170 ms of Python / autograd for ~107 ms of GPU work), and a few ms of un-overlapped all-reduce
+        cost far less than that.
+    ``capturable`` keeps the Adam step counters on the device (needed for capture)."""
 
     def __init__(self, size=512, batch=4, device="cuda", world=1, local_rank=0, rank=0, r1=10.0, d_reg_every=16,
-                 style_dim=512, n_mlp=8, mixing=0.9, capturable=False, seed=0):
+                 style_dim=512, n_mlp=8, mixing=0.9, capturable=False, seed=0, reduce="ddp"):
+        if reduce not in ("ddp", "flat"):
+            raise ValueError(f"reduce must be 'ddp' or 'flat', got {reduce!r}")
         self.size, self.batch, self.world, self.device = size, batch, world, torch.device(device)
         self.r1, self.d_reg_every, self.style_dim, self.mixing = r1, d_reg_every, style_dim, mixing
+        self.reduce = reduce
         dev = self.device
         torch.manual_seed(seed)
         self.g_module = Restoration_net(size, style_dim, n_mlp, channel_multiplier=2).to(dev)
@@ -72,11 +81,14 @@ class TrainStep:
         self.d_module = Discriminator(size, channel_multiplier=2).to(dev)
         self.decoder = Generator(max(size * 2, 16), style_dim, n_mlp, channel_multiplier=2).to(dev).eval()
         self.generator, self.discriminator = self.g_module, self.d_module
-        if world > 1:
+        self.flat_g = self.flat_d = None
+        if world > 1 and reduce == "ddp":
             ddp = torch.nn.parallel.DistributedDataParallel
             ids = [local_rank] if dev.type == "cuda" else None
             self.generator = ddp(self.g_module, device_ids=ids, broadcast_buffers=False)
             self.discriminator = ddp(self.d_module, device_ids=ids, broadcast_buffers=False)
+        if reduce == "flat":
+            self.flat_g, self.flat_d = _flatten_grads(self.g_module), _flatten_grads(self.d_module)
         g_ratio, d_ratio = 4 / 5, d_reg_every / (d_reg_every + 1)          # restoration_train.py:410-422
         self.g_optim = torch.optim.Adam(self.generator.parameters(), lr=0.002 * g_ratio, betas=(0.0, 0.99 ** g_ratio),
                                         capturable=capturable)
@@ -86,57 +98,100 @@ class TrainStep:
         self.real_img = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).to(dev)
         self.low_img = (torch.rand(batch, 3, size, size, generator=g) * 2 - 1).to(dev)
         self.codes = torch.randn(batch, 18, style_dim, generator=g).to(dev)
+        self._de_feats = None
+        self._losses = [None, None, None]
 
     def grad_bytes(self):
         """fp32 gradient bytes all-reduced per iteration: D twice (logistic + R1 steps), G once."""
         n = lambda m: sum(p.numel() for p in m.parameters()) * 4
         return {"generator": n(self.g_module), "discriminator": n(self.d_module), "per_step": n(self.g_module) + 2 * n(self.d_module)}
 
-    def _nosync(self, module, sync):
-        return module.no_sync() if (self.world > 1 and not sync) else contextlib.nullcontext()
+    # ---- gradient bookkeeping -------------------------------------------------------------------------------------
+    def _zero(self, module, flat):
+        if flat is not None:
+            flat.zero_()                               # .grad tensors are views of `flat`: one memset
+        else:
+            module.zero_grad()
 
-    def step(self, sync=True):
-        """One iteration; ``sync=False`` skips the gradient all-reduce (to measure its exposed cost)."""
+    def _exchange(self, flat, sync):
+        """Average the gradients of the backward that just ran (flat mode; DDP's reducer has already done it)."""
+        if flat is not None and self.world > 1 and sync:
+            import torch.distributed as dist
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            else:                                       # gloo (CPU-side tests) has no AVG
+                dist.all_reduce(flat)
+                flat.div_(self.world)
+
+    def _nosync(self, module, sync):
+        ddp = self.world > 1 and self.reduce == "ddp"
+        return module.no_sync() if (ddp and not sync) else contextlib.nullcontext()
+
+    # ---- the four phases of restoration_train.py:159-256; a gradient exchange sits between consecutive phases ---------
+    def _phase_d(self, sync=True):
+        """Style-decoder features, generator forward (no grad), discriminator logistic loss and its backward."""
         dev = self.device
         with torch.no_grad():
-            _, de_feats = self.decoder([self.codes], input_is_latent=True, return_features=True)
-        # ---- discriminator, logistic loss
+            _, self._de_feats = self.decoder([self.codes], input_is_latent=True, return_features=True)
         requires_grad(self.generator, False)
         requires_grad(self.discriminator, True)
         noise = mixing_noise(self.batch, self.style_dim, self.mixing, dev)
         with torch.no_grad():
-            restored = self.generator(self.low_img, de_feats, self.codes, noise)
+            restored = self.generator(self.low_img, self._de_feats, self.codes, noise)
         with self._nosync(self.discriminator, sync):
             d_loss = d_logistic_loss(self.discriminator(self.real_img), self.discriminator(restored.detach()))
-            self.discriminator.zero_grad()
+            self._zero(self.discriminator, self.flat_d)
             d_loss.backward()
+        self._losses[0] = d_loss.detach()
+
+    def _phase_r1(self, sync=True):
+        """Discriminator update, then the R1 penalty and its (double) backward — every iteration here: that path is what
+        configs[4] is about; the reference runs it every d_reg_every-th iteration with the same weight."""
         self.d_optim.step()
-        # ---- R1 (every iteration here: the double-backward path is what configs[4] is about; the reference runs it
-        # every d_reg_every-th iteration with the same weight)
         tmp = self.real_img.detach().clone().requires_grad_(True)
         with self._nosync(self.discriminator, sync):
             real_pred = self.discriminator(tmp)
             r1_loss = d_r1_loss(real_pred, tmp)
-            self.discriminator.zero_grad()
+            self._zero(self.discriminator, self.flat_d)
             (self.r1 / 2 * r1_loss * self.d_reg_every + 0 * real_pred[0]).backward()
+        self._losses[1] = r1_loss.detach()
+
+    def _phase_g(self, sync=True):
+        """Discriminator update, then the generator's non-saturating loss and its backward."""
         self.d_optim.step()
-        # ---- generator, non-saturating loss
         requires_grad(self.generator, True)
         requires_grad(self.discriminator, False)
-        noise = mixing_noise(self.batch, self.style_dim, self.mixing, dev)
+        noise = mixing_noise(self.batch, self.style_dim, self.mixing, self.device)
         with self._nosync(self.generator, sync):
-            restored = self.generator(self.low_img, de_feats, self.codes, noise)
+            restored = self.generator(self.low_img, self._de_feats, self.codes, noise)
             g_loss = g_nonsaturating_loss(self.discriminator(restored))
-            self.generator.zero_grad()
+            self._zero(self.generator, self.flat_g)
             g_loss.backward()
+        self._losses[2] = g_loss.detach()
+
+    def _phase_update(self):
+        """Generator update and EMA."""
         self.g_optim.step()
         accumulate(self.g_ema, self.g_module, 0.5 ** (32 / (10 * 1000)))
-        return d_loss.detach(), r1_loss.detach(), g_loss.detach()
+
+    def step(self, sync=True):
+        """One eager iteration; ``sync=False`` skips the gradient exchange (to measure its exposed cost)."""
+        self._phase_d(sync)
+        self._exchange(self.flat_d, sync)
+        self._phase_r1(sync)
+        self._exchange(self.flat_d, sync)
+        self._phase_g(sync)
+        self._exchange(self.flat_g, sync)
+        self._phase_update()
+        return tuple(self._losses)
 
     def capture(self, warmup=3):
-        """The whole iteration as ONE CUDA graph (single GPU): returns ``replay() -> (d, r1, g)`` losses (static tensors)."""
-        if self.world != 1:
-            raise RuntimeError("whole-iteration capture is single-GPU (DDP's bucketed all-reduce is not captured)")
+        """The iteration as CUDA graphs: ONE graph on a single GPU; with ``reduce="flat"`` on several GPUs one graph per
+        phase (shared memory pool) with the NCCL all-reduces issued between the replays.  Returns
+        ``replay(sync=True) -> (d, r1, g)`` losses (static tensors)."""
+        from . import _lib
+        if self.world > 1 and self.reduce != "flat":
+            raise RuntimeError("graph capture on several GPUs needs reduce='flat' (DDP's reducer is not captured)")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -144,17 +199,49 @@ class TrainStep:
                 self.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.generator.zero_grad(set_to_none=True)
-        self.discriminator.zero_grad(set_to_none=True)
-        from . import _lib
-        graph = torch.cuda.CUDAGraph()
+        if self.flat_g is None:
+            self.generator.zero_grad(set_to_none=True)
+            self.discriminator.zero_grad(set_to_none=True)
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
-            out = self.step()
-        self._graph = graph
-        self.graph_launches = _lib.launch_count() - n0          # this library's kernels inside one replay
+        if self.world == 1:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.step()
+            graphs = [graph]
+        else:
+            graphs, pool = [], None
+            for phase in (self._phase_d, self._phase_r1, self._phase_g, self._phase_update):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    phase()
+                pool = pool or g.pool()
+                graphs.append(g)
+        self._graphs = graphs
+        self.graph_launches = _lib.launch_count() - n0          # this library's kernels inside one replayed iteration
+        out = tuple(self._losses)
 
-        def replay():
-            graph.replay()
+        def replay(sync=True):
+            if len(graphs) == 1:
+                graphs[0].replay()
+                return out
+            graphs[0].replay()
+            self._exchange(self.flat_d, sync)
+            graphs[1].replay()
+            self._exchange(self.flat_d, sync)
+            graphs[2].replay()
+            self._exchange(self.flat_g, sync)
+            graphs[3].replay()
             return out
         return replay
+
+
+def _flatten_grads(module):
+    """Give every parameter of ``module`` a ``.grad`` that is a view into one flat fp32 buffer (returned): autograd
+    accumulates into existing gradients in place, so one all-reduce / one memset covers the whole network."""
+    params = [p for p in module.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return flat
