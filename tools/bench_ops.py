@@ -60,6 +60,7 @@ def main():
     FLUSH = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
     k = (k1[None] * k1[:, None] / 64).to(dev)
+    k4 = (k * 4).contiguous()
     rows = []
 
     def run(name, make, bytes_, sets=None):
@@ -81,12 +82,12 @@ def main():
 
     def mk_up2():
         x = R(4, 512, 64, 64)
-        return lambda: upfirdn2d_raw(x, k * 4, *up2)
+        return lambda: upfirdn2d_raw(x, k4, *up2)
     run("upfirdn2d up2 [4,512,64,64]", mk_up2, (nx + ny) * 4)
 
     def mk_down2():
         y = R(4, 512, 128, 128)
-        return lambda: upfirdn2d_raw(y, k * 4, (1, 1), (2, 2), (1, 1, 1, 1))
+        return lambda: upfirdn2d_raw(y, k4, (1, 1), (2, 2), (1, 1, 1, 1))
     run("upfirdn2d down2 (bwd of up2) [4,512,128,128]", mk_down2, (nx + ny) * 4)
 
     def mk_ba(shape):
@@ -104,13 +105,14 @@ def main():
 
     def mk_fused():
         x = R(4, 512, 64, 64)
-        return lambda: upfirdn2d_raw(x, k * 4, *up2, bias=b, act=3, alpha=0.2, scale=2 ** 0.5)
+        return lambda: upfirdn2d_raw(x, k4, *up2, bias=b, act=3, alpha=0.2, scale=2 ** 0.5)
     run("fused upfirdn2d+bias+lrelu [4,512,64,64]", mk_fused, (nx + ny) * 4)
 
     def mk_blur(shape, gain, pad):
         def mk():
             x = R(*shape)
-            return lambda: upfirdn2d_raw(x, k * gain, (1, 1), (1, 1), pad)
+            kk = (k * gain).contiguous()
+            return lambda: upfirdn2d_raw(x, kk, (1, 1), (1, 1), pad)
         return mk
     run("blur pad(1,1) [4,512,65,65]", mk_blur((4, 512, 65, 65), 4, (1, 1, 1, 1)), (4 * 512 * 65 * 65 + nx) * 4)
     run("blur pad(1,1) [4,32,1025,1025]", mk_blur((4, 32, 1025, 1025), 4, (1, 1, 1, 1)),

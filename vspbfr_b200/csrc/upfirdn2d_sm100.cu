@@ -858,6 +858,198 @@ int dispatch_tile(const UfdParams &p, cudaStream_t stream) {
   return launch_tile<U, D, QX, QY, 8, 8, 32>(p, stream);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-band kernel for up = down = 1 on planes whose row pitch is NOT a multiple of 16 bytes (the model's blurs on odd
+// extents: [.,.,65,65], [.,.,1025,1025], [.,.,513,513] ...), where no tensor map exists and the tile kernel fell back to
+// per-element LDG staging (0.27-0.44 of HBM).  A band of TOH output rows spans the whole width, so the input rows it needs
+// are ONE contiguous byte range of the plane: it is brought in by a single 1-D bulk copy (cp.async.bulk, 16-byte aligned by
+// over-fetching <= 12 bytes at each end) into a 3-stage mbarrier ring — no address arithmetic, predicates or registers on the
+// load side, every input row read once per band (+ kh - 1 halo rows).  Compute: thread = (output column, group of kBandR
+// rows); consecutive lanes own consecutive columns (conflict-free scalar LDS, 128-byte coalesced stores); an input row's four
+// values feed the rolling accumulators of the <= 4 output rows that use it, in the reference's tap order (ky outer, kx
+// inner), so results are bit-identical to the generic kernel.
+constexpr int kBandThreads = 512;
+constexpr int kBandStages = 3;
+constexpr int kBandStageBytes = 73728;          // 3 x 72 KiB + barriers < 227 KiB
+constexpr int kBandR = 8;                       // output rows per thread item
+
+struct BandParams {
+  UfdParams u;
+  int toh;                  // output rows per band
+  int bands;                // bands per plane
+  long long units;          // planes x bands
+  long long total_floats;   // elements of x (bulk copies never read past the last whole 16 bytes)
+};
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// input rows [iy_lo, iy_hi) of band `j` and the aligned float range [g_lo, g_hi) of x that holds them
+__device__ __forceinline__ void band_range(const BandParams &p, long long unit, int &oy0, int &iy_lo, int &iy_hi,
+                                           long long &plane, long long &g_lo, long long &g_hi) {
+  plane = unit / p.bands;
+  const int j = (int)(unit % p.bands);
+  oy0 = j * p.toh;
+  const int rows = min(p.toh, p.u.out_h - oy0);
+  iy_lo = max(0, oy0 - p.u.pad_y0);
+  iy_hi = min(p.u.in_h, oy0 + rows - 1 - p.u.pad_y0 + p.u.kh);
+  if (iy_hi < iy_lo) iy_hi = iy_lo;
+  const long long base = plane * p.u.in_h * (long long)p.u.in_w;
+  g_lo = (base + (long long)iy_lo * p.u.in_w) & ~3LL;
+  g_hi = (base + (long long)iy_hi * p.u.in_w + 3) & ~3LL;
+}
+
+__global__ void __launch_bounds__(kBandThreads, 1)
+upfirdn2d_band_kernel(const BandParams p) {
+  extern __shared__ __align__(128) unsigned char band_smem[];
+  auto stage = [&](int i) { return reinterpret_cast<float *>(band_smem + (size_t)i * kBandStageBytes); };
+  uint64_t *full = reinterpret_cast<uint64_t *>(band_smem + (size_t)kBandStages * kBandStageBytes);
+  uint64_t *empty = full + kBandStages;
+  __shared__ float filt[kK * kK];
+  const int tid = threadIdx.x;
+  const UfdParams &u = p.u;
+  if (tid < kK * kK) {            // flipped, zero-extended taps: filt[jy][jx] multiplies x[oy - pad_y0 + jy][ox - pad_x0 + jx]
+    const int jy = tid / kK, jx = tid % kK;
+    filt[tid] = (jy < u.kh && jx < u.kw) ? __ldg(u.filt + (u.kh - 1 - jy) * u.kw + (u.kw - 1 - jx)) : 0.f;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kBandStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kBandThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long total_al = p.total_floats & ~3LL;
+
+  auto issue = [&](long long unit, int s) {     // thread 0 only
+    int oy0, iy_lo, iy_hi;
+    long long plane, g_lo, g_hi;
+    band_range(p, unit, oy0, iy_lo, iy_hi, plane, g_lo, g_hi);
+    const long long hi = g_hi < total_al ? g_hi : total_al;
+    const uint32_t bytes = hi > g_lo ? (uint32_t)((hi - g_lo) * 4) : 0u;
+    mbar_arrive_expect_tx(&full[s], bytes);
+    if (bytes) bulk_load_1d(stage(s), u.x + g_lo, bytes, &full[s]);
+  };
+
+  long long k = 0;
+  if (tid == 0)
+    for (int i = 0; i < kBandStages; ++i) {
+      const long long unit = blockIdx.x + (long long)i * gridDim.x;
+      if (unit < p.units) issue(unit, i);
+    }
+  float f[kK * kK];
+  for (long long unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++k) {
+    const int s = (int)(k % kBandStages);
+    const uint32_t phase = (uint32_t)((k / kBandStages) & 1);
+    int oy0, iy_lo, iy_hi;
+    long long plane, g_lo, g_hi;
+    band_range(p, unit, oy0, iy_lo, iy_hi, plane, g_lo, g_hi);
+    const int rows = min(p.toh, u.out_h - oy0);
+    mbar_wait(&full[s], phase);
+    float *sm = stage(s);
+    // the (< 16 byte) tail of the tensor that a bulk copy may not touch: plain loads by the first lanes
+    if (g_hi > total_al) {
+      const long long n_tail = p.total_floats - total_al;
+      if (tid < n_tail && total_al + tid >= g_lo) sm[total_al + tid - g_lo] = __ldg(u.x + total_al + tid);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < kK * kK; ++i) f[i] = filt[i];
+    const long long plane_base = plane * u.in_h * (long long)u.in_w;
+    const float *srow0 = sm + (plane_base - g_lo);                 // srow0[iy * in_w + ix] = x[plane, iy, ix]
+    float *yp = u.y + plane * u.out_h * (long long)u.out_w;
+    float bias = 0.f;
+    if (u.act != 0 && u.bias != nullptr) bias = __ldg(u.bias + (int)(plane % u.channels));
+    const int groups = (rows + kBandR - 1) / kBandR;
+    const int items = groups * u.out_w;
+    for (int it = tid; it < items; it += kBandThreads) {
+      const int g = it / u.out_w, ox = it - g * u.out_w;
+      const int r0 = oy0 + g * kBandR;                              // first output row of this item
+      const int nr = min(kBandR, oy0 + rows - r0);
+      const int cx = ox - u.pad_x0;                                  // input column of tap jx = 0
+      const bool in0 = cx >= 0 && cx < u.in_w, in1 = cx + 1 >= 0 && cx + 1 < u.in_w, in2 = cx + 2 >= 0 && cx + 2 < u.in_w,
+                 in3 = cx + 3 >= 0 && cx + 3 < u.in_w;
+      float acc[kBandR];
+#pragma unroll
+      for (int q = 0; q < kBandR; ++q) acc[q] = 0.f;
+      // input row r0 - pad_y0 + t (t = 0 .. nr + 2) is tap jy = t - q of output row r0 + q
+#pragma unroll
+      for (int t = 0; t < kBandR + kK - 1; ++t) {
+        const int iy = r0 - u.pad_y0 + t;
+        if (t < nr + kK - 1 && iy >= 0 && iy < u.in_h) {
+          const float *sr = srow0 + (long long)iy * u.in_w + cx;
+          const float v0 = in0 ? sr[0] : 0.f, v1 = in1 ? sr[1] : 0.f, v2 = in2 ? sr[2] : 0.f, v3 = in3 ? sr[3] : 0.f;
+#pragma unroll
+          for (int jy = 0; jy < kK; ++jy) {
+            const int q = t - jy;
+            if (q >= 0 && q < kBandR) {
+              float a = acc[q];
+              a = fmaf(v0, f[jy * kK + 0], a);
+              a = fmaf(v1, f[jy * kK + 1], a);
+              a = fmaf(v2, f[jy * kK + 2], a);
+              a = fmaf(v3, f[jy * kK + 3], a);
+              acc[q] = a;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kBandR; ++q) {
+        if (q < nr) {
+          float a = acc[q];
+          if (u.act != 0) {
+            a += bias;
+            a = (a > 0.f ? a : a * u.alpha) * u.scale;
+          }
+          st_stream_f1(yp + (long long)(r0 + q) * u.out_w + ox, a);
+        }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    if (tid == 0) {
+      const long long next = unit + (long long)kBandStages * gridDim.x;
+      if (next < p.units) {
+        mbar_wait(&empty[s], phase);
+        issue(next, s);
+      }
+    }
+  }
+}
+
+int launch_band(const UfdParams &u, cudaStream_t stream) {
+  BandParams p;
+  p.u = u;
+  const long long row_bytes = (long long)u.in_w * 4;
+  long long toh = (kBandStageBytes - 64) / row_bytes - (u.kh - 1);
+  if (toh < 1) return -1;                                   // a single band does not fit: caller falls back
+  if (toh > u.out_h) toh = u.out_h;
+  // enough units to keep every SM's ring busy
+  while (toh > kBandR && (long long)u.major * ((u.out_h + toh - 1) / toh) < 4LL * num_sms()) toh = (toh + 1) / 2;
+  if (toh > kBandR) toh = toh / kBandR * kBandR;
+  p.toh = (int)toh;
+  p.bands = (int)((u.out_h + toh - 1) / toh);
+  p.units = (long long)u.major * p.bands;
+  p.total_floats = (long long)u.major * u.in_h * u.in_w;
+  auto kern = upfirdn2d_band_kernel;
+  constexpr int smem = kBandStages * kBandStageBytes + 2 * kBandStages * 8;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  long long grid = p.units < num_sms() ? p.units : num_sms();
+  kern<<<(unsigned)grid, kBandThreads, smem, stream>>>(p);
+  return check_launch("upfirdn2d_band_kernel");
+}
+
 inline int pmod(int a, int m) { return ((a % m) + m) % m; }
 
 }  // namespace
@@ -898,7 +1090,15 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
   const bool small_filt = kh <= kK && kw <= kK;
   const bool sane_pad = pad_x0 > -(1 << 28) && pad_x0 < (1 << 28) && pad_y0 > -(1 << 28) && pad_y0 < (1 << 28);
   if (small_filt && sane_pad && in_h > 0 && in_w > 0) {
-    if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1) return dispatch_tile<1, 1, 0, 0>(p, stream);
+    if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1) {
+      // odd row pitch (no tensor map): contiguous row bands through 1-D bulk copies
+      static const bool no_band = getenv("VSP_NO_BAND") != nullptr;
+      if (!p.use_tma && !no_band && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && out_w >= 32 && major < (1LL << 31)) {
+        const int rc = launch_band(p, stream);
+        if (rc >= 0) return rc;
+      }
+      return dispatch_tile<1, 1, 0, 0>(p, stream);
+    }
     if (up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) return dispatch_tile<1, 2, 0, 0>(p, stream);
     if (up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1) {
       // tile origins are even, so the phase of the first tap is fixed by the pad parity

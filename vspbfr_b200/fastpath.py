@@ -139,7 +139,7 @@ class ModulationBank:
         self._build(styles.device, d, b)
         lib = _lib.load()
         y = torch.empty(self._total, dtype=torch.float32, device=styles.device)
-        with torch.cuda.device(styles.device):
+        with _lib.device_guard(styles.device):
             rc = lib.vsp_grouped_linear_f32(ptr(self._descs), ptr(self._rows), len(self.entries), self._rows_total,
                                             ptr(styles), n * d, ptr(y), b, stream_ptr())
         _lib.check(rc, "grouped_linear_f32")
@@ -148,7 +148,7 @@ class ModulationBank:
         if self._dem:
             y2 = y * y
             dpre = torch.empty(self._dtotal, dtype=torch.float32, device=styles.device)
-            with torch.cuda.device(styles.device):
+            with _lib.device_guard(styles.device):
                 rc = lib.vsp_grouped_linear_f32(ptr(self._ddescs), ptr(self._drows), len(self._dem), self._drows_total,
                                                 ptr(y2), 0, ptr(dpre), b, stream_ptr())
             _lib.check(rc, "grouped_linear_f32(demod)")
@@ -263,12 +263,12 @@ def upfirdn_nhwc(x, kernel, up=1, down=1, pad=(0, 0), epi=None):
     e, keep = epi if epi is not None else (None, None)
     taps = _separable_taps(kernel) if (up == 1 and down == 1 and _SEP_BLUR) else None
     if taps is not None:
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             rc = lib.vsp_blur_sep_nhwc_bf16(ptr(x), taps[0], taps[1], ptr(y), n, h, w, c, kh, kw, pad[0], pad[1], pad[0],
                                             pad[1], ctypes.byref(e) if e is not None else None, stream_ptr())
         _lib.check(rc, "blur_sep_nhwc_bf16")
         return y
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         rc = lib.vsp_upfirdn2d_nhwc_bf16(ptr(x), ptr(kernel), ptr(y), n, h, w, c, kh, kw, up, up, down, down,
                                          pad[0], pad[1], pad[0], pad[1],
                                          ctypes.byref(e) if e is not None else None, stream_ptr())
@@ -482,7 +482,7 @@ def _split3_nhwc(x, s=None):
     b, c, h, w = x.shape
     x = x.contiguous()
     y = torch.empty((b, h, w, 3 * c), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         rc = _lib.load().vsp_nchw_f32_to_nhwc_split3_bf16(ptr(x), ptr(s.contiguous()) if s is not None else None, ptr(y),
                                                           b, c, h * w, stream_ptr())
     _lib.check(rc, "nchw_f32_to_nhwc_split3_bf16")
@@ -598,7 +598,7 @@ def to_rgb(m: ToRGB, x, style, skip=None):
     if c != conv.in_channel:
         s = F.pad(s, (0, c - conv.in_channel))
     out = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         rc = _lib.load().vsp_torgb_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(res), ptr(out),
                                              b, h * w, c, conv.scale, stream_ptr())
     _lib.check(rc, "torgb_nhwc_bf16")
@@ -656,7 +656,7 @@ def to_rgb_pooled(m: ToRGB, x, style, skip):
     k3 = _cached(m.upsample, "pool_k3", [m.upsample.kernel], lambda: torch.tensor(
         list(_pool_upsample_taps(m.upsample)), dtype=torch.float32, device=x.device).view(3, 3).flip(0, 1).contiguous())
     res = upfirdn2d_raw(skip.contiguous(), k3, (1, 1), (1, 1), (1, 1, 1, 1))
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         rc = _lib.load().vsp_torgb_pool2_nhwc_bf16(ptr(x), ptr(w3), ptr(s.contiguous()), ptr(bias), ptr(res), None,
                                                    ptr(out), b, h // 2, w // 2, c, conv.scale, stream_ptr())
     _lib.check(rc, "torgb_pool2_nhwc_bf16")

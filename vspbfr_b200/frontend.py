@@ -147,7 +147,7 @@ class Encoder4Editing(nn.Module):
                 y = torch.empty_like(r)
                 zz = torch.empty_like(r) if i + 1 < n_units else None
                 a, b = affine[i + 1] if i + 1 < n_units else (None, None)
-                with torch.cuda.device(r.device):
+                with _lib.device_guard(r.device):
                     rc = lib.vsp_se_tail_nhwc_bf16(_lib.ptr(r), _lib.ptr(gate), _lib.ptr(sc), _lib.ptr(y), _lib.ptr(zz),
                                                    _lib.ptr(a), _lib.ptr(b), n, h, w, c, sc.stride(0), sc.stride(2),
                                                    sc.stride(3), _lib.stream_ptr())

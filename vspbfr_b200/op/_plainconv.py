@@ -151,7 +151,7 @@ def conv_weight_grad(grad_output, input, weight_shape, spec: ConvSpec):
         # RGB-side 1x1 layers (3 -> 16, 3 -> 64): a streaming reduction beats a GEMM whose N is 8 padded columns
         go, x = grad_output.contiguous(), input.contiguous()
         gw = torch.empty(weight_shape, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             rc = _lib.load().vsp_conv1x1_wgrad_small_f32(_lib.ptr(go), _lib.ptr(x), _lib.ptr(gw), n, c_pix, c_smp,
                                                          x.shape[2] * x.shape[3], _lib.stream_ptr())
         _lib.check(rc, "conv1x1_wgrad_small_f32")

@@ -49,7 +49,7 @@ def bias_act_raw(x, bias, ref, act, grad, alpha, scale):
     y = torch.empty_like(x)
     if n == 0:
         return y
-    with torch.cuda.device(x.device):
+    with _lib.device_guard(x.device):
         rc = _lib.load().vsp_bias_act_f32(_lib.ptr(x), _lib.ptr(bias), _lib.ptr(ref), _lib.ptr(y), n, step_b, size_b,
                                           act, grad, alpha, scale, _lib.stream_ptr())
     _lib.check(rc, "bias_act")
@@ -66,7 +66,7 @@ def bias_act_bwd_raw(grad_out, out, want_bias, alpha, scale):
         if dbias is not None:
             dbias.zero_()
         return dx, dbias
-    with torch.cuda.device(grad_out.device):
+    with _lib.device_guard(grad_out.device):
         rc = _lib.load().vsp_bias_act_bwd_f32(_lib.ptr(grad_out), _lib.ptr(out), _lib.ptr(dx), _lib.ptr(dbias),
                                               n, step_b, size_b, alpha, scale, _lib.stream_ptr())
     _lib.check(rc, "bias_act_bwd")
@@ -182,4 +182,6 @@ class FusedLeakyReLU(nn.Module):
 
 def fused_leaky_relu(input, bias=None, negative_slope=0.2, scale=2 ** 0.5):
     """op/fused_act.py:216-233 (CUDA branch)."""
+    if not (torch.is_grad_enabled() and (input.requires_grad or (bias is not None and bias.requires_grad))):
+        return bias_act_raw(input, bias, None, 3, 0, negative_slope, scale)     # nothing to record
     return FusedLeakyReLUFunction.apply(input.contiguous(), bias, negative_slope, scale)

@@ -90,7 +90,7 @@ def nchw_to_nhwc_bf16(x, scale_nc=None, c_pad=None, dot_with=None):
             dot_with = dot_with.contiguous()
             dot = torch.empty((n, c), dtype=torch.float32, device=x.device)
     if y.numel():
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             rc = _lib.load().vsp_nchw_f32_to_nhwc_bf16_dot(ptr(xc), ptr(scale_nc), ptr(dot_with), ptr(y),
                                                            ptr(dot) if dot_with is not None else None, n, c, h * w, c_pad,
                                                            stream_ptr())
@@ -118,7 +118,7 @@ def nhwc_bf16_to_nchw(x, c=None, scale_nc=None, dot_with=None):
     if scale_nc is not None:
         scale_nc = scale_nc.contiguous()
     if y.numel():
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             rc = _lib.load().vsp_nhwc_bf16_to_nchw_f32_dot(ptr(x.contiguous()), ptr(scale_nc), ptr(dot_with), ptr(y), ptr(dot),
                                                            n, c, h * w, c_pad, stream_ptr())
         _lib.check(rc, "nhwc_bf16_to_nchw_f32")
@@ -131,7 +131,7 @@ def nchw_to_bf16(x, scale_nc=None):
     x = x.contiguous()
     y = torch.empty_like(x, dtype=torch.bfloat16)
     if y.numel():
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             rc = _lib.load().vsp_nchw_f32_to_bf16(ptr(x), ptr(scale_nc), ptr(y), n * c, h * w, stream_ptr())
         _lib.check(rc, "nchw_f32_to_bf16")
     return y
@@ -142,7 +142,7 @@ def weight_sumsq(weight):
     cout, cin, kh, kw = weight.shape
     weight = weight.contiguous()
     wsq = torch.empty((cout, cin), dtype=torch.float32, device=weight.device)
-    with torch.cuda.device(weight.device):
+    with _lib.device_guard(weight.device):
         rc = _lib.load().vsp_weight_sumsq_f32(ptr(weight), ptr(wsq), cout, cin, kh * kw, stream_ptr())
     _lib.check(rc, "weight_sumsq_f32")
     return wsq
@@ -164,7 +164,7 @@ def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want
         style = style.contiguous()
     wq = torch.empty((g, taps, n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
     demod = torch.empty((g, cout), dtype=torch.float32, device=weight.device) if (want_demod or fold_demod) else None
-    with torch.cuda.device(weight.device):
+    with _lib.device_guard(weight.device):
         rc = _lib.load().vsp_modulate_weights_bf16(ptr(weight), ptr(style), ptr(demod), ptr(wq), g, cout, cin, taps,
                                                    wscale, eps, int(transpose), int(fold_demod), n_pad, k_pad,
                                                    ptr(wsq), stream_ptr())
@@ -226,7 +226,7 @@ def conv_fprop(x_nhwc, wq, cout, kh, kw, stride=1, pad=0, dil=1, epi=None, out=N
             out = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=x_nhwc.device)
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         # algo_cin: channels of the layer this launch stands for when the operand carries extra terms (two-term operands)
         rc = _prof("conv_fprop", 2.0 * b * oh * ow * cout * (algo_cin or cin) * kh * kw, lambda: _lib.load().vsp_conv2d_fprop_bf16(
             ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, stride, pad, dil, int(out_nhwc),
@@ -253,7 +253,7 @@ def conv_gather(x_nhwc, wq, cout, tap_w, tap_dy, tap_dx, stride, out_hw, full_hw
             out = torch.zeros((b, cout, fh, fw), dtype=torch.float32, device=x_nhwc.device)
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         rc = _lib.load().vsp_conv2d_gather_bf16(ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad,
                                                 taps_total, len(tap_w), _int_array(tap_w), _int_array(tap_dy),
                                                 _int_array(tap_dx), stride, oh, ow, int(out_nhwc), fh, fw, os_,
@@ -280,7 +280,7 @@ def conv_transpose_s2(x_nhwc, wq, cout, kh, kw, epi=None, out_nhwc=False):
             out.zero_()
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         rc = _prof("conv_transpose_s2", 2.0 * b * h * w * cout * cin * kh * kw,
                    lambda: _lib.load().vsp_conv_transpose2d_s2_bf16(
                        ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, cout_pad, kh, kw, int(out_nhwc), ldo, 0,
@@ -298,7 +298,7 @@ def scale_nhwc(x_nhwc, s):
         s = torch.nn.functional.pad(s, (0, c - s.shape[1]))
     s = s.contiguous()
     y = torch.empty_like(x_nhwc)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         rc = _lib.load().vsp_scale_nhwc_bf16(ptr(x_nhwc), ptr(s), ptr(y), b, h * w, c, stream_ptr())
     _lib.check(rc, "scale_nhwc_bf16")
     return y
@@ -309,7 +309,7 @@ def demod_from_wsq(s, wsq, wscale, eps=1e-8):
     b, cin = s.shape
     cout = wsq.shape[0]
     d = torch.empty((b, cout), dtype=torch.float32, device=s.device)
-    with torch.cuda.device(s.device):
+    with _lib.device_guard(s.device):
         rc = _lib.load().vsp_modulate_weights_bf16(ptr(wsq), ptr(s.contiguous()), ptr(d), None, b, cout, cin, 1, wscale, eps,
                                                    0, 0, cout, cin, ptr(wsq), stream_ptr())
     _lib.check(rc, "modulate_weights_bf16(demod)")
@@ -327,7 +327,7 @@ def conv_branches(x_nhwc, wq, cout, dils, epi=None, out=None, out_nhwc=True, co_
     ldo = out.shape[3] if out_nhwc else cout
     e, keep = epi if epi is not None else (None, None)
     dl = _int_array(dils)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         rc = _prof("conv_branches", 2.0 * b * h * w * cout * (algo_cin or cin) * 9, lambda: _lib.load().vsp_conv2d_branches_bf16(
             ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, len(dils), dl, int(out_nhwc), ldo, co_off,
             ctypes.byref(e) if e is not None else None, stream_ptr()),
@@ -366,7 +366,7 @@ def conv_up2_fused(x_nhwc, wq, cout, epi=None, out=None, co_off=0):
     if out is None:
         out = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x_nhwc.device)
     e, keep = epi if epi is not None else (None, None)
-    with torch.cuda.device(x_nhwc.device):
+    with _lib.device_guard(x_nhwc.device):
         # algorithmic FLOPs of the layer it replaces (the transposed conv); the dense form executes 4x as many
         rc = _prof("conv_up2_fused", 2.0 * b * h * w * cout * cin * 9,
                    lambda: _lib.load().vsp_conv2d_up2_fused_bf16(
@@ -386,7 +386,7 @@ def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
     _, h, w, cin = x_nhwc.shape
     gw = torch.empty((groups, kh * kw, cout, cin), dtype=torch.float32, device=dy_nhwc.device)
     (ph, pw), (dh, dw) = (pad if isinstance(pad, tuple) else (pad, pad)), (dil if isinstance(dil, tuple) else (dil, dil))
-    with torch.cuda.device(dy_nhwc.device):
+    with _lib.device_guard(dy_nhwc.device):
         rc = _lib.load().vsp_conv2d_wgrad_bf16(ptr(dy_nhwc), ptr(x_nhwc), ptr(gw), b, groups, h, w, cin, cout,
                                                oh, ow, kh, kw, stride, ph, pw, dh, dw, stream_ptr())
     _lib.check(rc, "conv2d_wgrad_bf16")

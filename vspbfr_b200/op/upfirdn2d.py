@@ -38,8 +38,8 @@ def upfirdn2d_raw(input, kernel, up, down, pad, bias=None, act=0, alpha=0.2, sca
     n, c, in_h, in_w = input.shape
     kh, kw = kernel.shape
     lib = _lib.load()
-    out_h = lib.vsp_upfirdn2d_out_size(in_h, kh, up_y, down_y, pad_y0, pad_y1)
-    out_w = lib.vsp_upfirdn2d_out_size(in_w, kw, up_x, down_x, pad_x0, pad_x1)
+    out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) // down_y          # op/upfirdn2d.py:301-302 (== vsp_upfirdn2d_out_size)
+    out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) // down_x
     x = input.contiguous()
     k = kernel.contiguous()
     out = torch.empty((n, c, max(out_h, 0), max(out_w, 0)), dtype=torch.float32, device=input.device)
@@ -47,7 +47,7 @@ def upfirdn2d_raw(input, kernel, up, down, pad, bias=None, act=0, alpha=0.2, sca
         return out
     if bias is not None:
         bias = bias.contiguous()
-    with torch.cuda.device(input.device):
+    with _lib.device_guard(input.device):
         rc = lib.vsp_upfirdn2d_f32(_lib.ptr(x), _lib.ptr(k), _lib.ptr(out), n * c, in_h, in_w, kh, kw,
                                    up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1,
                                    _lib.ptr(bias), c, act, alpha, scale, _lib.stream_ptr())
@@ -96,7 +96,8 @@ class UpFirDn2d(Function):
                      in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
                      kernel_h - pad_y0 - 1,
                      in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        # the flipped filter is only needed by the backward (the reference flips on every call, :299)
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]) if ctx.needs_input_grad[0] else kernel)
         return out
 
     @staticmethod
@@ -123,6 +124,8 @@ def _normalize(up, down, pad):
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     """Same signature and semantics as op/upfirdn2d.py:346-362 (CUDA only)."""
     up, down, pad = _normalize(up, down, pad)
+    if not (torch.is_grad_enabled() and input.requires_grad):
+        return upfirdn2d_raw(input, kernel, up, down, pad)          # nothing to record: skip the autograd.Function round trip
     return UpFirDn2d.apply(input, kernel, up, down, pad)
 
 
