@@ -327,6 +327,23 @@ int vsp_conv2d_up2_fused_bf16(const void *x, const void *wq, void *out,
                               const vsp_conv_epilogue *epi, void *stream);
 
 /*
+ * The same up-sampling layer (conv_transpose2d stride 2, 3x3 -> Blur 4x4 pad 1, models/RestoreNet.py:522-535) at HALF the
+ * dense form's tensor work, for the wide levels (in_w >= 128; cin = 64 or 128; cout % 32 == 0; in_w % 32 == 0): only the
+ * HORIZONTAL half of the separable blur is composed into the weights, the vertical 4-tap half is applied in the epilogue
+ * to fp32 accumulators while the CTA walks down a 128-column strip (conv_up2h_sm100.cu).
+ *   wq  [groups, 9, 2*cout, cin] bf16: vsp_modulate_weights_bf16 applied to the horizontally composed weights
+ *       Wc[q*cout + o, i, kh, dx] = sum_{v, kw : q + v - 1 - kw = 2 (dx - 1)} fx[3 - v] * W[o, i, kh, kw]
+ *       (W = the transposed convolution's [cout, cin, 3, 3] weights, fx = horizontal factor of the blur filter)
+ *   ky_host [4] (HOST memory): vertical factor of the blur as applied, out[y] = sum_u ky[u] * hz[y + u - 1]
+ *       (= the flipped vertical factor; the model's filters are symmetric)
+ *   out [batch, 2*in_h, 2*in_w, ldo] bf16 NHWC; epilogue as vsp_conv2d_up2_fused_bf16 (no first activation stage)
+ */
+int vsp_conv2d_up2h_bf16(const void *x, const void *wq, void *out,
+                         int64_t batch, int64_t groups, int64_t in_h, int64_t in_w,
+                         int64_t cin, int64_t cout, int64_t ldo, int64_t co_off,
+                         const float *ky_host, const vsp_conv_epilogue *epi, void *stream);
+
+/*
  * The four dilated branches of a SMART_layer (models/RestoreNet.py:196-209,229-233: Dilated_ModulatedConv2d x4 ->
  * torch.cat) as ONE launch: branch j is a 3x3 stride-1 convolution with dilation = padding = dils[j] producing
  * channels [j*cout/n, (j+1)*cout/n) of the output (channel tile = branch; no torch.cat, one wave of tiles).

@@ -534,6 +534,58 @@ def test_up2_fused_matches_transposed_conv_then_blur(b, cin, cout, h, w_, per_sa
     assert psnr(got, want) > 45.0
 
 
+@pytest.mark.parametrize("b,cin,cout,h,w_", [(2, 64, 32, 9, 128), (1, 128, 64, 7, 256), (2, 64, 64, 33, 160), (1, 128, 32, 5, 384),
+                                             (3, 64, 32, 4, 128), (1, 64, 32, 70, 512)])
+@pytest.mark.parametrize("per_sample", [False, True])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_up2h_half_composed_up_convolution(b, cin, cout, h, w_, per_sample, with_res):
+    """vsp_conv2d_up2h_bf16 (horizontal blur in the weights, vertical blur in the epilogue from a TMEM ring) against the
+    reference formulation conv_transpose2d(stride 2) -> upfirdn2d blur pad (1,1) with the StyledConv(up) tail, and tightly
+    against an fp32 emulation on the same bf16-rounded operands (asymmetric filter: flips and tap order must be right)."""
+    from oracle import upfirdn2d_ref
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + h + w_)
+    x = torch.randn(b, cin, h, w_, generator=g).to(DEV)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(DEV)
+    fy, fx = torch.tensor([1.0, 3.0, 4.0, 2.0]), torch.tensor([2.0, 5.0, 3.0, 1.0])
+    fy, fx = fy / fy.sum() * 2, fx / fx.sum() * 2
+    k4 = torch.outer(fy, fx).to(DEV)
+    s = (torch.randn(b, cin, generator=g) * 0.3 + 1).to(DEV) if per_sample else None
+    noise = torch.randn(b, 1, 2 * h, 2 * w_, generator=g).to(DEV)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    rs = (torch.rand(b, cout, generator=g) + 0.5).to(DEV)
+    res = torch.randn(b, cout, 2 * h, 2 * w_, generator=g).to(DEV)
+    res2 = torch.randn(b, cout, 2 * h, 2 * w_, generator=g).to(DEV)
+    assert mc.up2h_supported(cin, cout, h, w_)
+    wc = mc.compose_up2h_weights(wt, fx.tolist())
+    wq, _ = mc.pack_weights(wc, s)
+    xq = mc.nchw_to_nhwc_bf16(x)
+    kw = dict(residual=mc.nchw_to_nhwc_bf16(res), residual2=mc.nchw_to_nhwc_bf16(res2)) if with_res else {}
+    epi = mc.make_epilogue(row_scale=rs, noise=noise, noise_weight=0.3, bias=bias, act=3, alpha=0.2, scale=math.sqrt(2), **kw)
+    ky = [float(fy[3 - u]) for u in range(4)]
+    out = mc.conv_up2h(xq, wq, cout, ky, epi=epi)
+    assert out.shape == (b, 2 * h, 2 * w_, cout)
+    got = out.permute(0, 3, 1, 2).float()
+    tail = (bf16r(res) + bf16r(res2)) if with_res else 0.0
+    # tight: fp32 emulation of the kernel's own decomposition on the bf16-rounded composed weights
+    from test_up2h_cpu import emulate_up2h
+    zs = []
+    for i in range(b):
+        wi = wr(wc * s[i][None, :, None, None]) if per_sample else wr(wc)
+        zs.append(emulate_up2h(bf16r(x[i:i + 1]).double().cpu(), wi.double().cpu(), ky, cout).float().to(DEV))
+    z = torch.cat(zs)
+    want_t = F.leaky_relu(z * rs[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2) + tail
+    assert_close_tight(got, want_t, tol=1e-2)
+    # reference formulation (3x3 weights un-rounded, blur in fp32)
+    ys = []
+    for i in range(b):
+        wi = wt * s[i][None, :, None, None] if per_sample else wt
+        ys.append(F.conv_transpose2d(bf16r(x[i:i + 1]), wi.transpose(0, 1), stride=2))
+    yb = torch.from_numpy(upfirdn2d_ref(torch.cat(ys).cpu().numpy(), k4.cpu().numpy(), 1, 1, (1, 1))).to(DEV)
+    want = F.leaky_relu(yb * rs[:, :, None, None] + 0.3 * noise + bias[None, :, None, None], 0.2) * math.sqrt(2) + tail
+    assert_close_tight(got, want, tol=2e-2)
+    assert psnr(got, want) > 45.0
+
+
 @pytest.mark.parametrize("b,cin,cq,h,w_", [(8, 512, 128, 4, 4), (3, 512, 128, 8, 8), (2, 128, 32, 16, 16), (2, 64, 16, 32, 32),
                                            (2, 256, 64, 64, 64), (5, 64, 64, 4, 8),
                                            # wide 16/32-channel branches -> branch slices of the kh-folded row-ring kernel

@@ -29,6 +29,7 @@ SOURCES = [
     "layout_sm100.cu",
     "conv_sm100.cu",
     "conv_ring_sm100.cu",
+    "conv_up2h_sm100.cu",
     "wgrad_sm100.cu",
     "torgb_sm100.cu",
     "linear_sm100.cu",
@@ -188,6 +189,8 @@ SIGNATURES = {
     "vsp_grouped_linear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "vsp_conv2d_up2_fused_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                           c_int64, c_int64, c_int64, POINTER(ConvEpilogue), c_void_p]),
+    "vsp_conv2d_up2h_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                     c_int64, c_int64, c_int64, POINTER(c_float), POINTER(ConvEpilogue), c_void_p]),
     "vsp_torgb_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vsp_torgb_pool2_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_float), c_void_p,

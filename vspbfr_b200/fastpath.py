@@ -29,6 +29,7 @@ _cache: dict = {}
 # ModulatedConv2d(upsample=True) layers with Cin up to this run as the fused up-convolution (4x the transposed
 # conv's FLOPs, but no (2H+1)^2 intermediate and no blur pass): a win wherever the layer is bandwidth-bound
 _UP_FUSED_MAX_CIN = int(os.environ.get("VSP_UP_FUSED_MAX_CIN", "256"))
+_UP2H = os.environ.get("VSP_UP2H", "1") != "0"          # half-composed up-convolution on the wide levels (conv_up2h_sm100.cu)
 # Activations with at most this many pixels per sample run in the input-modulated form (x * s, shared cached
 # weights, demodulation in the epilogue: models/RestoreNet.py:481-508): below it the per-sample weight prologue
 # costs more than scaling the activation, and shared weights let one 128-row tile stack several samples
@@ -338,6 +339,20 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
             nz = _noise_for(noise, b, h, w, x.device)
             return mc.conv_fprop(xs, wqs, cout, k, k, 1, conv.padding, 1, out_nhwc=True,
                                  epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual, residual2=residual2, **act))
+    if (conv.upsample and k == 3 and _UP2H and x.shape[3] == cin and mc.up2h_supported(cin, cout, h, w)
+            and tuple(conv.blur.pad) == (1, 1) and tuple(conv.blur.kernel.shape) == (4, 4)
+            and _separable_taps(conv.blur.kernel) is not None):
+        # wide levels: horizontal half of the blur in the weights, vertical half in the epilogue (2x instead of 4x the FLOPs)
+        fy, fx = _separable_taps(conv.blur.kernel)
+        wc = _cached(conv, "w_up2h", [conv.weight, conv.blur.kernel], lambda: mc.compose_up2h_weights(w4, list(fx)))
+        ky = _cached(conv, "ky_up2h", [conv.blur.kernel], lambda: (ctypes.c_float * 4)(*[float(fy[3 - u]) for u in range(4)]))
+        wq2, _ = mc.pack_weights(wc, s, wscale=conv.scale)
+        d = None
+        if conv.demodulate:
+            d = d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, conv.scale, conv.eps)
+        nz = _noise_for(noise, b, 2 * h, 2 * w, x.device)
+        return mc.conv_up2h(x, wq2, cout, ky, epi=mc.make_epilogue(row_scale=d, noise=nz, residual=residual,
+                                                                    residual2=residual2, **act))
     if conv.upsample and k == 3 and cin <= _UP_FUSED_MAX_CIN and cout % 32 == 0 and w >= 32:
         # transposed conv + blur as ONE dense conv with the composite weights and a pixel-shuffle epilogue
         w3 = _cached(conv, "w_up2", [conv.weight, conv.blur.kernel], lambda: mc.compose_up2_weights(w4, conv.blur.kernel))

@@ -378,6 +378,54 @@ def conv_up2_fused(x_nhwc, wq, cout, epi=None, out=None, co_off=0):
     return out
 
 
+def compose_up2h_weights(weight, fx):
+    """Weights of `conv_transpose2d(stride=2, 3x3)` composed with the HORIZONTAL factor of the blur only (the vertical factor
+    is applied by the kernel's epilogue, see vsp_conv2d_up2h_bf16).
+
+    weight [Cout, Cin, 3, 3] (ModulatedConv2d.weight[0]), fx: the 4 horizontal taps (blur == outer(fy, fx))
+    -> [2*Cout, Cin, 3, 3] with row q*Cout + o (q = output column parity) and tap (kh, dx + 1), dx = -1..1 on the low-res grid:
+    hz[2a+pa][2j+q] = sum_{kh = pa (mod 2)} sum_dx x[a - (kh-pa)/2][j + dx] * Wc[q*Cout + o, :, kh, dx + 1],
+    Wc[.., kh, dx + 1] = sum_{v, kw : q + v - 1 - kw = 2 dx} fx[3 - v] * W[.., kh, kw]   (upfirdn2d correlates with the flip).
+    """
+    cout, cin, kh, kw = weight.shape
+    assert kh == 3 and kw == 3 and len(fx) == 4
+    w = weight.double()
+    out = torch.zeros((2, cout, cin, 3, 3), dtype=torch.float64, device=weight.device)
+    for q in range(2):
+        for v in range(4):
+            for kwi in range(3):
+                t = q + v - 1 - kwi
+                if t % 2 == 0 and -1 <= t // 2 <= 1:
+                    out[q, :, :, :, t // 2 + 1] += float(fx[3 - v]) * w[:, :, :, kwi]
+    return out.reshape(2 * cout, cin, 3, 3).float().contiguous()
+
+
+def up2h_supported(cin, cout, h, w):
+    """Shapes vsp_conv2d_up2h_bf16 takes (the wide levels of both networks)."""
+    return cin in (64, 128) and cout % 32 == 0 and w >= 128 and w % 32 == 0 and h >= 4
+
+
+def conv_up2h(x_nhwc, wq, cout, ky, epi=None, out=None, co_off=0):
+    """Up-sampling conv with the horizontal blur in the weights and the vertical blur in the epilogue (see
+    vsp_conv2d_up2h_bf16): x [B,H,W,Cin] -> [B,2H,2W,ldo] NHWC bf16.  ``ky``: 4 vertical taps as applied (host floats)."""
+    b, h, w, cin = x_nhwc.shape
+    g, taps, rows, k_pad = wq.shape
+    assert taps == 9 and k_pad == cin and rows == 2 * cout, (wq.shape, cout)
+    if out is None:
+        out = torch.empty((b, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    e, keep = epi if epi is not None else (None, None)
+    kyc = ky if isinstance(ky, ctypes.Array) else (ctypes.c_float * 4)(*[float(v) for v in ky])
+    with _lib.device_guard(x_nhwc.device):
+        rc = _prof("conv_up2_fused", 2.0 * b * h * w * cout * cin * 9,
+                   lambda: _lib.load().vsp_conv2d_up2h_bf16(
+                       ptr(x_nhwc), ptr(wq), ptr(out), b, g, h, w, cin, cout, out.shape[3], co_off, kyc,
+                       ctypes.byref(e) if e is not None else None, stream_ptr()),
+                   detail=f"b{b} {cin}->{cout} up2-hfold {h}x{w} g{g}",
+                   nbytes=2.0 * b * (h * w * cin + 4 * h * w * cout))
+    _lib.check(rc, "conv2d_up2h_bf16")
+    return out
+
+
 def conv_wgrad(dy_nhwc, x_nhwc, groups, kh, kw, stride, pad, dil):
     """gw[g,t,o,i] = sum_p dy[b,p,o] x[b, p*stride + t*dil - pad, i] (tap-major); groups == batch or 1; ``pad`` / ``dil``
     are ints or per-axis (h, w) pairs.
