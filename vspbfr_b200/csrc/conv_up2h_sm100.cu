@@ -174,6 +174,7 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc128 = umma_idesc_bf16(kBlockM, 4 * kUpC);
     constexpr uint32_t idesc64 = umma_idesc_bf16(kBlockM, 2 * kUpC);
+    constexpr uint32_t idesc192 = umma_idesc_bf16(kBlockM, 6 * kUpC);
     const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
     int aslot = 0;
     uint32_t aph = 0, res_ph = 0;
@@ -211,6 +212,7 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t d_own = tmem_base + (uint32_t)(((row0 + k) % kUpNR) * kUpSlotCols);
           const uint32_t d_next = tmem_base + (uint32_t)(((row0 + k + 1) % kUpNR) * kUpSlotCols);
           const bool has_next = k + 1 < rows;
+          const bool joined = has_next && (int)((row0 + k) % kUpNR) != kUpNR - 1;   // slot r+1 is the next 128 columns
           int s = s0;
           for (int cb = 0; cb < kc; ++cb) {
             const uint32_t arow = a_base + (uint32_t)s * kUpSlotBytes;
@@ -225,14 +227,29 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
               for (int ks = 0; ks < kBlockK / kUmmaK; ++ks) {
                 const bool first = cb == 0 && dx == 0 && ks == 0;
                 const uint64_t ko = (uint64_t)(2 * ks);
-                if (has_next) umma_bf16_ss(d_next, adesc + ko, b2 + ko, idesc64, first ? 0u : 1u);   // E[r+1] = T2[r] (first write)
-                if (k == 0) {
-                  umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc128, first ? 0u : 1u);     // unit's first row: plain first write
+                // Slot r+1 starts right after slot r in TMEM, so [E_r | O_r | E_{r+1}] = [T0 | T1 | T2] is ONE N = 192
+                // MMA (the activation slab is fetched once per k-step) except across the ring wrap; only the very first
+                // k-step of a row is split, because E_r accumulates while O_r and E_{r+1} are written for the first time.
+                if (k == 0) {                   // unit's first row: every target is a first write
+                  if (joined) {
+                    umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc192, first ? 0u : 1u);
+                  } else {
+                    umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc128, first ? 0u : 1u);
+                    if (has_next) umma_bf16_ss(d_next, adesc + ko, b2 + ko, idesc64, first ? 0u : 1u);
+                  }
                 } else if (first) {
-                  umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc64, 1u);                   // E[r] += T0[r]
-                  umma_bf16_ss(d_own + 2 * kUpC, adesc + ko, b1 + ko, idesc64, 0u);         // O[r]  = T1[r] (first write)
+                  umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc64, 1u);                     // E[r] += T0[r]
+                  if (joined) {
+                    umma_bf16_ss(d_own + 2 * kUpC, adesc + ko, b1 + ko, idesc128, 0u);        // O[r] | E[r+1] = T1 | T2
+                  } else {
+                    umma_bf16_ss(d_own + 2 * kUpC, adesc + ko, b1 + ko, idesc64, 0u);         // O[r]  = T1[r]
+                    if (has_next) umma_bf16_ss(d_next, adesc + ko, b2 + ko, idesc64, 0u);     // E[r+1] = T2[r]
+                  }
+                } else if (joined) {
+                  umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc192, 1u);
                 } else {
                   umma_bf16_ss(d_own, adesc + ko, b01 + ko, idesc128, 1u);
+                  if (has_next) umma_bf16_ss(d_next, adesc + ko, b2 + ko, idesc64, 1u);
                 }
               }
             }
