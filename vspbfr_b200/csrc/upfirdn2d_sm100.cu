@@ -860,26 +860,33 @@ int dispatch_tile(const UfdParams &p, cudaStream_t stream) {
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row-band kernel for up = down = 1 on planes whose row pitch is NOT a multiple of 16 bytes (the model's blurs on odd
-// extents: [.,.,65,65], [.,.,1025,1025], [.,.,513,513] ...), where no tensor map exists and the tile kernel fell back to
-// per-element LDG staging (0.27-0.44 of HBM).  A band of TOH output rows spans the whole width, so the input rows it needs
-// are ONE contiguous byte range of the plane: it is brought in by a single 1-D bulk copy (cp.async.bulk, 16-byte aligned by
-// over-fetching <= 12 bytes at each end) into a 3-stage mbarrier ring — no address arithmetic, predicates or registers on the
-// load side, every input row read once per band (+ kh - 1 halo rows).  Compute: thread = (output column, group of kBandR
-// rows); consecutive lanes own consecutive columns (conflict-free scalar LDS, 128-byte coalesced stores); an input row's four
-// values feed the rolling accumulators of the <= 4 output rows that use it, in the reference's tap order (ky outer, kx
-// inner), so results are bit-identical to the generic kernel.
-constexpr int kBandThreads = 512;
+// Row-band kernel for up = down = 1 (the model's Blur: models/RestoreNet.py:84-101 after every transposed / before every
+// strided convolution, almost always on ODD extents — [.,.,65,65], [.,.,513,513], [.,.,1025,1025] — whose row pitch no
+// tensor map can describe).  A unit is a run of whole input rows of the flat tensor — R output rows (+ kh-1 halo rows)
+// of one wide plane, or several whole small planes — i.e. ONE contiguous byte range, brought in by a single 1-D bulk copy
+// (cp.async.bulk, 16-byte aligned by over-fetching <= 12 bytes at each end) into a 3-stage mbarrier ring by a producer
+// warp: no address arithmetic, predicates or registers on the load side, every input row read once per unit.
+// Compute (16 warps): item = (output column, group of R rows); the 32 lanes of a warp own 32 consecutive columns
+// (conflict-free scalar LDS, 128-byte coalesced stores), warps take 32-item chunks round-robin with a rotation per unit so
+// that ragged chunk counts (1026 columns = 32 chunks + 2 columns) average out over the ring instead of idling 15 warps.
+// The filter is factorised in the kernel (rank-1 test on the 16 taps): separable filters — every filter the model
+// builds, make_kernel's outer([1,3,3,1]) — take one 4-tap horizontal pass per input row and a vertical scatter into
+// the rolling accumulators of the <= 4 output rows that use it (8 FMAs per output instead of 16; fp32 results differ from
+// the 2-D tap order by rounding only); other filters run the 2-D form.
+constexpr int kBandWarps = 16;
+constexpr int kBandThreads = (kBandWarps + 1) * 32;   // + producer warp
 constexpr int kBandStages = 3;
-constexpr int kBandStageBytes = 73728;          // 3 x 72 KiB + barriers < 227 KiB
-constexpr int kBandR = 8;                       // output rows per thread item
+constexpr int kBandStageBytes = 73728;                // 3 x 72 KiB + barriers < 227 KiB
+constexpr int kBandR = 8;                             // output rows per item
 
 struct BandParams {
   UfdParams u;
-  int toh;                  // output rows per band
-  int bands;                // bands per plane
-  long long units;          // planes x bands
+  int P;                    // whole planes per unit (> 1 only when a plane is small)
+  int G;                    // row groups per unit
+  int upp;                  // units per plane (P == 1)
+  long long units;
   long long total_floats;   // elements of x (bulk copies never read past the last whole 16 bytes)
+  unsigned magic_ow, magic_pp;   // floor(2^32 / d) + 1 for d = out_w and d = G * out_w (items per plane when P > 1)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -888,19 +895,178 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                : "memory");
 }
 
-// input rows [iy_lo, iy_hi) of band `j` and the aligned float range [g_lo, g_hi) of x that holds them
-__device__ __forceinline__ void band_range(const BandParams &p, long long unit, int &oy0, int &iy_lo, int &iy_hi,
-                                           long long &plane, long long &g_lo, long long &g_hi) {
-  plane = unit / p.bands;
-  const int j = (int)(unit % p.bands);
-  oy0 = j * p.toh;
-  const int rows = min(p.toh, p.u.out_h - oy0);
-  iy_lo = max(0, oy0 - p.u.pad_y0);
-  iy_hi = min(p.u.in_h, oy0 + rows - 1 - p.u.pad_y0 + p.u.kh);
-  if (iy_hi < iy_lo) iy_hi = iy_lo;
-  const long long base = plane * p.u.in_h * (long long)p.u.in_w;
-  g_lo = (base + (long long)iy_lo * p.u.in_w) & ~3LL;
-  g_hi = (base + (long long)iy_hi * p.u.in_w + 3) & ~3LL;
+struct BandUnit {
+  long long plane0;         // first plane
+  int np;                   // planes in the unit
+  int oy0, rows;            // output rows [oy0, oy0 + rows) of each plane
+  int iy_lo, iy_hi;         // input rows [iy_lo, iy_hi) of each plane held in the stage
+  long long g_lo, g_hi;     // aligned float range of x in shared memory
+};
+
+__device__ __forceinline__ BandUnit band_unit(const BandParams &p, long long unit) {
+  BandUnit b;
+  const UfdParams &u = p.u;
+  int iy_hi;
+  if (p.P > 1) {
+    b.plane0 = unit * p.P;
+    b.np = (int)min((long long)p.P, u.major - b.plane0);
+    b.oy0 = 0; b.rows = u.out_h;
+    b.iy_lo = 0; iy_hi = u.in_h;
+    b.iy_hi = iy_hi;
+  } else {
+    b.plane0 = unit / p.upp;
+    b.np = 1;
+    b.oy0 = (int)(unit % p.upp) * p.G * kBandR;
+    b.rows = min(p.G * kBandR, u.out_h - b.oy0);
+    b.iy_lo = max(0, b.oy0 - u.pad_y0);
+    iy_hi = min(u.in_h, b.oy0 + b.rows - 1 - u.pad_y0 + u.kh);
+    if (iy_hi < b.iy_lo) iy_hi = b.iy_lo;
+    b.iy_hi = iy_hi;
+  }
+  const long long plane_sz = (long long)u.in_h * u.in_w;
+  b.g_lo = (b.plane0 * plane_sz + (long long)b.iy_lo * u.in_w) & ~3LL;
+  b.g_hi = ((b.plane0 + b.np - 1) * plane_sz + (long long)iy_hi * u.in_w + 3) & ~3LL;
+  return b;
+}
+
+// Compute side of the band kernel.  SEP: the filter is fy (x) fx.  Interior items (all taps inside the image, full row
+// group) run a predicate-free body: one shared-memory pointer bumped by the row pitch, four LDS at immediate offsets, the
+// horizontal 4-tap product and the vertical scatter — 13 instructions per input row and column; items touching the image
+// border take the predicated form.
+template <bool SEP>
+__device__ __forceinline__ void band_compute(const BandParams &p, unsigned char *band_smem, uint64_t *full, uint64_t *empty,
+                                             const float *filt, const float *sep) {
+  const UfdParams &u = p.u;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  float fy[kK], fx[kK], w2[SEP ? 1 : kK * kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) { fy[j] = sep[j]; fx[j] = sep[kK + j]; }
+  if constexpr (!SEP) {
+#pragma unroll
+    for (int j = 0; j < kK * kK; ++j) w2[j] = filt[j];
+  }
+  const long long total_al = p.total_floats & ~3LL;
+  const long long plane_sz = (long long)u.in_h * u.in_w;
+  const int in_w = u.in_w, in_h = u.in_h, out_w = u.out_w;
+  long long k = 0;
+  for (long long unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++k) {
+    const int s = (int)(k % kBandStages);
+    const BandUnit b = band_unit(p, unit);
+    mbar_wait(&full[s], (uint32_t)((k / kBandStages) & 1));
+    float *sm = reinterpret_cast<float *>(band_smem + (size_t)s * kBandStageBytes);
+    if (b.g_hi > total_al) {        // the (< 16 byte) tail of the tensor that a bulk copy may not touch: plain loads
+      const long long n_tail = p.total_floats - total_al;
+      if (tid < n_tail && total_al + tid >= b.g_lo) sm[total_al + tid - b.g_lo] = __ldg(u.x + total_al + tid);
+      asm volatile("bar.sync 1, %0;" ::"n"(kBandWarps * 32) : "memory");
+    }
+    const int groups = (b.rows + kBandR - 1) / kBandR;
+    const int per_plane = groups * out_w;
+    const int items = b.np * per_plane;
+    const int chunks = (items + 31) >> 5;
+    const int rot = (int)((k * 5) & (kBandWarps - 1));
+    const int base0 = (int)(b.plane0 * plane_sz - b.g_lo);           // smem index of x[plane0, 0, 0] (may be negative)
+    // rows of each plane that the stage holds (loads outside the image are clamped into this range, then discarded)
+    const int ylo = b.iy_lo, yhi = b.iy_hi;
+    for (int c = (warp - rot) & (kBandWarps - 1); c < chunks; c += kBandWarps) {
+      const int it = c * 32 + lane;
+      const bool live = it < items;
+      // (plane, row group, column) of the item: multiply-high by host-computed reciprocals (exact for it * divisor < 2^32)
+      int pl = 0, rem = live ? it : 0;
+      if (p.P > 1) {
+        pl = (int)__umulhi((unsigned)rem, p.magic_pp);
+        rem -= pl * per_plane;
+      }
+      const int g = (int)__umulhi((unsigned)rem, p.magic_ow), ox = rem - g * out_w;
+      const int r0 = b.oy0 + g * kBandR;                            // first output row of this item
+      const int nr = live ? min(kBandR, b.oy0 + b.rows - r0) : 0;
+      const int cx = ox - u.pad_x0;                                  // input column of tap jx = 0
+      const int iy0 = r0 - u.pad_y0;                                 // input row of tap jy = 0 of output row r0
+      const float *colp = sm + (base0 + pl * (int)plane_sz + cx);    // &x[plane, 0, cx]
+      float acc[kBandR];
+#pragma unroll
+      for (int q = 0; q < kBandR; ++q) acc[q] = 0.f;
+      const bool interior = nr == kBandR && cx >= 0 && cx + kK - 1 < in_w && iy0 >= 0 && iy0 + kBandR + kK - 2 < in_h;
+      if (__all_sync(0xffffffffu, interior)) {
+        const float *sr = colp + iy0 * in_w;
+#pragma unroll
+        for (int t = 0; t < kBandR + kK - 1; ++t) {
+          const float v0 = sr[0], v1 = sr[1], v2 = sr[2], v3 = sr[3];
+          sr += in_w;
+          if constexpr (SEP) {
+            const float h = fmaf(v3, fx[3], fmaf(v2, fx[2], fmaf(v1, fx[1], v0 * fx[0])));
+#pragma unroll
+            for (int jy = 0; jy < kK; ++jy) {
+              const int q = t - jy;
+              if (q >= 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
+            }
+          } else {
+#pragma unroll
+            for (int jy = 0; jy < kK; ++jy) {
+              const int q = t - jy;
+              if (q >= 0 && q < kBandR)
+                acc[q] = fmaf(v3, w2[jy * kK + 3], fmaf(v2, w2[jy * kK + 2], fmaf(v1, w2[jy * kK + 1], fmaf(v0, w2[jy * kK], acc[q]))));
+            }
+          }
+        }
+      } else {
+        // border form, branch-free: column taps outside the image are predicated off, rows outside it are read from
+        // the nearest held row and their contribution replaced by zero
+        const bool any = live && yhi > ylo;
+        const bool in0 = any && cx >= 0 && cx < in_w, in1 = any && cx + 1 >= 0 && cx + 1 < in_w,
+                   in2 = any && cx + 2 >= 0 && cx + 2 < in_w, in3 = any && cx + 3 >= 0 && cx + 3 < in_w;
+#pragma unroll
+        for (int t = 0; t < kBandR + kK - 1; ++t) {
+          const int iy = iy0 + t;
+          const float *sr = colp + min(max(iy, ylo), yhi - 1) * in_w;
+          const float v0 = in0 ? sr[0] : 0.f, v1 = in1 ? sr[1] : 0.f, v2 = in2 ? sr[2] : 0.f, v3 = in3 ? sr[3] : 0.f;
+          const bool rv = (unsigned)iy < (unsigned)in_h && t < nr + kK - 1;
+          if constexpr (SEP) {
+            float h = fmaf(v3, fx[3], fmaf(v2, fx[2], fmaf(v1, fx[1], v0 * fx[0])));
+            h = rv ? h : 0.f;
+#pragma unroll
+            for (int jy = 0; jy < kK; ++jy) {
+              const int q = t - jy;
+              if (q >= 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
+            }
+          } else {
+            const float z0 = rv ? v0 : 0.f, z1 = rv ? v1 : 0.f, z2 = rv ? v2 : 0.f, z3 = rv ? v3 : 0.f;
+#pragma unroll
+            for (int jy = 0; jy < kK; ++jy) {
+              const int q = t - jy;
+              if (q >= 0 && q < kBandR)
+                acc[q] = fmaf(z3, w2[jy * kK + 3], fmaf(z2, w2[jy * kK + 2], fmaf(z1, w2[jy * kK + 1], fmaf(z0, w2[jy * kK], acc[q]))));
+            }
+          }
+        }
+      }
+      const long long plane = b.plane0 + pl;
+      float *yp = u.y + (plane * u.out_h + r0) * (long long)out_w + ox;
+      if (u.act != 0) {
+        const float bias = (u.bias != nullptr && live) ? __ldg(u.bias + (int)(plane % u.channels)) : 0.f;
+#pragma unroll
+        for (int q = 0; q < kBandR; ++q) {
+          const float a = acc[q] + bias;
+          acc[q] = (a > 0.f ? a : a * u.alpha) * u.scale;
+        }
+      }
+      if (__all_sync(0xffffffffu, nr == kBandR)) {
+#pragma unroll
+        for (int q = 0; q < kBandR; ++q) {
+          st_stream_f1(yp, acc[q]);
+          yp += out_w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < kBandR; ++q) {
+          if (q < nr) st_stream_f1(yp, acc[q]);
+          yp += out_w;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
 }
 
 __global__ void __launch_bounds__(kBandThreads, 1)
@@ -909,133 +1075,94 @@ upfirdn2d_band_kernel(const BandParams p) {
   auto stage = [&](int i) { return reinterpret_cast<float *>(band_smem + (size_t)i * kBandStageBytes); };
   uint64_t *full = reinterpret_cast<uint64_t *>(band_smem + (size_t)kBandStages * kBandStageBytes);
   uint64_t *empty = full + kBandStages;
-  __shared__ float filt[kK * kK];
+  __shared__ float filt[kK * kK];        // flipped, zero-extended: filt[jy][jx] multiplies x[oy - pad_y0 + jy][ox - pad_x0 + jx]
+  __shared__ float sep[2 * kK + 1];      // fy[4], fx[4], flag
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const UfdParams &u = p.u;
-  if (tid < kK * kK) {            // flipped, zero-extended taps: filt[jy][jx] multiplies x[oy - pad_y0 + jy][ox - pad_x0 + jx]
+  if (tid < kK * kK) {
     const int jy = tid / kK, jx = tid % kK;
     filt[tid] = (jy < u.kh && jx < u.kw) ? __ldg(u.filt + (u.kh - 1 - jy) * u.kw + (u.kw - 1 - jx)) : 0.f;
   }
+  __syncthreads();
   if (tid == 0) {
     for (int i = 0; i < kBandStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kBandThreads / 32);
+      mbar_init(&empty[i], kBandWarps);
     }
     fence_barrier_init();
+    // rank-1 test: pivot on the largest tap, fx = its row, fy = its column / pivot
+    int best = 0;
+    for (int i = 1; i < kK * kK; ++i)
+      if (fabsf(filt[i]) > fabsf(filt[best])) best = i;
+    const int j0 = best / kK, i0 = best % kK;
+    const float piv = filt[best];
+    float ok = piv != 0.f ? 1.f : 0.f;
+    for (int j = 0; j < kK; ++j) {
+      sep[j] = piv != 0.f ? filt[j * kK + i0] / piv : 0.f;
+      sep[kK + j] = filt[j0 * kK + j];
+    }
+    for (int j = 0; j < kK; ++j)
+      for (int i = 0; i < kK; ++i)
+        if (fabsf(sep[j] * sep[kK + i] - filt[j * kK + i]) > 2e-7f * fabsf(piv)) ok = 0.f;
+    sep[2 * kK] = ok;
   }
   __syncthreads();
   const long long total_al = p.total_floats & ~3LL;
 
-  auto issue = [&](long long unit, int s) {     // thread 0 only
-    int oy0, iy_lo, iy_hi;
-    long long plane, g_lo, g_hi;
-    band_range(p, unit, oy0, iy_lo, iy_hi, plane, g_lo, g_hi);
-    const long long hi = g_hi < total_al ? g_hi : total_al;
-    const uint32_t bytes = hi > g_lo ? (uint32_t)((hi - g_lo) * 4) : 0u;
-    mbar_arrive_expect_tx(&full[s], bytes);
-    if (bytes) bulk_load_1d(stage(s), u.x + g_lo, bytes, &full[s]);
-  };
-
-  long long k = 0;
-  if (tid == 0)
-    for (int i = 0; i < kBandStages; ++i) {
-      const long long unit = blockIdx.x + (long long)i * gridDim.x;
-      if (unit < p.units) issue(unit, i);
-    }
-  float f[kK * kK];
-  for (long long unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++k) {
-    const int s = (int)(k % kBandStages);
-    const uint32_t phase = (uint32_t)((k / kBandStages) & 1);
-    int oy0, iy_lo, iy_hi;
-    long long plane, g_lo, g_hi;
-    band_range(p, unit, oy0, iy_lo, iy_hi, plane, g_lo, g_hi);
-    const int rows = min(p.toh, u.out_h - oy0);
-    mbar_wait(&full[s], phase);
-    float *sm = stage(s);
-    // the (< 16 byte) tail of the tensor that a bulk copy may not touch: plain loads by the first lanes
-    if (g_hi > total_al) {
-      const long long n_tail = p.total_floats - total_al;
-      if (tid < n_tail && total_al + tid >= g_lo) sm[total_al + tid - g_lo] = __ldg(u.x + total_al + tid);
-      __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < kK * kK; ++i) f[i] = filt[i];
-    const long long plane_base = plane * u.in_h * (long long)u.in_w;
-    const float *srow0 = sm + (plane_base - g_lo);                 // srow0[iy * in_w + ix] = x[plane, iy, ix]
-    float *yp = u.y + plane * u.out_h * (long long)u.out_w;
-    float bias = 0.f;
-    if (u.act != 0 && u.bias != nullptr) bias = __ldg(u.bias + (int)(plane % u.channels));
-    const int groups = (rows + kBandR - 1) / kBandR;
-    const int items = groups * u.out_w;
-    for (int it = tid; it < items; it += kBandThreads) {
-      const int g = it / u.out_w, ox = it - g * u.out_w;
-      const int r0 = oy0 + g * kBandR;                              // first output row of this item
-      const int nr = min(kBandR, oy0 + rows - r0);
-      const int cx = ox - u.pad_x0;                                  // input column of tap jx = 0
-      const bool in0 = cx >= 0 && cx < u.in_w, in1 = cx + 1 >= 0 && cx + 1 < u.in_w, in2 = cx + 2 >= 0 && cx + 2 < u.in_w,
-                 in3 = cx + 3 >= 0 && cx + 3 < u.in_w;
-      float acc[kBandR];
-#pragma unroll
-      for (int q = 0; q < kBandR; ++q) acc[q] = 0.f;
-      // input row r0 - pad_y0 + t (t = 0 .. nr + 2) is tap jy = t - q of output row r0 + q
-#pragma unroll
-      for (int t = 0; t < kBandR + kK - 1; ++t) {
-        const int iy = r0 - u.pad_y0 + t;
-        if (t < nr + kK - 1 && iy >= 0 && iy < u.in_h) {
-          const float *sr = srow0 + (long long)iy * u.in_w + cx;
-          const float v0 = in0 ? sr[0] : 0.f, v1 = in1 ? sr[1] : 0.f, v2 = in2 ? sr[2] : 0.f, v3 = in3 ? sr[3] : 0.f;
-#pragma unroll
-          for (int jy = 0; jy < kK; ++jy) {
-            const int q = t - jy;
-            if (q >= 0 && q < kBandR) {
-              float a = acc[q];
-              a = fmaf(v0, f[jy * kK + 0], a);
-              a = fmaf(v1, f[jy * kK + 1], a);
-              a = fmaf(v2, f[jy * kK + 2], a);
-              a = fmaf(v3, f[jy * kK + 3], a);
-              acc[q] = a;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kBandR; ++q) {
-        if (q < nr) {
-          float a = acc[q];
-          if (u.act != 0) {
-            a += bias;
-            a = (a > 0.f ? a : a * u.alpha) * u.scale;
-          }
-          st_stream_f1(yp + (long long)(r0 + q) * u.out_w + ox, a);
-        }
+  if (warp == kBandWarps) {
+    // ===================== producer: one bulk copy per unit =====================
+    if (lane == 0) {
+      long long k = 0;
+      for (long long unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++k) {
+        const int s = (int)(k % kBandStages);
+        if (k >= kBandStages) mbar_wait(&empty[s], (uint32_t)(((k / kBandStages) - 1) & 1));
+        const BandUnit b = band_unit(p, unit);
+        const long long hi = b.g_hi < total_al ? b.g_hi : total_al;
+        const uint32_t bytes = hi > b.g_lo ? (uint32_t)((hi - b.g_lo) * 4) : 0u;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        if (bytes) bulk_load_1d(stage(s), u.x + b.g_lo, bytes, &full[s]);
       }
     }
-    __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
-    if (tid == 0) {
-      const long long next = unit + (long long)kBandStages * gridDim.x;
-      if (next < p.units) {
-        mbar_wait(&empty[s], phase);
-        issue(next, s);
-      }
-    }
+    return;
   }
+
+  // ===================== compute warps =====================
+  if (sep[2 * kK] != 0.f) band_compute<true>(p, band_smem, full, empty, filt, sep);
+  else band_compute<false>(p, band_smem, full, empty, filt, sep);
 }
 
 int launch_band(const UfdParams &u, cudaStream_t stream) {
   BandParams p;
   p.u = u;
   const long long row_bytes = (long long)u.in_w * 4;
-  long long toh = (kBandStageBytes - 64) / row_bytes - (u.kh - 1);
-  if (toh < 1) return -1;                                   // a single band does not fit: caller falls back
-  if (toh > u.out_h) toh = u.out_h;
-  // enough units to keep every SM's ring busy
-  while (toh > kBandR && (long long)u.major * ((u.out_h + toh - 1) / toh) < 4LL * num_sms()) toh = (toh + 1) / 2;
-  if (toh > kBandR) toh = toh / kBandR * kBandR;
-  p.toh = (int)toh;
-  p.bands = (int)((u.out_h + toh - 1) / toh);
-  p.units = (long long)u.major * p.bands;
-  p.total_floats = (long long)u.major * u.in_h * u.in_w;
+  const long long plane_bytes = row_bytes * u.in_h;
+  const long long budget = kBandStageBytes - 64;           // alignment over-fetch at both ends
+  if (2 * plane_bytes <= budget) {
+    // small planes: several whole planes per unit, but keep >= 3 units per SM in flight when the tensor allows it
+    long long P = budget / plane_bytes;
+    while (P > 1 && (u.major + P - 1) / P < 3LL * num_sms()) --P;
+    p.P = (int)P;
+    p.G = (u.out_h + kBandR - 1) / kBandR;
+    p.upp = 1;
+    p.units = (u.major + P - 1) / P;
+  } else {
+    long long in_rows = budget / row_bytes;                 // input rows a stage holds
+    long long G = (in_rows - (u.kh - 1)) / kBandR;
+    if (G < 1) return -1;                                   // one row group does not fit: caller falls back
+    const long long gmax = (u.out_h + kBandR - 1) / kBandR;
+    if (G > gmax) G = gmax;
+    while (G > 1 && u.major * ((gmax + G - 1) / G) < 3LL * num_sms()) --G;
+    p.P = 1;
+    p.G = (int)G;
+    p.upp = (int)((gmax + G - 1) / G);
+    p.units = u.major * p.upp;
+  }
+  p.total_floats = u.major * (long long)u.in_h * u.in_w;
+  // items of a unit are < 2^15 and the divisors < 2^15, so the multiply-high quotients are exact
+  if ((long long)p.G * u.out_w >= (1 << 15)) return -1;
+  p.magic_ow = (unsigned)((1ULL << 32) / (unsigned)u.out_w) + 1u;
+  p.magic_pp = (unsigned)((1ULL << 32) / (unsigned)(p.G * u.out_w)) + 1u;
   auto kern = upfirdn2d_band_kernel;
   constexpr int smem = kBandStages * kBandStageBytes + 2 * kBandStages * 8;
   static bool attr_done[64] = {false};
@@ -1091,9 +1218,11 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
   const bool sane_pad = pad_x0 > -(1 << 28) && pad_x0 < (1 << 28) && pad_y0 > -(1 << 28) && pad_y0 < (1 << 28);
   if (small_filt && sane_pad && in_h > 0 && in_w > 0) {
     if (up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1) {
-      // odd row pitch (no tensor map): contiguous row bands through 1-D bulk copies
+      // contiguous row bands through 1-D bulk copies (any row pitch; VSP_BAND_ODD_ONLY=1 keeps even pitches on the tile kernel)
       static const bool no_band = getenv("VSP_NO_BAND") != nullptr;
-      if (!p.use_tma && !no_band && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && out_w >= 32 && major < (1LL << 31)) {
+      static const bool odd_only = getenv("VSP_BAND_ODD_ONLY") != nullptr;
+      if ((!p.use_tma || !odd_only) && !no_band && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && out_w >= 32 &&
+          major < (1LL << 31)) {
         const int rc = launch_band(p, stream);
         if (rc >= 0) return rc;
       }
