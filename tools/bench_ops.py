@@ -125,6 +125,17 @@ def main():
         dst = torch.empty_like(src)
         return lambda: dst.copy_(src)
     run("torch copy 256MB (yardstick)", mk_copy, 2 * 64 * 1024 * 1024 * 4, sets=4)
+
+    # same-size yardsticks: what a plain device copy moving the SAME number of bytes reaches (launch ramp + tail of a 15-40 us
+    # kernel are a fixed cost that the 256 MB copy amortises)
+    def mk_copy_n(nfloat):
+        def mk():
+            src = R(nfloat)
+            dst = torch.empty_like(src)
+            return lambda: dst.copy_(src)
+        return mk
+    run("torch copy, 168 MB of traffic (= config 1 / down2 / fused)", mk_copy_n((nx + ny) // 2), (nx + ny) * 4)
+    run("torch copy, 67 MB of traffic (= bias_act [4,512,64,64] / blur [4,512,65,65])", mk_copy_n(nx), 2 * nx * 4)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(rows, open("gpurun_out/bench_ops.json", "w"), indent=1)
 

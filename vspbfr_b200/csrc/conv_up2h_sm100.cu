@@ -280,9 +280,11 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
     const int full_h = 2 * p.in_h, full_w = 2 * p.in_w;
     const bool has_res = p.res1 != nullptr || p.res2 != nullptr;
     const long long rstride = (long long)full_w * p.ldo;       // one output row, in elements
-    float R[kUpC];
+    unsigned long long R2[kUpC / 2];           // ky0 * O[a-1], packed (channel 2i, 2i+1): all epilogue arithmetic is FFMA2
 #pragma unroll
-    for (int i = 0; i < kUpC; ++i) R[i] = 0.f;
+    for (int i = 0; i < kUpC / 2; ++i) R2[i] = 0ull;
+    const unsigned long long ky0p = f2pack(ky0, ky0), ky1p = f2pack(ky1, ky1), ky2p = f2pack(ky2, ky2), ky3p = f2pack(ky3, ky3);
+    const unsigned long long a2p = f2pack(a2, a2);
     uint32_t rr[2][2][16];                      // [residual][row parity][64 bytes of this thread's pixel], one row pair ahead
 #pragma unroll
     for (int i = 0; i < 64; ++i) (&rr[0][0][0])[i] = 0u;
@@ -376,19 +378,29 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
               if (k == rows - 1) mbar_arrive(&acc_empty[slot]);
             }
           }
+          unsigned long long o2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o2[i] = f2pack(__uint_as_float(o[2 * i]), __uint_as_float(o[2 * i + 1]));
           if (emit) {
+            const unsigned long long n0p = f2pack(n0, n0), n1p = f2pack(n1, n1);
             float v0[8], v1[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float E = __uint_as_float(e[i]), O = __uint_as_float(o[i]);
-              const float En = __uint_as_float(en[i]), On = __uint_as_float(on[i]);
-              const int c = h * 8 + i;
-              const float f0 = fmaf(ky3, En, fmaf(ky2, O, fmaf(ky1, E, R[c])));
-              const float f1 = fmaf(ky3, On, fmaf(ky2, En, fmaf(ky1, O, ky0 * E)));
-              const float t0 = fmaf(f0, vec_rs[c], n0 + vec_b2[c]);
-              const float t1 = fmaf(f1, vec_rs[c], n1 + vec_b2[c]);
-              v0[i] = fmaxf(t0, t0 * a2);
-              v1[i] = fmaxf(t1, t1 * a2);
+            for (int i = 0; i < 4; ++i) {
+              const int c2 = h * 4 + i;                                        // channel pair index
+              const unsigned long long e2 = f2pack(__uint_as_float(e[2 * i]), __uint_as_float(e[2 * i + 1]));
+              const unsigned long long en2 = f2pack(__uint_as_float(en[2 * i]), __uint_as_float(en[2 * i + 1]));
+              const unsigned long long on2 = f2pack(__uint_as_float(on[2 * i]), __uint_as_float(on[2 * i + 1]));
+              const unsigned long long f0 = f2fma(ky3p, en2, f2fma(ky2p, o2[i], f2fma(ky1p, e2, R2[c2])));
+              const unsigned long long f1 = f2fma(ky3p, on2, f2fma(ky2p, en2, f2fma(ky1p, o2[i], f2mul(ky0p, e2))));
+              const unsigned long long rs2 = reinterpret_cast<const unsigned long long *>(vec_rs)[c2];
+              const unsigned long long b22 = reinterpret_cast<const unsigned long long *>(vec_b2)[c2];
+              const unsigned long long t0 = f2fma(f0, rs2, f2add(b22, n0p));
+              const unsigned long long t1 = f2fma(f1, rs2, f2add(b22, n1p));
+              const unsigned long long s0 = f2mul(t0, a2p), s1 = f2mul(t1, a2p);
+              float t0l, t0h, t1l, t1h, s0l, s0h, s1l, s1h;
+              f2unpack(t0, t0l, t0h); f2unpack(t1, t1l, t1h); f2unpack(s0, s0l, s0h); f2unpack(s1, s1l, s1h);
+              v0[2 * i] = fmaxf(t0l, s0l); v0[2 * i + 1] = fmaxf(t0h, s0h);
+              v1[2 * i] = fmaxf(t1l, s1l); v1[2 * i + 1] = fmaxf(t1h, s1h);
             }
             if (has_res) {
               const uint4 a0v = make_uint4(rr[0][0][4 * h], rr[0][0][4 * h + 1], rr[0][0][4 * h + 2], rr[0][0][4 * h + 3]);
@@ -402,7 +414,7 @@ conv_up2h_kernel(const Up2hParams p, const __grid_constant__ CUtensorMap tmap_a,
             *reinterpret_cast<uint4 *>(buf1 + lane * 64 + ((h ^ sw) << 4)) = pack8_bf16(v1);
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) R[h * 8 + i] = ky0 * __uint_as_float(o[i]);
+          for (int i = 0; i < 4; ++i) R2[h * 4 + i] = f2mul(ky0p, o2[i]);
         }
         if (emit) {
           fence_proxy_async();

@@ -819,11 +819,23 @@ int launch_tile(UfdParams p, cudaStream_t stream) {
   p.tiles_y = (p.out_h + TOH - 1) / TOH;
   p.zgroups = (int)((p.major + PZ - 1) / PZ);
   const long long tiles_xy = (long long)p.tiles_x * p.tiles_y;
-  // enough blocks for >= ~8 per SM, at most 8 plane groups per block
-  long long want_blocks = (long long)num_sms() * 16;
+  // Grid: measured on B200 — the up-sampling and blur tiles (small input tile, many blocks per SM) run best oversubscribed
+  // (~16 blocks per SM, at most 8 plane groups per block: config 1 34.8 us vs 37.6 us as one resident wave); the decimating
+  // tile (36 KB per stage, 3 blocks per SM) runs best as exactly one resident wave (39.1 vs 41.0 us).
+  long long want_blocks = (long long)num_sms() * 16, cap = 8;
+  if (D == 2) {
+    static int occ[64] = {0};
+    if (dev >= 0 && dev < 64 && occ[dev] == 0) {
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, C::SMEM_BYTES) != cudaSuccess || nb < 1) nb = 1;
+      occ[dev] = nb;
+    }
+    want_blocks = (long long)num_sms() * ((dev >= 0 && dev < 64) ? occ[dev] : 3);
+    cap = 64;
+  }
   long long iters = (tiles_xy * p.zgroups + want_blocks - 1) / want_blocks;
   if (iters < 1) iters = 1;
-  if (iters > 8) iters = 8;
+  if (iters > cap) iters = cap;
   if (iters > p.zgroups) iters = p.zgroups;
   p.iters = (int)iters;
   const long long zchunks = (p.zgroups + iters - 1) / iters;
