@@ -123,6 +123,17 @@ int vsp_bias_act_bwd_f32(const float *dy, const float *ref, float *dx, float *db
 
 /* ---- layout / modulation prologues ------------------------------------- */
 
+/*
+ * Output side of the inference loop (restoration_test.py:138-157: every restored / low / sample image goes through
+ * torchvision.utils.save_image(..., normalize=True, range=(-1, 1))): quantise on the DEVICE, so the device->host copy
+ * moves 3 bytes per pixel instead of 12 and the host only encodes.
+ *   x [batch, channels, hw] fp32 (NCHW)  ->  y [batch, hw, channels] uint8 (HWC), channels <= 4
+ *   y = trunc(clamp(((clamp(x, lo, hi) - lo) / max(hi - lo, 1e-5)) * 255 + 0.5, 0, 255))  — torchvision's arithmetic,
+ *   operation by operation in round-to-nearest fp32, so the bytes equal the reference's.
+ */
+int vsp_quantize_nchw_f32_to_hwc_u8(const float *x, void *y, int64_t batch, int64_t channels, int64_t hw,
+                                    float lo, float hi, void *stream);
+
 /* NCHW fp32 -> NHWC bf16 (optionally scaled per (n, c): `scale_nc` may be NULL).
  * x [n, c, hw] -> y [n, hw, c_pad]; channels c..c_pad-1 are zero filled. */
 int vsp_nchw_f32_to_nhwc_bf16(const float *x, const float *scale_nc, void *y,

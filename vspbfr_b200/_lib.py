@@ -162,6 +162,7 @@ SIGNATURES = {
     "vsp_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "vsp_nchw_f32_to_nhwc_split3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "vsp_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "vsp_quantize_nchw_f32_to_hwc_u8": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_float, c_void_p]),
     "vsp_nchw_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vsp_modulate_weights_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_int64, c_int64, c_int,

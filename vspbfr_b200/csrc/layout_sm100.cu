@@ -557,6 +557,75 @@ extern "C" int vsp_nchw_f32_to_bf16(const float *x, const float *scale_nc, void 
   return 0;
 }
 
+// Image quantisation for the output side (restoration_test.py:138-157 saves every image through
+// torchvision.utils.save_image(normalize=True, range=(-1, 1))): NCHW fp32 -> HWC uint8 on the device, so the device->host
+// copy moves 3 bytes per pixel instead of 12 and the host only has to encode.  Same arithmetic, operation by operation, as
+// torchvision (clamp to [lo, hi]; (x - lo) / max(hi - lo, 1e-5); * 255; + 0.5; clamp to [0, 255]; truncate) in
+// round-to-nearest fp32 without contraction, so the bytes are identical.
+namespace vsp {
+namespace {
+__device__ __forceinline__ unsigned quant_u8(float v, float lo, float hi, float inv_is_div, float span) {
+  v = fminf(fmaxf(v, lo), hi);
+  v = __fsub_rn(v, lo);
+  v = __fdiv_rn(v, span);
+  v = __fmul_rn(v, 255.f);
+  v = __fadd_rn(v, 0.5f);
+  v = fminf(fmaxf(v, 0.f), 255.f);
+  (void)inv_is_div;
+  return (unsigned)(int)v;          // truncation, as .to(torch.uint8)
+}
+
+__global__ void __launch_bounds__(256)
+quantize_nchw_to_hwc_u8_kernel(const float *__restrict__ x, unsigned char *__restrict__ y, long long hw, int c, float lo,
+                               float hi) {
+  const long long b = blockIdx.y;
+  const float *xb = x + b * c * hw;
+  unsigned char *yb = y + b * c * hw;
+  const float span = fmaxf(hi - lo, 1e-5f);
+  if (c == 3 && (hw & 3) == 0) {
+    // four pixels per thread: three 128-bit plane loads -> twelve bytes = three 32-bit stores
+    for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 4; i < hw; i += (long long)gridDim.x * 1024) {
+      const float4 r = ld_stream_f4(reinterpret_cast<const float4 *>(xb + i));
+      const float4 g = ld_stream_f4(reinterpret_cast<const float4 *>(xb + hw + i));
+      const float4 bl = ld_stream_f4(reinterpret_cast<const float4 *>(xb + 2 * hw + i));
+      const float rr[4] = {r.x, r.y, r.z, r.w}, gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {bl.x, bl.y, bl.z, bl.w};
+      unsigned q[12];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        q[3 * k] = quant_u8(rr[k], lo, hi, 0.f, span);
+        q[3 * k + 1] = quant_u8(gg[k], lo, hi, 0.f, span);
+        q[3 * k + 2] = quant_u8(bb[k], lo, hi, 0.f, span);
+      }
+      uint32_t *dst = reinterpret_cast<uint32_t *>(yb + i * 3);
+#pragma unroll
+      for (int w = 0; w < 3; ++w)
+        dst[w] = q[4 * w] | (q[4 * w + 1] << 8) | (q[4 * w + 2] << 16) | (q[4 * w + 3] << 24);
+    }
+  } else {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < hw; i += (long long)gridDim.x * 256)
+      for (int ch = 0; ch < c; ++ch) yb[i * c + ch] = (unsigned char)quant_u8(xb[ch * hw + i], lo, hi, 0.f, span);
+  }
+}
+}  // namespace
+}  // namespace vsp
+
+extern "C" int vsp_quantize_nchw_f32_to_hwc_u8(const float *x, void *y, int64_t batch, int64_t channels, int64_t hw,
+                                               float lo, float hi, void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  VSP_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4 && hw >= 0, "quantize: bad geometry");
+  if (batch == 0 || hw == 0) return 0;
+  VSP_REQUIRE(x && y, "quantize: null pointer");
+  VSP_REQUIRE(batch <= 65535, "quantize: batch too large");
+  VSP_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0,
+              "quantize: operands must be 16 / 4-byte aligned");
+  long long bx = ceil_div64(hw, 1024);
+  if (bx > 2 * num_sms()) bx = 2 * num_sms();
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)batch);
+  quantize_nchw_to_hwc_u8_kernel<<<grid, 256, 0, stream>>>(x, static_cast<unsigned char *>(y), hw, (int)channels, lo, hi);
+  return check_launch("quantize_nchw_to_hwc_u8_kernel");
+}
+
 extern "C" int vsp_modulate_weights_bf16(const float *w, const float *s, float *demod, void *wq,
                                          int64_t batch, int64_t cout, int64_t cin, int taps,
                                          float wscale, float eps, int transpose, int fold_demod,
