@@ -24,6 +24,8 @@ struct ConvParams {
   int branch_mode;         // channel tile n_i is branch n_i of a SMART layer: tap offsets scaled by n_dil[n_i]
   int n_dil[4];
   long long total_tiles;
+  int mpairs;              // CTA-pair kernel: pairs of spatial tiles per sample, pair-tiles in the launch
+  long long total_pairs;
   int kc;                  // channel blocks per tap = ceil(cin / 64)
   int halo_d, halo_w;      // row-halo / row-ring kernels: dilation and padded halo row length (pixels)
   // row-ring kernel: R output rows per accumulator hand-off, S row slots, segments of L rows per chain

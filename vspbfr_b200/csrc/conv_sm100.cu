@@ -117,10 +117,12 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
 // swizzled shared memory and writes them with one TMA store (full lines instead of 16-byte pieces at pixel
 // pitch).  Handles the parity-class output mappings (one tensor map per class) and the pixel-shuffle mapping of
 // the fused up-convolution.  Requires tw >= 32 (a warp's pixels lie in one output row).
-template <int BLOCK_N>
+// PAIR: the CTA-pair kernel — tiles come in pairs (spatial tiles 2*mp + cluster rank of one sample and channel tile) and
+// the accumulator is handed back to the LEADER's barrier (a remote arrive for the peer CTA).
+template <int BLOCK_N, bool PAIR = false>
 __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const OutMaps &maps, float *epi_vec,
                                                      unsigned char *o_buf, uint64_t *tmem_full, uint64_t *tmem_empty,
-                                                     uint32_t tmem_base, int warp, int lane) {
+                                                     uint32_t tmem_base, int warp, int lane, int rank = 0) {
   using C = ConvCfg<BLOCK_N>;
   constexpr int CHUNK = C::CHUNK;
   constexpr int ROW_BYTES = CHUNK * 2;
@@ -139,11 +141,23 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   const __nv_bfloat16 *res2 = static_cast<const __nv_bfloat16 *>(p.residual2);
   int acc = 0;
   uint32_t acc_phase = 0, sbuf = 0;
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+  auto release_acc = [&](int a) {               // hand accumulator stage `a` back to the MMA warp
+    if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[a]), 0));
+    else mbar_arrive(&tmem_empty[a]);
+  };
+  const long long t_begin = PAIR ? (blockIdx.x >> 1) : blockIdx.x, t_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const long long t_end = PAIR ? p.total_pairs : p.total_tiles;
+  for (long long tile = t_begin; tile < t_end; tile += t_step) {
     long long t = tile;
     const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
-    const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
-    const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
+    int w_i, h_i;
+    if (PAIR) {
+      const int m = 2 * (int)(t % p.mpairs) + rank; t /= p.mpairs;
+      w_i = m % p.tiles_w; h_i = m / p.tiles_w;          // h_i == tiles_h for the odd tail: every pixel out of range
+    } else {
+      w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
+      h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
+    }
     const int b = (int)t;
     const int oh = h_i * p.th + row / p.tw;
     const int ow = w_i * p.tw + row % p.tw;
@@ -204,7 +218,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
     if (wg >= NCH) {                 // single-chunk tiles: the second warp of the quadrant has nothing to read
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) release_acc(acc);
     }
 #pragma unroll 1
     for (int ch = wg; ch < NCH; ch += 2) {
@@ -214,7 +228,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
         if (last_ch) {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) release_acc(acc);
         }
         continue;
       }
@@ -230,7 +244,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
       if (last_ch) {                 // accumulators are in registers: the MMA warp may reuse this stage
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) release_acc(acc);
       }
       unsigned char *buf = stage + (C::NBUF == 2 ? (sbuf & 1) : 0) * C::SBUF_BYTES;
       ++sbuf;
@@ -398,6 +412,146 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair form of the N = 256 kernel (tcgen05 cta_group::2).  The single-CTA mainloop above is bound by load LATENCY, not by
+// the tensor pipe: a stage is 48 KB (16 KB of A + 32 KB of B), four stages fill the shared memory and cover only ~2000
+// cycles of L2 latency at the rate the MMAs consume them (ncu: tensor pipe 69 % active, shared-memory operand path 52 %,
+// L2 39 %).  Two CTAs on the SMs of one TPC that work on neighbouring spatial tiles of the same sample and channel tile need
+// the same weights: as a pair they issue ONE M = 256 MMA per k-step, each CTA supplying its own 128 activation rows and HALF
+// of the weight rows.  A stage shrinks to 32 KB, six stages fit, and the same shared memory covers 1.5x the latency; the
+// weight tile crosses L2 -> SM once per pair instead of once per CTA.
+// Protocol: both producers wait for their OWN empty barrier (the leader's tcgen05.commit multicasts its arrive to both
+// CTAs) and issue TMA loads that complete on the LEADER's full barrier (one expect_tx of both CTAs' bytes by the leader);
+// only the leader's warp 1 issues MMAs; accumulator-ready is multicast to both CTAs' epilogues; accumulator-free is 16
+// arrives (8 epilogue warps x 2 CTAs, the peer's remote) on the leader's barrier.
+template <int BLOCK_N>
+struct PairCfg {
+  static constexpr int B_HALF_BYTES = (BLOCK_N / 2) * kBlockK * 2;
+  static constexpr int STAGE_BYTES = kABytes + B_HALF_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int SBUF_BYTES = 32 * 32 * 2;
+  static constexpr int OSTAGE_BYTES = 8 * SBUF_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 6 * BLOCK_N * 4 + OSTAGE_BYTES + 1024;
+  static_assert(SMEM_BYTES <= 232448, "conv_fprop_pair_kernel exceeds shared memory");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
+                       const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ OutMaps omaps) {
+  using P = PairCfg<BLOCK_N>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + P::STAGES * P::STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + P::STAGES;
+  uint64_t *tmem_full = empty_bar + P::STAGES;
+  uint64_t *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+  float *epi_vec = reinterpret_cast<float *>(smem + P::STAGES * P::STAGE_BYTES + 256);
+  unsigned char *o_buf = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(epi_vec + 6 * BLOCK_N) + 1023) & ~uintptr_t(1023));
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < P::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 16);   // 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 2 * BLOCK_N);
+    tmem_relinquish_2cta();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                  // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.ntaps * p.kc;
+  const long long t_begin = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tile = t_begin; tile < p.total_pairs; tile += t_step) {
+      long long t = tile;
+      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int m = 2 * (int)(t % p.mpairs) + rank; t /= p.mpairs;
+      const int w_i = m % p.tiles_w, h_i = m / p.tiles_w;
+      const int b = (int)t;
+      const int g = p.groups == 1 ? 0 : b;
+      const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.kc;
+        const int c0 = (kb - tap * p.kc) * kBlockK;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          unsigned char *sa = smem + stage * P::STAGE_BYTES;
+          unsigned char *sb = sa + kABytes;
+          const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * P::STAGE_BYTES);
+          tma_load_4d_2cta(sa, &tmap_a, lead_full, c0, iw0 + p.tap_dx[tap], ih0 + p.tap_dy[tap], b);
+          tma_load_4d_2cta(sb, &tmap_b, lead_full, c0, n_i * BLOCK_N + rank * (BLOCK_N / 2), p.tap_w[tap], g);
+        }
+        __syncwarp();
+        if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader only): M = 256 across the pair =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = t_begin; tile < p.total_pairs; tile += t_step) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * P::STAGE_BYTES);
+            const uint64_t adesc = umma_smem_desc(sa, 128);
+            const uint64_t bdesc = umma_smem_desc(sa + kABytes, 128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage]);                         // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) umma_commit_2cta(&tmem_full[acc]);     // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    epilogue_role_staged<BLOCK_N, true>(p, omaps, epi_vec, o_buf, tmem_full, tmem_empty, tmem_base, warp, lane, rank);
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                  // both CTAs are done with the pair's tensor memory and barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2cta(tmem_base, 2 * BLOCK_N);
   }
 }
 
@@ -700,6 +854,67 @@ int launch_conv_impl(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
   return check_launch("conv_fprop_kernel");
 }
 
+// CTA-pair launch (N = 256, staged epilogue, one sample per tile).  Returns -1 when the device cannot co-schedule a pair.
+int launch_conv_pair(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
+                     cudaStream_t stream) {
+  constexpr int BLOCK_N = 256;
+  using P = PairCfg<BLOCK_N>;
+  auto kern = conv_fprop_pair_kernel<BLOCK_N>;
+  static int state[64] = {0};            // 0 = unknown, 1 = usable, -1 = not
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return -1;
+  if (state[dev] == 0) {
+    state[dev] = -1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(2, 1, 1);
+      cfg.blockDim = dim3(kNumThreads, 1, 1);
+      cfg.dynamicSmemBytes = P::SMEM_BYTES;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) state[dev] = nclusters;
+    }
+    cudaGetLastError();
+  }
+  if (state[dev] < 1) return -1;
+  CUtensorMap tb;
+  {
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
+    uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
+                           (uint64_t)p.cin * cout_pad * taps_total * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(BLOCK_N / 2), 1, 1};
+    if (int rc = encode_tma(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, wq, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_128B))
+      return rc;
+  }
+  OutMaps om;
+  memset(&om, 0, sizeof(om));
+  {
+    const int ncls = p.shuffle_cout ? 4 : 1;
+    const int os = p.os;
+    const int creal = p.shuffle_cout ? p.shuffle_cout : p.cout;
+    for (int cls = 0; cls < ncls; ++cls) {
+      const int oh0 = p.oo_h + (cls >> 1), ow0 = p.oo_w + (cls & 1);
+      const __nv_bfloat16 *base = static_cast<const __nv_bfloat16 *>(p.out) + ((long long)oh0 * p.full_w + ow0) * p.ldo;
+      uint64_t dims[4] = {(uint64_t)(p.co_off + creal), (uint64_t)((p.full_w - ow0 + os - 1) / os),
+                          (uint64_t)((p.full_h - oh0 + os - 1) / os), (uint64_t)p.batch};
+      uint64_t strides[4] = {0, (uint64_t)p.ldo * 2 * os, (uint64_t)p.ldo * p.full_w * 2 * os,
+                             (uint64_t)p.ldo * p.full_w * p.full_h * 2};
+      uint32_t box[4] = {32, 32, 1, 1};
+      if (int rc = encode_tma(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, nullptr,
+                              CU_TENSOR_MAP_SWIZZLE_64B))
+        return rc;
+    }
+  }
+  p.tiles_n = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  p.mpairs = (p.tiles_h * p.tiles_w + 1) / 2;
+  p.total_pairs = (long long)p.batch * p.mpairs * p.tiles_n;
+  long long pairs = p.total_pairs < state[dev] ? p.total_pairs : state[dev];
+  kern<<<(unsigned)(2 * pairs), kNumThreads, P::SMEM_BYTES, stream>>>(p, ta, tb, om);
+  return check_launch("conv_fprop_pair_kernel");
+}
+
 template <int BLOCK_N>
 int launch_conv(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
                 cudaStream_t stream) {
@@ -844,6 +1059,14 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
       const long long waves = (tiles + num_sms() - 1) / num_sms();
       const double cost = (double)waves * ((double)p.ntaps * p.kc * (256.0 + 2.0 * bn) + 600.0 + 8.0 * bn);
       if (cost < best) { best = cost; best_bn = bn; }
+    }
+  }
+  if (best_bn == 256 && p.staged && p.tb == 1 && !p.branch_mode) {
+    // CTA pairs (tcgen05 cta_group::2) for the N = 256 layers; VSP_CONV_PAIR=0 keeps the single-CTA kernel
+    static const bool pair_on = getenv("VSP_CONV_PAIR") == nullptr || atoi(getenv("VSP_CONV_PAIR")) != 0;
+    if (pair_on) {
+      const int rc = launch_conv_pair(p, ta, wq, cout_pad, taps_total, stream);
+      if (rc >= 0) return rc;
     }
   }
   switch (best_bn) {
