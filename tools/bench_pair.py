@@ -10,7 +10,8 @@ def main():
     dev = "cuda"
     rows = []
     for (b, cin, cout, h, per_sample) in ((8, 512, 512, 64, True), (32, 512, 512, 64, True), (32, 256, 256, 128, False),
-                                          (32, 512, 512, 32, False), (3, 256, 256, 40, True)):
+                                          (32, 512, 512, 32, False), (3, 256, 256, 40, True), (32, 128, 128, 256, False), (32, 128, 128, 256, True),
+                                          (32, 256, 128, 64, True), (5, 128, 128, 48, True)):
         g = torch.Generator().manual_seed(b + cin + h)
         sets = []
         for _ in range(4):

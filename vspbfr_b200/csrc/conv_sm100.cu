@@ -431,9 +431,8 @@ template <int BLOCK_N>
 struct PairCfg {
   static constexpr int B_HALF_BYTES = (BLOCK_N / 2) * kBlockK * 2;
   static constexpr int STAGE_BYTES = kABytes + B_HALF_BYTES;
-  static constexpr int STAGES = 6;
-  static constexpr int SBUF_BYTES = 32 * 32 * 2;
-  static constexpr int OSTAGE_BYTES = 8 * SBUF_BYTES;
+  static constexpr int STAGES = BLOCK_N >= 256 ? 6 : 7;
+  static constexpr int OSTAGE_BYTES = ConvCfg<BLOCK_N>::OSTAGE_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 6 * BLOCK_N * 4 + OSTAGE_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "conv_fprop_pair_kernel exceeds shared memory");
 };
@@ -496,6 +495,7 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
       const int b = (int)t;
       const int g = p.groups == 1 ? 0 : b;
       const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
+      const int dmul = p.branch_mode ? p.n_dil[n_i] : 1;     // channel tile = SMART branch: its own dilation
       for (int kb = 0; kb < num_kb; ++kb) {
         const int tap = kb / p.kc;
         const int c0 = (kb - tap * p.kc) * kBlockK;
@@ -505,7 +505,7 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
           unsigned char *sb = sa + kABytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * P::STAGE_BYTES);
-          tma_load_4d_2cta(sa, &tmap_a, lead_full, c0, iw0 + p.tap_dx[tap], ih0 + p.tap_dy[tap], b);
+          tma_load_4d_2cta(sa, &tmap_a, lead_full, c0, iw0 + p.tap_dx[tap] * dmul, ih0 + p.tap_dy[tap] * dmul, b);
           tma_load_4d_2cta(sb, &tmap_b, lead_full, c0, n_i * BLOCK_N + rank * (BLOCK_N / 2), p.tap_w[tap], g);
         }
         __syncwarp();
@@ -855,9 +855,9 @@ int launch_conv_impl(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
 }
 
 // CTA-pair launch (N = 256, staged epilogue, one sample per tile).  Returns -1 when the device cannot co-schedule a pair.
+template <int BLOCK_N>
 int launch_conv_pair(ConvParams &p, const CUtensorMap &ta, const void *wq, int64_t cout_pad, int taps_total,
                      cudaStream_t stream) {
-  constexpr int BLOCK_N = 256;
   using P = PairCfg<BLOCK_N>;
   auto kern = conv_fprop_pair_kernel<BLOCK_N>;
   static int state[64] = {0};            // 0 = unknown, 1 = usable, -1 = not
@@ -901,7 +901,7 @@ int launch_conv_pair(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
                           (uint64_t)((p.full_h - oh0 + os - 1) / os), (uint64_t)p.batch};
       uint64_t strides[4] = {0, (uint64_t)p.ldo * 2 * os, (uint64_t)p.ldo * p.full_w * 2 * os,
                              (uint64_t)p.ldo * p.full_w * p.full_h * 2};
-      uint32_t box[4] = {32, 32, 1, 1};
+      uint32_t box[4] = {(uint32_t)ConvCfg<BLOCK_N>::CHUNK, 32, 1, 1};
       if (int rc = encode_tma(&om.m[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, nullptr,
                               CU_TENSOR_MAP_SWIZZLE_64B))
         return rc;
@@ -1010,7 +1010,10 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   // Row-halo path: stride-1 3x3 (dilated) "same" convolution on a wide image, plain output mapping
   {
     static const bool no_halo = getenv("VSP_NO_HALO") != nullptr;
-    bool grid3 = !no_halo && !p.branch_mode && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h;
+    // (Cout > 128 goes to the generic kernel: as a CTA pair it runs 256->256 @128^2 in 385 us vs 468 us here)
+    static const bool halo_wide = getenv("VSP_HALO_WIDE_N") != nullptr;
+    bool grid3 = !no_halo && !p.branch_mode && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h &&
+                 (cout <= 128 || halo_wide || !p.staged);
     int dd = grid3 ? tap_dx[8] : 0;   // tap (kh,kw) offset must be ((kh-1)*d, (kw-1)*d)
     grid3 = grid3 && dd >= 1 && dd <= 8;
     for (int t = 0; grid3 && t < 9; ++t)
@@ -1061,11 +1064,15 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
       if (cost < best) { best = cost; best_bn = bn; }
     }
   }
-  if (best_bn == 256 && p.staged && p.tb == 1 && !p.branch_mode) {
-    // CTA pairs (tcgen05 cta_group::2) for the N = 256 layers; VSP_CONV_PAIR=0 keeps the single-CTA kernel
-    static const bool pair_on = getenv("VSP_CONV_PAIR") == nullptr || atoi(getenv("VSP_CONV_PAIR")) != 0;
-    if (pair_on) {
-      const int rc = launch_conv_pair(p, ta, wq, cout_pad, taps_total, stream);
+  if ((best_bn == 256 || best_bn == 128) && p.staged && p.tb == 1) {
+    // CTA pairs (tcgen05 cta_group::2) for the N = 256 / 128 layers; VSP_CONV_PAIR=0 keeps the single-CTA kernel
+    static const int pair_on = getenv("VSP_CONV_PAIR") == nullptr ? 3 : atoi(getenv("VSP_CONV_PAIR"));   // bit 0: N = 256, bit 1: N = 128
+    if (best_bn == 256 && (pair_on & 1)) {
+      const int rc = launch_conv_pair<256>(p, ta, wq, cout_pad, taps_total, stream);
+      if (rc >= 0) return rc;
+    }
+    if (best_bn == 128 && (pair_on & 2)) {
+      const int rc = launch_conv_pair<128>(p, ta, wq, cout_pad, taps_total, stream);
       if (rc >= 0) return rc;
     }
   }
