@@ -266,6 +266,8 @@ typedef struct vsp_conv_epilogue {
   float scale;            /* output gain (sqrt 2)                                      */
   const void *residual;   /* same layout/dtype as the output; added after activation   */
   const void *residual2;  /* second residual (decoder skip fusion out + feat + feat2)  */
+  const float *alpha_vec; /* [cout] per-channel negative slope (PReLU, e4e/models/encoders/helpers.py:76-123): when non-NULL
+                             and act == 3 the activation is v > 0 ? v : alpha_vec[n] * v (times scale), `alpha` is ignored */
 } vsp_conv_epilogue;
 
 /*

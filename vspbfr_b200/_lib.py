@@ -123,6 +123,7 @@ class ConvEpilogue(Structure):
         ("scale", c_float),
         ("residual", c_void_p),
         ("residual2", c_void_p),
+        ("alpha_vec", c_void_p),
     ]
 
 

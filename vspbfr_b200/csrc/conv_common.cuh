@@ -52,6 +52,7 @@ struct ConvParams {
   float alpha, scale;
   const void *residual;
   const void *residual2;
+  const float *alpha_vec;  // per-channel negative slope (PReLU) replacing `alpha` in the second stage
 };
 
 __device__ __forceinline__ uint4 pack8_bf16(const float *v) {
@@ -147,7 +148,8 @@ __device__ __forceinline__ void epi_compute(const ConvParams &p, uint32_t taddr,
     for (int e = 0; e < 4; ++e) {
       float x = __uint_as_float(r[j + e]) * aa[e];
       if (p.pre_act) x = epi_act(x + b1[e], p.pre_act, p.alpha, p.scale);   // stage 1 (SMART fusion conv)
-      x = epi_act(x + nz + b2[e], p.act, p.alpha, p.scale);                   // noise + bias + activation
+      const float al = (p.alpha_vec != nullptr && (fullc || c0 + j + e < ctot)) ? __ldg(p.alpha_vec + c0 + j + e) : p.alpha;
+      x = epi_act(x + nz + b2[e], p.act, al, p.scale);                        // noise + bias + activation
       v[j + e] = live ? x + rsd[j + e] : 0.f;
     }
   }
@@ -224,6 +226,22 @@ __device__ __forceinline__ void epi_lean8f_t(const uint32_t *r, const float *vrs
         const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], nzs + b2[e]);
         v[4 * h + e] = fmaxf(t, t * k.a2);
       }
+    }
+  }
+}
+// PReLU form of the single-stage epilogue (per-channel slope, any sign): t = acc * vrs + (nzs + vb2); out = max(t, 0) + a min(t, 0)
+__device__ __forceinline__ void epi_lean8f_prelu(const uint32_t *r, const float *vrs, const float *vb2, const float *va, float nzs,
+                                                 float (&v)[8]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = reinterpret_cast<const float4 *>(vrs)[h];
+    const float4 c2 = reinterpret_cast<const float4 *>(vb2)[h];
+    const float4 s = reinterpret_cast<const float4 *>(va)[h];
+    const float aa[4] = {a.x, a.y, a.z, a.w}, b2[4] = {c2.x, c2.y, c2.z, c2.w}, sl[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float t = fmaf(__uint_as_float(r[4 * h + e]), aa[e], nzs + b2[e]);
+      v[4 * h + e] = fmaf(sl[e], fminf(t, 0.f), fmaxf(t, 0.f));
     }
   }
 }

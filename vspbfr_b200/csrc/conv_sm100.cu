@@ -36,7 +36,7 @@ struct ConvCfg {
   static constexpr int SBUF_BYTES = 32 * CHUNK * 2;          // staged epilogue: 32 pixels x CHUNK channels bf16
   static constexpr int NBUF = BLOCK_N >= 256 ? 1 : 2;         // staging buffers per epilogue warp (smem budget)
   static constexpr int OSTAGE_BYTES = 8 * NBUF * SBUF_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 6 * BLOCK_N * 4 /*epilogue vectors*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8 * BLOCK_N * 4 /*epilogue vectors*/;
   static constexpr int SMEM_BYTES_STAGED = SMEM_BYTES + OSTAGE_BYTES + 1024;
   static_assert(SMEM_BYTES_STAGED <= 232448, "conv_fprop_kernel exceeds shared memory");
 };
@@ -130,9 +130,10 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   const int wg = (warp - 2) >> 2;         // the two warps of a quadrant alternate accumulator chunks
   const int row = quad * 32 + lane;
   const int et = threadIdx.x - 64;
-  float *vec_rs = epi_vec, *vec_b1 = epi_vec + 2 * BLOCK_N, *vec_b2 = epi_vec + 4 * BLOCK_N;
+  float *vec_rs = epi_vec, *vec_b1 = epi_vec + 2 * BLOCK_N, *vec_b2 = epi_vec + 4 * BLOCK_N, *vec_a = epi_vec + 6 * BLOCK_N;
   const float nw = p.noise ? (p.noise_weight_dev ? __ldg(p.noise_weight_dev) : p.noise_weight) : 0.f;
   const LeanK lk = lean_consts(p);
+  const bool prelu = p.alpha_vec != nullptr && p.act != 0 && p.pre_act == 0;     // per-channel slope (host guarantees the form)
   const int sw = ROW_BYTES == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
   unsigned char *stage = o_buf + (warp - 2) * C::NBUF * C::SBUF_BYTES;
   const long long plane = (long long)p.full_h * p.full_w;
@@ -171,6 +172,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
       vec_rs[acc * BLOCK_N + c] = lean_scale_rs(lk, (ok && p.row_scale) ? __ldg(p.row_scale + (long long)b * creal + cr) : 1.f);
       vec_b1[acc * BLOCK_N + c] = lean_scale_b1(lk, (ok && p.pre_bias) ? __ldg(p.pre_bias + cr) : 0.f);
       vec_b2[acc * BLOCK_N + c] = lean_scale_b2(lk, (ok && p.bias) ? __ldg(p.bias + cr) : 0.f);
+      if (prelu) vec_a[acc * BLOCK_N + c] = ok ? __ldg(p.alpha_vec + cr) : 1.f;
     }
     // noise of this thread's pixel in every output class of the tile, fetched before the accumulator wait
     float nzc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -280,7 +282,8 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
 #pragma unroll
       for (int i = 0; i < PIECES; ++i) {
         float v[8];
-        epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz * lk.m2, lk, v);
+        if (prelu) epi_lean8f_prelu(&r[8 * i], vrs + 8 * i, vb2 + 8 * i, vec_a + acc * BLOCK_N + ch * CHUNK + 8 * i, nz * lk.m2, v);
+        else epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz * lk.m2, lk, v);
         if (has_res) add2_bf16x8(v, own1[i], own2[i]);
         *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
       }
@@ -309,9 +312,9 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   uint64_t *tmem_full = empty_bar + C::STAGES;
   uint64_t *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-  float *epi_vec = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES + 256);  // 6 * BLOCK_N floats
+  float *epi_vec = reinterpret_cast<float *>(smem + C::STAGES * C::STAGE_BYTES + 256);  // 8 * BLOCK_N floats
   unsigned char *o_buf = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(epi_vec + 6 * BLOCK_N) + 1023) & ~uintptr_t(1023));   // STAGED only
+      (reinterpret_cast<uintptr_t>(epi_vec + 8 * BLOCK_N) + 1023) & ~uintptr_t(1023));   // STAGED only
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -433,7 +436,7 @@ struct PairCfg {
   static constexpr int STAGE_BYTES = kABytes + B_HALF_BYTES;
   static constexpr int STAGES = BLOCK_N >= 256 ? 6 : 7;
   static constexpr int OSTAGE_BYTES = ConvCfg<BLOCK_N>::OSTAGE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 6 * BLOCK_N * 4 + OSTAGE_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * BLOCK_N * 4 + OSTAGE_BYTES + 1024;
   static_assert(SMEM_BYTES <= 232448, "conv_fprop_pair_kernel exceeds shared memory");
 };
 
@@ -452,7 +455,7 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
   float *epi_vec = reinterpret_cast<float *>(smem + P::STAGES * P::STAGE_BYTES + 256);
   unsigned char *o_buf = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(epi_vec + 6 * BLOCK_N) + 1023) & ~uintptr_t(1023));
+      (reinterpret_cast<uintptr_t>(epi_vec + 8 * BLOCK_N) + 1023) & ~uintptr_t(1023));
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -571,10 +574,10 @@ struct HaloCfg {
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int B_SLOTS = RESIDENT_B ? 9 : (BLOCK_N >= 256 ? 3 : (BLOCK_N >= 64 ? 6 : 9));
   // three halo stages wherever shared memory allows (the loads are latency bound: bytes in flight matter)
-  static constexpr int A_STAGES = (3 * A_STAGE_BYTES + B_SLOTS * B_BYTES + 1024 + 512 + 6 * BLOCK_N * 4 <= 232448) ? 3 : 2;
+  static constexpr int A_STAGES = (3 * A_STAGE_BYTES + B_SLOTS * B_BYTES + 1024 + 512 + 8 * BLOCK_N * 4 <= 232448) ? 3 : 2;
   static constexpr int B_TOTAL = B_SLOTS * B_BYTES;
   static constexpr int DATA_BYTES = A_STAGES * A_STAGE_BYTES + B_TOTAL;
-  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512 + 6 * BLOCK_N * 4;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 + 512 + 8 * BLOCK_N * 4;
   static_assert(SMEM_BYTES <= 232448, "halo kernel exceeds shared memory");
 };
 
@@ -985,6 +988,8 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     p.act = epi->act; p.alpha = epi->alpha; p.scale = epi->scale; p.residual = epi->residual;
     p.noise = epi->noise; p.noise_bstride = epi->noise_bstride; p.residual2 = epi->residual2;
     p.noise_weight_dev = epi->noise_weight_dev; p.pre_bias = epi->pre_bias; p.pre_act = epi->pre_act;
+    p.alpha_vec = epi->act != 0 ? epi->alpha_vec : nullptr;
+    VSP_REQUIRE(p.alpha_vec == nullptr || p.pre_act == 0, "conv: a per-channel slope needs a single activation stage");
     VSP_REQUIRE(p.pre_act == 0 || p.pre_act == 3, "conv: epilogue pre_act must be 0 or 3");
     VSP_REQUIRE(p.act == 0 || p.act == 3, "conv: epilogue act must be 0 or 3");
   }
@@ -994,15 +999,16 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     static const bool no_staged = getenv("VSP_NO_STAGED") != nullptr;
     const float al = p.alpha, sc = p.scale;
     p.staged = (!no_staged && out_nhwc && (ldo % 8) == 0 && (co_off % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
-                p.tw >= 32 && p.tb == 1 && al >= 0.f && al <= 1.f && (sc > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
+                p.tw >= 32 && p.tb == 1 && ((al >= 0.f && al <= 1.f) || p.alpha_vec != nullptr) &&
+                (sc > 0.f || (p.act == 0 && p.pre_act == 0))) ? 1 : 0;
     if (shuffle_cout) {
       VSP_REQUIRE(os == 2 && oo_h == 0 && oo_w == 0 && shuffle_cout % 32 == 0 && cout == 4 * shuffle_cout,
                   "conv: pixel-shuffle epilogue needs Cout %% 32 == 0");
     }
   }
 
-  // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers
-  {
+  // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers (scalar slopes only)
+  if (p.alpha_vec == nullptr) {
     const int rc = conv_ring_try_launch(p, x, wq, in_h, in_w, cout_pad, taps_total, ntaps == 9 ? tap_dx[8] : 1, stream);
     if (rc >= 0) return rc;
   }
@@ -1012,7 +1018,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     static const bool no_halo = getenv("VSP_NO_HALO") != nullptr;
     // (Cout > 128 goes to the generic kernel: as a CTA pair it runs 256->256 @128^2 in 385 us vs 468 us here)
     static const bool halo_wide = getenv("VSP_HALO_WIDE_N") != nullptr;
-    bool grid3 = !no_halo && !p.branch_mode && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h &&
+    bool grid3 = !no_halo && p.alpha_vec == nullptr && !p.branch_mode && stride == 1 && ntaps == 9 && os == 1 && out_w >= kBlockM && out_w == in_w && out_h == in_h &&
                  (cout <= 128 || halo_wide || !p.staged);
     int dd = grid3 ? tap_dx[8] : 0;   // tap (kh,kw) offset must be ((kh-1)*d, (kw-1)*d)
     grid3 = grid3 && dd >= 1 && dd <= 8;

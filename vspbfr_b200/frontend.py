@@ -39,6 +39,9 @@ def _irse_plan(num_layers):
     return plan
 
 
+_OWN_CONVS = os.environ.get("VSP_FRONT_OWN_CONVS", "1") != "0"     # encoder convolutions on the tcgen05 kernel (inference form)
+
+
 class SEModule(nn.Module):
     """Squeeze-and-excitation gate (helpers.py:56-73)."""
 
@@ -87,6 +90,12 @@ class GradualStyleBlock(nn.Module):
         self.linear = EqualLinear(out_c, out_c, lr_mul=1)
 
     def forward(self, x):
+        if (_OWN_CONVS and x.is_cuda and not self.training and x.dtype == torch.bfloat16
+                and x.is_contiguous(memory_format=torch.channels_last) and Encoder4Editing._own_ok(self.convs[0], x)):
+            # stride-2 conv + bias + LeakyReLU(0.01) as ONE tcgen05 launch per level (the library issues three)
+            for i in range(0, len(self.convs), 2):
+                x = Encoder4Editing._own_conv(x, self.convs[i], act=3, alpha=self.convs[i + 1].negative_slope)
+            return self.linear(x.reshape(-1, self.out_c))
         return self.linear(self.convs(x).view(-1, self.out_c))
 
 
@@ -110,6 +119,31 @@ class Encoder4Editing(nn.Module):
         self.latlayer1 = nn.Conv2d(256, 512, kernel_size=1, stride=1, padding=0)
         self.latlayer2 = nn.Conv2d(128, 512, kernel_size=1, stride=1, padding=0)
 
+    @staticmethod
+    def _own_conv(x_cl, conv, act=0, alpha=0.0, alpha_vec=None):
+        """One nn.Conv2d (groups 1, square kernel, dilation 1, Cin % 8 == 0) of the folded encoder on the tcgen05 implicit-GEMM
+        kernel with bias and activation in its epilogue: x_cl [N,C,H,W] bf16 channels-last -> same form.  The library path
+        launches the convolution, a bias add and the activation as three passes."""
+        from .op import modconv as mc
+
+        k, st, pd = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        cache = conv.__dict__.setdefault("_vsp_packed", {})
+        key = (conv.weight.data_ptr(), conv.weight._version)
+        if cache.get("key") != key:
+            cache["key"] = key
+            cache["wq"] = mc.pack_weights(conv.weight.detach().float().contiguous())[0]
+            cache["bias"] = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        y = mc.conv_fprop(x_cl.permute(0, 2, 3, 1), cache["wq"], conv.out_channels, k, k, st, pd, 1, out_nhwc=True,
+                          epi=mc.make_epilogue(bias=cache["bias"], act=act, alpha=alpha, scale=1.0, alpha_vec=alpha_vec))
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def _own_ok(conv, x):
+        return (isinstance(conv, nn.Conv2d) and conv.groups == 1 and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
+                and conv.kernel_size[0] == conv.kernel_size[1] and conv.dilation == (1, 1) and conv.stride[0] == conv.stride[1]
+                and conv.padding[0] == conv.padding[1] and not isinstance(conv.padding, str) and x.dtype == torch.bfloat16
+                and x.is_contiguous(memory_format=torch.channels_last))
+
     def _body_fused(self, x):
         """Inference form of the backbone after ``fold_for_inference_`` on a CUDA bf16 channels-last activation: per unit,
         SE scale + shortcut add + the NEXT unit's leading BatchNorm run as ONE pass (vsp_se_tail_nhwc_bf16) instead of three
@@ -130,14 +164,23 @@ class Encoder4Editing(nn.Module):
         n_units = len(self.body)
         for i, unit in enumerate(self.body):
             res = unit.res_layer
-            r = res[3](res[2](res[1](z)))
+            if _OWN_CONVS and self._own_ok(res[1], z) and self._own_ok(res[3], z) and isinstance(res[2], nn.PReLU):
+                # conv1 + PReLU (per-channel slope) and conv2 + folded-BatchNorm bias: one tcgen05 launch each
+                slope = res[2].__dict__.get("_vsp_slope")
+                if slope is None or slope.data_ptr() == 0 or res[2].__dict__.get("_vsp_ver") != res[2].weight._version:
+                    slope = res[2].weight.detach().float().contiguous()
+                    res[2].__dict__["_vsp_slope"], res[2].__dict__["_vsp_ver"] = slope, res[2].weight._version
+                r = self._own_conv(self._own_conv(z, res[1], act=3, alpha_vec=slope), res[3])
+            else:
+                r = res[3](res[2](res[1](z)))
             se = res[5] if len(res) > 5 else None
             n, c, h, w = r.shape
             if se is not None:
                 gate = se.sigmoid(se.fc2(se.relu(se.fc1(se.avg_pool(r))))).float().reshape(n, c).contiguous()
             else:
                 gate = torch.ones(n, c, device=r.device, dtype=torch.float32)
-            sc = unit.shortcut_layer(x)
+            scl = unit.shortcut_layer
+            sc = self._own_conv(x, scl) if (_OWN_CONVS and self._own_ok(scl, x)) else scl(x)
             ok = (r.is_contiguous(memory_format=torch.channels_last) and sc.stride(1) == 1 and c % 8 == 0
                   and all(st % 8 == 0 for st in (sc.stride(0), sc.stride(2), sc.stride(3))) and sc.shape == r.shape)
             if not ok:          # unusual layout: the plain composition

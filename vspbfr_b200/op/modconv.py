@@ -173,7 +173,7 @@ def pack_weights(weight, style=None, wscale=1.0, eps=1e-8, transpose=False, want
 
 
 def make_epilogue(row_scale=None, noise=None, noise_weight=0.0, noise_weight_dev=None, bias=None, act=0, alpha=0.2,
-                  scale=1.0, residual=None, residual2=None, pre_bias=None, pre_act=0):
+                  scale=1.0, residual=None, residual2=None, pre_bias=None, pre_act=0, alpha_vec=None):
     """Build a ``vsp_conv_epilogue``; returns (struct, keepalive tuple)."""
     e = ConvEpilogue()
     e.row_scale = row_scale.data_ptr() if row_scale is not None else None
@@ -188,7 +188,8 @@ def make_epilogue(row_scale=None, noise=None, noise_weight=0.0, noise_weight_dev
     e.pre_act = int(pre_act)
     e.residual = residual.data_ptr() if residual is not None else None
     e.residual2 = residual2.data_ptr() if residual2 is not None else None
-    return e, (row_scale, noise, noise_weight_dev, bias, residual, residual2, pre_bias)
+    e.alpha_vec = alpha_vec.data_ptr() if alpha_vec is not None else None
+    return e, (row_scale, noise, noise_weight_dev, bias, residual, residual2, pre_bias, alpha_vec)
 
 
 def _int_array(vals):
