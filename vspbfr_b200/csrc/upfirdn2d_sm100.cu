@@ -23,7 +23,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kK = 4;   // fast path filter extent (smaller filters are zero-extended)
-constexpr int kRO = 2;  // outputs per thread, rows
+// (output rows per thread follow from the tile: Cfg::RO = 2 for the 2048-output tiles, 4 for the 4096-output one)
 constexpr int kCO = 4;  // outputs per thread, cols
 
 struct UfdParams {
@@ -46,11 +46,12 @@ __host__ __device__ constexpr int round_up4(int v) { return (v + 3) & ~3; }
 
 template <int U, int D, int QX, int QY, int TOW, int TOH, int PZ>
 struct Cfg {
-  static constexpr int TX = TOW / kCO, TY = TOH / kRO;
-  static_assert(TX * TY * PZ == kThreads, "tile must map onto 256 threads");
-  static_assert((kRO * D) % U == 0 && (kCO * D) % U == 0, "micro tile must keep the phase");
-  static constexpr int SY = kRO * D / U, SX = kCO * D / U;       // thread stride in input samples
-  static constexpr int WR = (QY + (kRO - 1) * D + kK - 1) / U + 1;  // window rows
+  static constexpr int TX = TOW / kCO, TY = kThreads / (TX * PZ);
+  static constexpr int RO = TOH / TY;                              // output rows per thread
+  static_assert(TX * TY * PZ == kThreads && RO * TY == TOH && RO >= 1, "tile must map onto 256 threads");
+  static_assert((RO * D) % U == 0 && (kCO * D) % U == 0, "micro tile must keep the phase");
+  static constexpr int SY = RO * D / U, SX = kCO * D / U;        // thread stride in input samples
+  static constexpr int WR = (QY + (RO - 1) * D + kK - 1) / U + 1;   // window rows
   static constexpr int WC = (QX + (kCO - 1) * D + kK - 1) / U + 1;  // window cols
   static constexpr int V = (SX % 4 == 0) ? 4 : 2;                 // LDS vector width (floats)
   // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: a misaligned
@@ -84,11 +85,13 @@ __device__ __forceinline__ void lds_row(const float *p, float (&dst)[N]) {
   }
 }
 
-// Micro-tile of kRO x kCO outputs from the staged tile; XS = column shift of the window
+// Micro-tile of RO x kCO outputs from the staged tile; XS = column shift of the window
 // inside the 16-byte-aligned tile (compile time so every LDS stays a 64/128-bit access).
 template <int U, int D, int QX, int QY, int TOW, int TOH, int PZ, int XS>
-__device__ __forceinline__ void micro_tile(const float *wp, const float (&w)[kK][kK], float (&acc)[kRO][kCO]) {
+__device__ __forceinline__ void micro_tile(const float *wp, const float (&w)[kK][kK],
+                                           float (&acc)[Cfg<U, D, QX, QY, TOW, TOH, PZ>::RO][kCO]) {
   using C = Cfg<U, D, QX, QY, TOW, TOH, PZ>;
+  constexpr int kRO = C::RO;
   constexpr int LO = (XS / C::V) * C::V;                               // first aligned column read
   constexpr int NV = ((XS + C::WC + C::V - 1) / C::V) * C::V - LO;     // columns read (multiple of V)
   float win[C::WR][NV];
@@ -224,6 +227,7 @@ upfirdn2d_tile_kernel(const UfdParams p, const __grid_constant__ CUtensorMap tma
     }
 
     // ---- compute the 2x4 micro tile (uniform switch on the alignment shift)
+    constexpr int kRO = C::RO;
     float acc[kRO][kCO];
     const float *wp = tile + (tz * C::TIH + ty * C::SY) * C::TIW + tx * C::SX;
     switch (xs) {
@@ -862,6 +866,10 @@ int dispatch_tile(const UfdParams &p, cudaStream_t stream) {
   if constexpr (D == 2) {
     if (ow > 32) return launch_tile<U, D, QX, QY, 64, 32, 1>(p, stream);
   } else {
+    if constexpr (U == 2) {        // four output rows per thread: the 2 x 4 micro-tile was issue-bound (24 instructions per output)
+      static const bool ro2 = getenv("VSP_UFD_RO2") != nullptr;
+      if (ow > 64 && oh >= 32 && !ro2) return launch_tile<U, D, QX, QY, 128, 32, 1>(p, stream);
+    }
     if (ow > 64) return launch_tile<U, D, QX, QY, 128, 16, 1>(p, stream);
     if (ow > 32) return launch_tile<U, D, QX, QY, 64, 32, 1>(p, stream);
   }
