@@ -907,6 +907,7 @@ struct BandParams {
   long long units;
   long long total_floats;   // elements of x (bulk copies never read past the last whole 16 bytes)
   unsigned magic_ow, magic_pp;   // floor(2^32 / d) + 1 for d = out_w and d = G * out_w (items per plane when P > 1)
+  int dn;                   // decimation factor (1: blur, 2: the Downsample / Upsample-backward mode), both axes
 };
 
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -938,8 +939,8 @@ __device__ __forceinline__ BandUnit band_unit(const BandParams &p, long long uni
     b.np = 1;
     b.oy0 = (int)(unit % p.upp) * p.G * kBandR;
     b.rows = min(p.G * kBandR, u.out_h - b.oy0);
-    b.iy_lo = max(0, b.oy0 - u.pad_y0);
-    iy_hi = min(u.in_h, b.oy0 + b.rows - 1 - u.pad_y0 + u.kh);
+    b.iy_lo = max(0, b.oy0 * p.dn - u.pad_y0);
+    iy_hi = min(u.in_h, (b.oy0 + b.rows - 1) * p.dn - u.pad_y0 + u.kh);
     if (iy_hi < b.iy_lo) iy_hi = b.iy_lo;
     b.iy_hi = iy_hi;
   }
@@ -953,7 +954,7 @@ __device__ __forceinline__ BandUnit band_unit(const BandParams &p, long long uni
 // group) run a predicate-free body: one shared-memory pointer bumped by the row pitch, four LDS at immediate offsets, the
 // horizontal 4-tap product and the vertical scatter — 13 instructions per input row and column; items touching the image
 // border take the predicated form.
-template <bool SEP>
+template <bool SEP, int DN>
 __device__ __forceinline__ void band_compute(const BandParams &p, unsigned char *band_smem, uint64_t *full, uint64_t *empty,
                                              const float *filt, const float *sep) {
   const UfdParams &u = p.u;
@@ -1000,31 +1001,32 @@ __device__ __forceinline__ void band_compute(const BandParams &p, unsigned char 
       const int g = (int)__umulhi((unsigned)rem, p.magic_ow), ox = rem - g * out_w;
       const int r0 = b.oy0 + g * kBandR;                            // first output row of this item
       const int nr = live ? min(kBandR, b.oy0 + b.rows - r0) : 0;
-      const int cx = ox - u.pad_x0;                                  // input column of tap jx = 0
-      const int iy0 = r0 - u.pad_y0;                                 // input row of tap jy = 0 of output row r0
+      constexpr int kRowsIn = DN * (kBandR - 1) + kK;              // input rows one item walks
+      const int cx = ox * DN - u.pad_x0;                             // input column of tap jx = 0
+      const int iy0 = r0 * DN - u.pad_y0;                            // input row of tap jy = 0 of output row r0
       const float *colp = sm + (base0 + pl * (int)plane_sz + cx);    // &x[plane, 0, cx]
       float acc[kBandR];
 #pragma unroll
       for (int q = 0; q < kBandR; ++q) acc[q] = 0.f;
-      const bool interior = nr == kBandR && cx >= 0 && cx + kK - 1 < in_w && iy0 >= 0 && iy0 + kBandR + kK - 2 < in_h;
+      const bool interior = nr == kBandR && cx >= 0 && cx + kK - 1 < in_w && iy0 >= 0 && iy0 + kRowsIn - 1 < in_h;
       if (__all_sync(0xffffffffu, interior)) {
         const float *sr = colp + iy0 * in_w;
 #pragma unroll
-        for (int t = 0; t < kBandR + kK - 1; ++t) {
+        for (int t = 0; t < kRowsIn; ++t) {
           const float v0 = sr[0], v1 = sr[1], v2 = sr[2], v3 = sr[3];
           sr += in_w;
           if constexpr (SEP) {
             const float h = fmaf(v3, fx[3], fmaf(v2, fx[2], fmaf(v1, fx[1], v0 * fx[0])));
 #pragma unroll
             for (int jy = 0; jy < kK; ++jy) {
-              const int q = t - jy;
-              if (q >= 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
+              const int q = (t - jy) / DN;
+              if (t - jy >= 0 && (t - jy) % DN == 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
             }
           } else {
 #pragma unroll
             for (int jy = 0; jy < kK; ++jy) {
-              const int q = t - jy;
-              if (q >= 0 && q < kBandR)
+              const int q = (t - jy) / DN;
+              if (t - jy >= 0 && (t - jy) % DN == 0 && q < kBandR)
                 acc[q] = fmaf(v3, w2[jy * kK + 3], fmaf(v2, w2[jy * kK + 2], fmaf(v1, w2[jy * kK + 1], fmaf(v0, w2[jy * kK], acc[q]))));
             }
           }
@@ -1036,11 +1038,11 @@ __device__ __forceinline__ void band_compute(const BandParams &p, unsigned char 
         const bool in0 = any && cx >= 0 && cx < in_w, in1 = any && cx + 1 >= 0 && cx + 1 < in_w,
                    in2 = any && cx + 2 >= 0 && cx + 2 < in_w, in3 = any && cx + 3 >= 0 && cx + 3 < in_w;
 #pragma unroll
-        for (int t = 0; t < kBandR + kK - 1; ++t) {
+        for (int t = 0; t < kRowsIn; ++t) {
           const int iy = iy0 + t;
           const float *sr = colp + min(max(iy, ylo), yhi - 1) * in_w;
           const float v0 = in0 ? sr[0] : 0.f, v1 = in1 ? sr[1] : 0.f, v2 = in2 ? sr[2] : 0.f, v3 = in3 ? sr[3] : 0.f;
-          const bool rv = (unsigned)iy < (unsigned)in_h && t < nr + kK - 1;
+          const bool rv = (unsigned)iy < (unsigned)in_h && t < DN * (nr - 1) + kK;
           if constexpr (SEP) {
             float h = fmaf(v3, fx[3], fmaf(v2, fx[2], fmaf(v1, fx[1], v0 * fx[0])));
             h = rv ? h : 0.f;
@@ -1148,27 +1150,40 @@ upfirdn2d_band_kernel(const BandParams p) {
   }
 
   // ===================== compute warps =====================
-  if (sep[2 * kK] != 0.f) band_compute<true>(p, band_smem, full, empty, filt, sep);
-  else band_compute<false>(p, band_smem, full, empty, filt, sep);
+  if (p.dn == 2) {
+    if (sep[2 * kK] != 0.f) band_compute<true, 2>(p, band_smem, full, empty, filt, sep);
+    else band_compute<false, 2>(p, band_smem, full, empty, filt, sep);
+  } else {
+    if (sep[2 * kK] != 0.f) band_compute<true, 1>(p, band_smem, full, empty, filt, sep);
+    else band_compute<false, 1>(p, band_smem, full, empty, filt, sep);
+  }
 }
 
-int launch_band(const UfdParams &u, cudaStream_t stream) {
+int launch_band(const UfdParams &u, int dn, cudaStream_t stream) {
   BandParams p;
   p.u = u;
+  p.dn = dn;
   const long long row_bytes = (long long)u.in_w * 4;
   const long long plane_bytes = row_bytes * u.in_h;
   const long long budget = kBandStageBytes - 64;           // alignment over-fetch at both ends
   if (2 * plane_bytes <= budget) {
     // small planes: several whole planes per unit, but keep >= 3 units per SM in flight when the tensor allows it
-    long long P = budget / plane_bytes;
-    while (P > 1 && (u.major + P - 1) / P < 3LL * num_sms()) --P;
+    // the P that wastes least of the last wave of units over the SMs (each SM holds one CTA); larger P on near-ties
+    long long P = 1;
+    double best = -1.0;
+    for (long long c = budget / plane_bytes; c >= 1; --c) {
+      const long long un = (u.major + c - 1) / c;
+      const long long waves = (un + num_sms() - 1) / num_sms();
+      const double eff = (double)un / (double)(waves * num_sms());
+      if (eff > best + 0.03) { best = eff; P = c; }
+    }
     p.P = (int)P;
     p.G = (u.out_h + kBandR - 1) / kBandR;
     p.upp = 1;
     p.units = (u.major + P - 1) / P;
   } else {
-    long long in_rows = budget / row_bytes;                 // input rows a stage holds
-    long long G = (in_rows - (u.kh - 1)) / kBandR;
+    long long in_rows = budget / row_bytes;                 // input rows a stage holds: dn * (G * R - 1) + kh of them are needed
+    long long G = ((in_rows - u.kh) / dn + 1) / kBandR;
     if (G < 1) return -1;                                   // one row group does not fit: caller falls back
     const long long gmax = (u.out_h + kBandR - 1) / kBandR;
     if (G > gmax) G = gmax;
@@ -1243,12 +1258,20 @@ extern "C" int vsp_upfirdn2d_f32(const float *x, const float *filt, float *y, in
       static const bool odd_only = getenv("VSP_BAND_ODD_ONLY") != nullptr;
       if ((!p.use_tma || !odd_only) && !no_band && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && out_w >= 32 &&
           major < (1LL << 31)) {
-        const int rc = launch_band(p, stream);
+        const int rc = launch_band(p, 1, stream);
         if (rc >= 0) return rc;
       }
       return dispatch_tile<1, 1, 0, 0>(p, stream);
     }
-    if (up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) return dispatch_tile<1, 2, 0, 0>(p, stream);
+    if (up_x == 1 && up_y == 1 && down_x == 2 && down_y == 2) {
+      // decimation by 2 (Downsample, the backward of Upsample): the same row bands, two input rows / columns per output
+      static const bool no_band2 = getenv("VSP_NO_BAND2") != nullptr;
+      if (!no_band2 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && out_w >= 32 && major < (1LL << 31)) {
+        const int rc = launch_band(p, 2, stream);
+        if (rc >= 0) return rc;
+      }
+      return dispatch_tile<1, 2, 0, 0>(p, stream);
+    }
     if (up_x == 2 && up_y == 2 && down_x == 1 && down_y == 1) {
       // tile origins are even, so the phase of the first tap is fixed by the pad parity
       const int qx = pmod(-pad_x0, 2), qy = pmod(-pad_y0, 2);
