@@ -1048,15 +1048,15 @@ __device__ __forceinline__ void band_compute(const BandParams &p, unsigned char 
             h = rv ? h : 0.f;
 #pragma unroll
             for (int jy = 0; jy < kK; ++jy) {
-              const int q = t - jy;
-              if (q >= 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
+              const int q = (t - jy) / DN;
+              if (t - jy >= 0 && (t - jy) % DN == 0 && q < kBandR) acc[q] = fmaf(h, fy[jy], acc[q]);
             }
           } else {
             const float z0 = rv ? v0 : 0.f, z1 = rv ? v1 : 0.f, z2 = rv ? v2 : 0.f, z3 = rv ? v3 : 0.f;
 #pragma unroll
             for (int jy = 0; jy < kK; ++jy) {
-              const int q = t - jy;
-              if (q >= 0 && q < kBandR)
+              const int q = (t - jy) / DN;
+              if (t - jy >= 0 && (t - jy) % DN == 0 && q < kBandR)
                 acc[q] = fmaf(z3, w2[jy * kK + 3], fmaf(z2, w2[jy * kK + 2], fmaf(z1, w2[jy * kK + 1], fmaf(z0, w2[jy * kK], acc[q]))));
             }
           }
