@@ -222,6 +222,11 @@ def main():
     if args.graph:
         fastpath.restore_faces(net, dec, low_d[:micro], codes_d[:micro], [z_d[:micro]])
         graphed = fastpath.GraphedRestorer(net, dec, micro, device=dev)
+    # a shard that is ONE micro-batch (one rank of an 8-GPU job) has nothing to overlap its result copy with: for the
+    # host-buffer path the restorer's last level runs in 4 sample groups whose rows leave while the next groups compute
+    graphed_e2e = graphed
+    if graphed is not None and n_micro == 1 and micro % 4 == 0 and os.environ.get("VSP_NO_TAIL_GROUPS") is None:
+        graphed_e2e = fastpath.GraphedRestorer(net, dec, micro, device=dev, tail_groups=4)
 
     def step_resident():
         for m in range(n_micro):
@@ -234,7 +239,7 @@ def main():
     def step_e2e():
         # the public host-buffer API: pinned H2D of every micro-batch's inputs and D2H of its restored images are part of
         # the timed region (copy streams overlap them with the kernels of the neighbouring micro-batches)
-        sharding.restore_from_host(net, dec, low_h, codes_h, z_h, out_h, micro=micro, device=dev, restorer=graphed)
+        sharding.restore_from_host(net, dec, low_h, codes_h, z_h, out_h, micro=micro, device=dev, restorer=graphed_e2e)
 
     def barrier():
         if world > 1:

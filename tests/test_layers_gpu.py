@@ -270,6 +270,50 @@ def test_graphed_restorer_matches_eager_and_feeds_host_pipeline():
     np.testing.assert_array_equal(out_a.numpy(), out_b.numpy())
 
 
+@pytest.mark.parametrize("size,micro,groups", [(None, 4, 2), (128, 8, 4)])
+def test_grouped_tail_restorer_is_bit_identical_and_streams_groups(size, micro, groups):
+    """GraphedRestorer(tail_groups=G): the restorer's last level as G per-group graphs == the one-graph restorer, with live
+    noise paths (explicit noise images, weights 0.05), and through sharding.restore_from_host the rows of every group reach
+    the host buffer (per-group device->host copies enqueued between the tail graphs)."""
+    from vspbfr_b200 import sharding
+    if size is None:
+        net, dec = _build_nets()
+        size = int(NET["size"])
+    else:
+        torch.manual_seed(3)
+        net = Restoration_net(size, 512, 2, channel_multiplier=2).to(DEV).eval()
+        dec = Generator(2 * size, 512, 2, channel_multiplier=2).to(DEV).eval()
+    n_latent = dec.n_latent
+    _set_noise_weights((net, dec), 0.05)
+    g = torch.Generator().manual_seed(8)
+    low = (torch.rand(micro, 3, size, size, generator=g) * 2 - 1).to(DEV)
+    codes = torch.randn(micro, n_latent, 512, generator=g).to(DEV)
+    z = torch.randn(micro, 512, generator=g).to(DEV)
+    dsh, nsh = fp.noise_shapes(net, dec, micro)
+    dn = [torch.randn(sh, generator=g).to(DEV) for sh in dsh]
+    nn_ = {k: [torch.randn(sh, generator=g).to(DEV) for sh in v] for k, v in nsh.items()}
+    one = fp.GraphedRestorer(net, dec, micro, n_latent=n_latent, device=DEV, explicit_noise=True)
+    grp = fp.GraphedRestorer(net, dec, micro, n_latent=n_latent, device=DEV, explicit_noise=True, tail_groups=groups)
+    assert grp.tail_groups == groups and len(grp.graph_tail) == groups
+    one.set_noise(dn, nn_)
+    grp.set_noise(dn, nn_)
+    want, _ = one(low, codes, z)
+    seen = []
+    got, _ = grp(low, codes, z, on_group=lambda gi, lo, hi, r: seen.append((gi, lo, hi)))
+    assert seen == [(i, i * micro // groups, (i + 1) * micro // groups) for i in range(groups)]
+    torch.testing.assert_close(got, want, rtol=0, atol=0)
+    eager, _ = fp.restore_faces(net, dec, low, codes, [z], dec_noise=dn, net_noise=nn_)
+    torch.testing.assert_close(got, eager, rtol=0, atol=0)
+    # host pipeline: one micro-batch shard (grouped copies) and a two-micro-batch job
+    for n in (micro, 2 * micro):
+        lh = low.repeat(n // micro, 1, 1, 1).cpu().pin_memory()
+        ch, zh = codes.repeat(n // micro, 1, 1).cpu().pin_memory(), z.repeat(n // micro, 1).cpu().pin_memory()
+        out = torch.zeros(n, 3, size, size).pin_memory()
+        sharding.restore_from_host(net, dec, lh, ch, zh, out, micro=micro, device=DEV, restorer=grp)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.numpy(), want.repeat(n // micro, 1, 1, 1).cpu().numpy())
+
+
 def test_full_size_hot_path_matches_cpu_oracle():
     """BASELINE-size parity: style decoder @1024 + Restoration_net @512 (random init, noise weights 0, batch 2) through
     the fused sm_100a pipeline — row-ring / kh-fold / fused up-conv / branch / low-resolution kernels at the sizes

@@ -226,10 +226,22 @@ def _banks_for(owner, build):
     return hit[0]
 
 
+_bank_rows = None      # slice of the batch the current calls work on (tail groups of restoration_forward), or None
+
+
+def _rows(t):
+    return t if (_bank_rows is None or t is None) else t[_bank_rows].contiguous()
+
+
 def _modulation(lin, style):
     """s = modulation(style): from the pass's ModulationBank when one is active, else a plain linear."""
     hit = _mod_ctx.get(id(lin))
-    return hit if hit is not None else _linear(lin, style)
+    return _rows(hit) if hit is not None else _linear(lin, style)
+
+
+def _demod_pre(obj):
+    """Demodulation coefficients of ``obj`` from the pass's ModulationBank (rows of the current batch slice), or None."""
+    return _rows(_demod_ctx.get(id(obj)))
 
 
 _sep_cache: dict = {}
@@ -316,7 +328,7 @@ def styled_conv(m: StyledConv, x, style, noise=None, residual=None, residual2=No
     s = _modulation(conv.modulation, style)
     w4 = conv.weight.detach().view(cout, cin, k, k)
     wsq = _conv_wsq(conv) if conv.demodulate else None
-    d_pre = _demod_ctx.get(id(conv)) if conv.demodulate else None      # from the pass's ModulationBank, if any
+    d_pre = _demod_pre(conv) if conv.demodulate else None      # from the pass's ModulationBank, if any
     act = dict(bias=m.activate.bias.detach(), act=3, alpha=m.activate.negative_slope, scale=m.activate.scale,
                noise_weight_dev=m.noise.weight.detach())
     if h * w <= _LOWRES_PIXELS and cin % 64 == 0 and x.shape[3] == cin:
@@ -398,7 +410,7 @@ def smart_layer(m: SMART_layer, x, style, noise=None):
     s = _modulation(m.modulation, style)
     wcat = _smart_wcat(m)
     wsq = _smart_wsq(m) if branches[0].demodulate else None
-    d_pre = _demod_ctx.get(id(m)) if branches[0].demodulate else None
+    d_pre = _demod_pre(m) if branches[0].demodulate else None
     dils = [br.dilation for br in branches]
     # one launch for all branches: the generic kernel's branch mode up to 64 pixels wide, the kh-folded row-ring kernel's
     # branch slices (x read from HBM once, the other three branches hit L2) for the wide 16/32-channel branches
@@ -522,7 +534,7 @@ def smart_layer_split(m: SMART_layer, x, style, noise=None):
     cout = cq * len(branches)
     s = _modulation(m.modulation, style)
     wsq = _smart_wsq(m) if branches[0].demodulate else None
-    d_pre = _demod_ctx.get(id(m)) if branches[0].demodulate else None
+    d_pre = _demod_pre(m) if branches[0].demodulate else None
     d = (d_pre if d_pre is not None else mc.demod_from_wsq(s, wsq, branches[0].scale, branches[0].eps)) if wsq is not None else None
     wq = _split3_weights(m, "wq_split3", [br.weight for br in branches], lambda: _smart_wcat(m), branches[0].scale)
     buf = mc.conv_branches(_split3_nhwc(x, s), wq, cout, [br.dilation for br in branches], out_nhwc=False, algo_cin=cin,
@@ -547,7 +559,7 @@ def styled_conv_down_split(m, x, style, noise=None):
     s = _modulation(conv.modulation, style)
     d = None
     if conv.demodulate:
-        d = _demod_ctx.get(id(conv))
+        d = _demod_pre(conv)
         if d is None:
             d = mc.demod_from_wsq(s, _conv_wsq(conv), conv.scale, conv.eps)
     xb = upfirdn2d_raw((x * s[:, :, None, None]).contiguous(), conv.blur.kernel, (1, 1), (1, 1), tuple(conv.blur.pad) * 2)
@@ -708,7 +720,8 @@ def _as_nhwc(t):
 @torch.no_grad()
 @_clears_banks
 def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_index=None, truncation=1,
-                        truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True):
+                        truncation_latent=None, input_is_latent=False, noise=None, randomize_noise=True, tail_groups=1,
+                        tail_hook=None):
     """``Restoration_net.forward`` (models/RestoreNet.py:968-1046) as a fused pipeline.
     images [B,3,S,S] fp32 -> restored [B,3,S,S] fp32."""
     b = images.shape[0]
@@ -773,8 +786,33 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     out = smart_layer(net.conv1, features[0], sty(0), noise[0])
     skip = to_rgb(net.to_rgb1, out, sty(1))
     i = 1
-    for up, smart, n_up, n_smart, rgb in zip(net.convs[::2], net.convs[1::2], noise[1::2], noise[2::2], net.to_rgbs):
+    levels = list(zip(net.convs[::2], net.convs[1::2], noise[1::2], noise[2::2], net.to_rgbs))
+    for li, (up, smart, n_up, n_smart, rgb) in enumerate(levels):
         level = (i + 1) // 2
+        if li == len(levels) - 1 and tail_groups > 1 and b % tail_groups == 0:
+            # Last level in sample groups (images are independent): a caller that streams results to the host copies group g
+            # while groups g+1.. still compute (``tail_hook(g, lo, hi, restored)`` runs between groups; under CUDA-graph
+            # capture it ends one graph and begins the next).  Same kernels on batch slices: results are bit-identical.
+            global _bank_rows
+            restored = torch.empty((b, 3) + tuple(images.shape[2:]), dtype=torch.float32, device=images.device)
+            gsz = b // tail_groups
+            res1, res2 = features[level], _as_nhwc(de_feats[level])
+            if tail_hook is not None:
+                tail_hook(-1, 0, 0, restored)                 # everything before the tail has been enqueued
+            try:
+                for g in range(tail_groups):
+                    lo, hi = g * gsz, (g + 1) * gsz
+                    _bank_rows = slice(lo, hi)
+                    cut = lambda t: None if t is None else (t if t.shape[0] == 1 else t[lo:hi])
+                    o = styled_conv(up, out[lo:hi], sty(i)[lo:hi], cut(n_up), residual=res1[lo:hi], residual2=res2[lo:hi])
+                    o = smart_layer(smart, o, sty(i + 1)[lo:hi], cut(n_smart))
+                    restored[lo:hi] = to_rgb(rgb, o, sty(i + 2)[lo:hi], skip[lo:hi])
+                    if tail_hook is not None:
+                        tail_hook(g, lo, hi, restored)
+            finally:
+                _bank_rows = None
+            _bank_clear()
+            return restored
         out = styled_conv(up, out, sty(i), n_up, residual=features[level], residual2=_as_nhwc(de_feats[level]))
         out = smart_layer(smart, out, sty(i + 1), n_smart)
         skip = to_rgb(rgb, out, sty(i + 2), skip)
@@ -840,9 +878,10 @@ def decode_stage(decoder, codes, size, out_n_latent=16, noise=None):
 
 
 @torch.no_grad()
-def restore_stage(net, low_imgs, feats, codes, noise_styles, noise=None):
+def restore_stage(net, low_imgs, feats, codes, noise_styles, noise=None, tail_groups=1, tail_hook=None):
     """Second half of :func:`restore_faces`: the restoration network on the degraded images and the decoder features."""
-    return restoration_forward(net, low_imgs, feats, codes, noise_styles, noise=noise)
+    return restoration_forward(net, low_imgs, feats, codes, noise_styles, noise=noise, tail_groups=tail_groups,
+                               tail_hook=tail_hook)
 
 
 @torch.no_grad()
@@ -882,7 +921,8 @@ class GraphedRestorer:
     ``micro`` rows; outputs are copies (the static output buffers are overwritten by the next replay) unless
     ``clone=False``."""
 
-    def __init__(self, net, decoder, micro, size=None, n_latent=None, device=None, warmup=2, explicit_noise=False):
+    def __init__(self, net, decoder, micro, size=None, n_latent=None, device=None, warmup=2, explicit_noise=False,
+                 tail_groups=1):
         device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         size = size or net.size
         n_latent = n_latent or decoder.n_latent
@@ -911,8 +951,35 @@ class GraphedRestorer:
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.image, feats = decode_stage(decoder, self.codes, size, noise=self.dec_noise)
-        with torch.cuda.graph(self.graph_restore, pool=self.graph.pool()):
-            self.restored = restore_stage(net, self.low, feats, self.codes, [self.z], noise=self.net_noise)
+        # tail_groups > 1: the restorer's last level runs in sample groups, each its own graph, so that a caller streaming the
+        # results to the host can copy group g while groups g+1.. compute (``on_group`` of __call__): for a shard that is a
+        # single micro-batch (one rank of an 8-GPU job) the device->host copy of the result is otherwise fully exposed
+        self.tail_groups = tail_groups if (tail_groups > 1 and micro % tail_groups == 0) else 1
+        self.graph_tail = []
+        if self.tail_groups == 1:
+            with torch.cuda.graph(self.graph_restore, pool=self.graph.pool()):
+                self.restored = restore_stage(net, self.low, feats, self.codes, [self.z], noise=self.net_noise)
+        else:
+            state = {"cm": torch.cuda.graph(self.graph_restore, pool=self.graph.pool())}
+
+            def hook(g, lo, hi, restored):
+                state["cm"].__exit__(None, None, None)         # ends the main graph (g == -1) or tail graph g
+                if g + 1 < self.tail_groups:
+                    nxt = torch.cuda.CUDAGraph()
+                    self.graph_tail.append(nxt)
+                    state["cm"] = torch.cuda.graph(nxt, pool=self.graph.pool())
+                    state["cm"].__enter__()
+                else:
+                    state["cm"] = None
+
+            state["cm"].__enter__()
+            try:
+                self.restored = restore_stage(net, self.low, feats, self.codes, [self.z], noise=self.net_noise,
+                                              tail_groups=self.tail_groups, tail_hook=hook)
+            finally:
+                if state["cm"] is not None:                    # an exception between hooks: leave capture mode
+                    state["cm"].__exit__(None, None, None)
+            _bank_clear()
         self.launches = _lib.launch_count() - n0          # sm_100a kernels of this library inside one replay of both
 
     def set_noise(self, dec_noise, net_noise):
@@ -925,9 +992,10 @@ class GraphedRestorer:
             for dst, src in zip(self.net_noise[key], net_noise[key]):
                 dst.copy_(src, non_blocking=True)
 
-    def __call__(self, low, codes, z, clone=True, before_low=None):
+    def __call__(self, low, codes, z, clone=True, before_low=None, on_group=None):
         """``before_low``: optional callable run after the decoder half has been enqueued and before ``low`` is read (e.g.
-        ``lambda: stream.wait_event(low_arrived)``)."""
+        ``lambda: stream.wait_event(low_arrived)``).  ``on_group(g, lo, hi, restored)`` (``tail_groups`` > 1): called after
+        the kernels of samples [lo, hi) have been enqueued — ``restored[lo:hi]`` is final once they finish."""
         if low.shape[0] != self.micro:
             raise ValueError(f"GraphedRestorer captured for micro-batch {self.micro}, got {low.shape[0]}")
         self.codes.copy_(codes, non_blocking=True)
@@ -937,6 +1005,11 @@ class GraphedRestorer:
             before_low()
         self.low.copy_(low, non_blocking=True)
         self.graph_restore.replay()
+        gsz = self.micro // self.tail_groups
+        for g, tail in enumerate(self.graph_tail):
+            tail.replay()
+            if on_group is not None:
+                on_group(g, g * gsz, (g + 1) * gsz, self.restored)
         if clone:
             return self.restored.clone(), self.image.clone()
         return self.restored, self.image

@@ -104,6 +104,30 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
         if i + 1 < len(spans):
             stage_in(i + 1)                                # prefetch while this batch computes
         lo, co, zz = (t[:e - s] for t in stage[k])
+        if split and e - s == micro and getattr(restorer, "tail_groups", 1) > 1:
+            # grouped tail: the restorer's last level runs in sample groups; each group's rows go to the host while the
+            # following groups still compute (the only exposed copy is the last group's)
+            compute.wait_event(loaded_small[k])
+            for c in copied:
+                if c is not None:
+                    compute.wait_event(c[0])               # the static output buffer is free again
+            evs = []
+
+            def on_group(g, glo, ghi, restored, s=s, evs=evs):
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                d2h.wait_event(ready)
+                with torch.cuda.stream(d2h):
+                    out_h[s + glo:s + ghi].copy_(restored[glo:ghi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(d2h)
+                evs.append(ev)
+
+            restored, _ = restorer(lo, co, zz, clone=False, before_low=lambda k=k: compute.wait_event(loaded[k]),
+                                   on_group=on_group)
+            consumed[k].record(compute)
+            copied[k] = (evs[-1], restored)
+            continue
         if split and e - s == micro:
             # the style-decoder half starts as soon as the codes are on the device; the image copy overlaps it
             compute.wait_event(loaded_small[k])
