@@ -241,6 +241,13 @@ def main():
         # the timed region (copy streams overlap them with the kernels of the neighbouring micro-batches)
         sharding.restore_from_host(net, dec, low_h, codes_h, z_h, out_h, micro=micro, device=dev, restorer=graphed_e2e)
 
+    out_u8 = torch.empty(per_rank, SIZE, SIZE, 3, dtype=torch.uint8).pin_memory()
+
+    def step_e2e_u8():
+        # same call, results quantised on the device to the bytes save_image(normalize=True, range=(-1, 1)) writes
+        # (restoration_test.py:138-157): a quarter of the device->host traffic.  Reported beside `e2e`, never instead of it.
+        sharding.restore_from_host(net, dec, low_h, codes_h, z_h, out_u8, micro=micro, device=dev, restorer=graphed_e2e)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -277,6 +284,8 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     step_e2e()
     t_e2e = timed(step_e2e, args.steps)
+    step_e2e_u8()
+    t_e2e_u8 = timed(step_e2e_u8, args.steps)
     if os.environ.get("VSP_BENCH_RECHECK"):     # diagnostic: resident path again after the e2e run (clock / power drift)
         t_again = timed(step_resident, args.steps)
         if rank == 0:
@@ -294,7 +303,12 @@ def main():
         "dtype": "bf16", "data": "synthetic", "config": workload_config(args, micro),
         "e2e": {"value": e2e, "unit": UNIT,
                 "h2d_bytes_per_step": world * (low_h.numel() + codes_h.numel() + z_h.numel()) * 4,
-                "d2h_bytes_per_step": world * out_h.numel() * 4},
+                "d2h_bytes_per_step": world * out_h.numel() * 4,
+                "tail_groups": getattr(graphed_e2e, "tail_groups", 1) if graphed_e2e is not None else 1},
+        "e2e_u8_output": {"value": TOTAL_IMAGES * args.steps / t_e2e_u8, "unit": UNIT,
+                          "d2h_bytes_per_step": world * out_u8.numel(),
+                          "note": "same host-buffer call with the restored images quantised on the device to the 8-bit HWC "
+                                  "bytes the reference's save_image writes (extra information; `e2e` is the fp32 contract figure)"},
         "gpu_launches": int(lt.item()), "clocks": clk,
         "host_enqueue_ms_per_step": 1e3 * host_enqueue / args.steps,   # rank 0's Python + launch time; < ms_per_step = GPU-bound
     }

@@ -118,3 +118,29 @@ def test_restore_folder_runs_the_reference_test_loop(tmp_path):
         np.testing.assert_array_equal(got, quantize_u8(low)[0].cpu().numpy())
         r = np.asarray(Image.open(os.path.join(out, f"{i:06d}_0_toy_restore.png")).convert("RGB"))
         assert r.shape == (size, size, 3) and r.std() > 0
+
+
+@pytest.mark.gpu
+def test_restore_from_host_uint8_output_equals_quantised_fp32_output():
+    """sharding.restore_from_host with a uint8 [N,S,S,3] host buffer returns exactly quantize_u8 of its fp32 result
+    (eager micro-batches, a ragged tail, and the grouped-tail graph restorer)."""
+    from vspbfr_b200 import fastpath as fp, sharding
+    from vspbfr_b200.imageio import quantize_u8
+    from vspbfr_b200.restorenet import Restoration_net
+    from vspbfr_b200.stylegan2 import Generator
+    torch.manual_seed(2)
+    size, micro, n = 64, 4, 10
+    net = Restoration_net(size, 512, 2, channel_multiplier=2).cuda().eval()
+    dec = Generator(2 * size, 512, 2, channel_multiplier=2).cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    low = (torch.rand(n, 3, size, size, generator=g) * 2 - 1).pin_memory()
+    codes = torch.randn(n, dec.n_latent, 512, generator=g).pin_memory()
+    z = torch.randn(n, 512, generator=g).pin_memory()
+    out_f = torch.empty(n, 3, size, size).pin_memory()
+    out_u = torch.empty(n, size, size, 3, dtype=torch.uint8).pin_memory()
+    for restorer in (None, fp.GraphedRestorer(net, dec, micro, n_latent=dec.n_latent, device="cuda", tail_groups=2)):
+        sharding.restore_from_host(net, dec, low, codes, z, out_f, micro=micro, device="cuda", restorer=restorer)
+        sharding.restore_from_host(net, dec, low, codes, z, out_u, micro=micro, device="cuda", restorer=restorer)
+        torch.cuda.synchronize()
+        want = quantize_u8(out_f.cuda()).cpu()
+        assert torch.equal(out_u, want)

@@ -62,8 +62,9 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
     overlap the kernels of batch m (restoration_test.py:125-157 moves every batch synchronously).  Device staging
     buffers are two persistent sets guarded by events — nothing is allocated or freed across streams inside the loop.
 
-    low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S]; returns when every device->host copy
-    has completed.  ``restorer`` (e.g. a ``fastpath.GraphedRestorer`` captured for ``micro``) replaces the eager
+    low_h [N,3,S,S], codes_h [N,18,512], noise_z_h [N,512] -> out_h [N,3,S,S] fp32, or — when ``out_h`` is a uint8
+    [N,S,S,3] buffer — the images quantised on the device exactly as ``save_image(normalize=True, range=(-1, 1))`` would
+    (imageio.quantize_u8: a quarter of the device->host bytes); returns when every device->host copy has completed.  ``restorer`` (e.g. a ``fastpath.GraphedRestorer`` captured for ``micro``) replaces the eager
     ``fastpath.restore_faces`` call for full micro-batches: ``restorer(low, codes, z) -> (restored, image)`` must return
     tensors it does not overwrite later."""
     import torch
@@ -71,6 +72,13 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
     from . import fastpath
 
     device = torch.device(device if device is not None else torch.cuda.current_device())
+    as_u8 = out_h.dtype == torch.uint8
+    if as_u8:
+        from .imageio import quantize_u8
+
+    def result_rows(t):
+        return quantize_u8(t) if as_u8 else t
+
     n = low_h.shape[0]
     compute = torch.cuda.current_stream(device)
     h2d, d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
@@ -111,14 +119,16 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
             for c in copied:
                 if c is not None:
                     compute.wait_event(c[0])               # the static output buffer is free again
-            evs = []
+            evs, keep = [], []
 
-            def on_group(g, glo, ghi, restored, s=s, evs=evs):
+            def on_group(g, glo, ghi, restored, s=s, evs=evs, keep=keep):
+                rows = result_rows(restored[glo:ghi])
+                keep.append(rows)                          # alive until the caller's final synchronisation
                 ready = torch.cuda.Event()
                 ready.record(compute)
                 d2h.wait_event(ready)
                 with torch.cuda.stream(d2h):
-                    out_h[s + glo:s + ghi].copy_(restored[glo:ghi], non_blocking=True)
+                    out_h[s + glo:s + ghi].copy_(rows, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(d2h)
                 evs.append(ev)
@@ -126,7 +136,7 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
             restored, _ = restorer(lo, co, zz, clone=False, before_low=lambda k=k: compute.wait_event(loaded[k]),
                                    on_group=on_group)
             consumed[k].record(compute)
-            copied[k] = (evs[-1], restored)
+            copied[k] = (evs[-1], (restored, keep))        # keep the group tensors alive until their copies are done
             continue
         if split and e - s == micro:
             # the style-decoder half starts as soon as the codes are on the device; the image copy overlaps it
@@ -138,6 +148,7 @@ def restore_from_host(net, decoder, low_h, codes_h, noise_z_h, out_h, micro: int
                 restored, _ = restorer(lo, co, zz)
             else:
                 restored, _ = fastpath.restore_faces(net, decoder, lo, co, [zz])
+        restored = result_rows(restored)
         consumed[k].record(compute)
         if copied[k] is not None:
             copied[k][0].synchronize()                     # long finished; lets the tensor two batches back be freed safely
