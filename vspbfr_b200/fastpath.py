@@ -226,6 +226,7 @@ def _banks_for(owner, build):
     return hit[0]
 
 
+_TAIL_LEVELS = int(os.environ.get("VSP_TAIL_LEVELS", "2"))     # decoder levels of the restorer that run in sample groups (grouped tail)
 _bank_rows = None      # slice of the batch the current calls work on (tail groups of restoration_forward), or None
 
 
@@ -789,14 +790,13 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
     levels = list(zip(net.convs[::2], net.convs[1::2], noise[1::2], noise[2::2], net.to_rgbs))
     for li, (up, smart, n_up, n_smart, rgb) in enumerate(levels):
         level = (i + 1) // 2
-        if li == len(levels) - 1 and tail_groups > 1 and b % tail_groups == 0:
+        if li == len(levels) - min(_TAIL_LEVELS, len(levels)) and tail_groups > 1 and b % tail_groups == 0:
             # Last level in sample groups (images are independent): a caller that streams results to the host copies group g
             # while groups g+1.. still compute (``tail_hook(g, lo, hi, restored)`` runs between groups; under CUDA-graph
             # capture it ends one graph and begins the next).  Same kernels on batch slices: results are bit-identical.
             global _bank_rows
             restored = torch.empty((b, 3) + tuple(images.shape[2:]), dtype=torch.float32, device=images.device)
             gsz = b // tail_groups
-            res1, res2 = features[level], _as_nhwc(de_feats[level])
             if tail_hook is not None:
                 tail_hook(-1, 0, 0, restored)                 # everything before the tail has been enqueued
             try:
@@ -804,9 +804,15 @@ def restoration_forward(net, images, de_feats, pre_styles, noise_styles, inject_
                     lo, hi = g * gsz, (g + 1) * gsz
                     _bank_rows = slice(lo, hi)
                     cut = lambda t: None if t is None else (t if t.shape[0] == 1 else t[lo:hi])
-                    o = styled_conv(up, out[lo:hi], sty(i)[lo:hi], cut(n_up), residual=res1[lo:hi], residual2=res2[lo:hi])
-                    o = smart_layer(smart, o, sty(i + 1)[lo:hi], cut(n_smart))
-                    restored[lo:hi] = to_rgb(rgb, o, sty(i + 2)[lo:hi], skip[lo:hi])
+                    o, sk, j = out[lo:hi], skip[lo:hi], i
+                    for (up_, smart_, nu, ns, rgb_) in levels[li:]:
+                        lv = (j + 1) // 2
+                        o = styled_conv(up_, o, sty(j)[lo:hi], cut(nu), residual=features[lv][lo:hi],
+                                        residual2=_as_nhwc(de_feats[lv])[lo:hi])
+                        o = smart_layer(smart_, o, sty(j + 1)[lo:hi], cut(ns))
+                        sk = to_rgb(rgb_, o, sty(j + 2)[lo:hi], sk)
+                        j += 2
+                    restored[lo:hi] = sk
                     if tail_hook is not None:
                         tail_hook(g, lo, hi, restored)
             finally:
