@@ -581,6 +581,7 @@ def test_encoder_fused_unit_tail_matches_plain_composition(monkeypatch):
             m.bias.data.normal_(0, 0.2)
     front = fe.WPlusFrontEnd(enc, n_latent=18).to(DEV).eval().half_precision_()
     img = torch.rand(2, 3, 128, 128, device=DEV) * 2 - 1
+    monkeypatch.setattr(fe, "_OWN_CONVS", False)                # library convolutions: isolates the fused tail
     n0 = _lib.launch_count()
     got = front(img)
     assert _lib.launch_count() - n0 == 24                       # one fused tail per residual unit
@@ -588,4 +589,12 @@ def test_encoder_fused_unit_tail_matches_plain_composition(monkeypatch):
     want = front(img)
     assert _lib.launch_count() - n0 == 24
     err = float((got - want).abs().max())
+    assert err <= 3e-2 * float(want.abs().max()), (err, float(want.abs().max()))
+    # and with the convolutions on the own tcgen05 kernel (bias / PReLU / LeakyReLU epilogues): same result to bf16 rounding
+    monkeypatch.delenv("VSP_NO_SE_TAIL")
+    monkeypatch.setattr(fe, "_OWN_CONVS", True)
+    n1 = _lib.launch_count()
+    own = front(img)
+    assert _lib.launch_count() - n1 > 24 + 2 * 24               # tails + two convolutions per unit (+ shortcuts, heads)
+    err = float((own - want).abs().max())
     assert err <= 3e-2 * float(want.abs().max()), (err, float(want.abs().max()))

@@ -940,7 +940,9 @@ __device__ __forceinline__ BandUnit band_unit(const BandParams &p, long long uni
     b.oy0 = (int)(unit % p.upp) * p.G * kBandR;
     b.rows = min(p.G * kBandR, u.out_h - b.oy0);
     b.iy_lo = max(0, b.oy0 * p.dn - u.pad_y0);
-    iy_hi = min(u.in_h, (b.oy0 + b.rows - 1) * p.dn - u.pad_y0 + u.kh);
+    // (kK rows per output even when the filter has fewer: the compute loop walks the zero-extended 4-tap window, and a
+    // zero tap times a row that was never loaded — stale shared memory, possibly NaN bits — would not be zero)
+    iy_hi = min(u.in_h, (b.oy0 + b.rows - 1) * p.dn - u.pad_y0 + kK);
     if (iy_hi < b.iy_lo) iy_hi = b.iy_lo;
     b.iy_hi = iy_hi;
   }
@@ -1183,7 +1185,7 @@ int launch_band(const UfdParams &u, int dn, cudaStream_t stream) {
     p.units = (u.major + P - 1) / P;
   } else {
     long long in_rows = budget / row_bytes;                 // input rows a stage holds: dn * (G * R - 1) + kh of them are needed
-    long long G = ((in_rows - u.kh) / dn + 1) / kBandR;
+    long long G = ((in_rows - kK) / dn + 1) / kBandR;
     if (G < 1) return -1;                                   // one row group does not fit: caller falls back
     const long long gmax = (u.out_h + kBandR - 1) / kBandR;
     if (G > gmax) G = gmax;
