@@ -607,8 +607,9 @@ def train_step_numbers(args, dev, world, rank, local, steps, warmup, batch=4):
            "launch": ("one CUDA graph replay per iteration" if world == 1 else
                       "four CUDA graph replays per iteration (D / R1 / G / update phases), gradient all-reduce between them" if graphed
                       else "eager launches under DistributedDataParallel"),
-           "workload": "restoration_train.py:159-256 (D logistic + R1 double backward every iteration + G non-saturating + EMA), "
-                       "LPIPS / ArcFace weights 0 (pretrained nets unavailable), synthetic w+ codes for e4e + diffuser",
+           "workload": "restoration_train.py:159-256 (D logistic + R1 double backward every iteration + G non-saturating + "
+                       "LPIPS-VGG (0.5) + ArcFace-ResNet101 identity (0.1) terms + EMA); loss nets random-init (pretrained "
+                       "checkpoints unavailable offline), synthetic w+ codes for e4e + diffuser",
            "e2e": {"value": world * batch * steps / t_e2e, "unit": "images/s",
                    "h2d_bytes_per_step": world * sum(x.numel() * 4 for x in host), "d2h_bytes_per_step": world * 12},
            "gpu_launches": int(launches) * world,

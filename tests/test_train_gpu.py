@@ -170,3 +170,18 @@ def test_ddp_gradients_equal_single_process_gradients():
         got, want = torch.from_numpy(d_ddp[k]).to(DEV), want / world
         scale = float(want.abs().max()) + 1e-12
         assert float((got - want).abs().max()) <= 1e-2 * scale, (k, float((got - want).abs().max()), scale)
+
+
+def test_generator_step_includes_the_reference_loss_networks():
+    """restoration_train.py:236-245: with the default weights (0.5 / 0.1) the generator loss carries the LPIPS-VGG and the
+    ArcFace-ResNet identity terms (lossnets.py, frozen, eval mode); with both weights 0 the step is the GAN terms alone."""
+    full = TrainStep(SIZE, 2, DEV, seed=3)
+    bare = TrainStep(SIZE, 2, DEV, seed=3, percept_loss_weight=0.0, id_loss_weight=0.0)
+    assert full.percept_loss is not None and full.id_loss is not None and bare.percept_loss is None and bare.id_loss is None
+    assert not full.percept_loss.model.training and not full.id_loss.Z.training
+    assert not any(p.requires_grad for p in list(full.percept_loss.parameters()) + list(full.id_loss.parameters()))
+    torch.manual_seed(0)
+    _, _, g_full = full.step()
+    torch.manual_seed(0)
+    _, _, g_bare = bare.step()
+    assert torch.isfinite(g_full) and torch.isfinite(g_bare) and float((g_full - g_bare).abs()) > 0

@@ -5,8 +5,8 @@ regulariser with its double backward through the Discriminator (:63-73, :200-216
 (:220-250) and the EMA update (:46-51, :255) — with the loss helpers under the reference's own names
 (``d_logistic_loss`` :56-60, ``d_r1_loss`` :63-73, ``g_nonsaturating_loss`` :76-79, ``requires_grad`` :41-43,
 ``accumulate`` :46-51).  The w+ codes stand in for the frozen e4e encoder + code diffuser (:166-167, outside the hot
-path); LPIPS / ArcFace terms need pretrained networks that cannot be downloaded and are off (their weights are 0, the
-``--percept_loss_weight 0 --id_loss_weight 0`` setting).  Data parallelism is the reference's: one process per GPU,
+path); the LPIPS-VGG and ArcFace terms of the generator step (:236-245, default weights 0.5 / 0.1) run on ``lossnets.py`` —
+the reference's network structures, randomly initialised because the pretrained checkpoints cannot be downloaded here.  Data parallelism is the reference's: one process per GPU,
 ``DistributedDataParallel`` around generator and discriminator (:431-445), gradients all-reduced by NCCL during backward.
 
 Every convolution of the step — forward, input gradient, weight gradient and the second-order terms of R1 — runs on the
@@ -67,7 +67,8 @@ class TrainStep:
     ``capturable`` keeps the Adam step counters on the device (needed for capture)."""
 
     def __init__(self, size=512, batch=4, device="cuda", world=1, local_rank=0, rank=0, r1=10.0, d_reg_every=16,
-                 style_dim=512, n_mlp=8, mixing=0.9, capturable=False, seed=0, reduce="ddp"):
+                 style_dim=512, n_mlp=8, mixing=0.9, capturable=False, seed=0, reduce="ddp", percept_loss_weight=0.5,
+                 id_loss_weight=0.1, lpips_weights=None, arcface_path=None):
         if reduce not in ("ddp", "flat"):
             raise ValueError(f"reduce must be 'ddp' or 'flat', got {reduce!r}")
         self.size, self.batch, self.world, self.device = size, batch, world, torch.device(device)
@@ -100,6 +101,19 @@ class TrainStep:
         self.codes = torch.randn(batch, 18, style_dim, generator=g).to(dev)
         self._de_feats = None
         self._losses = [None, None, None]
+        # loss networks of the generator step (restoration_train.py:116,143,236-245; the reference's default weights 0.5 / 0.1):
+        # frozen LPIPS-VGG and ArcFace ResNet-101, randomly initialised unless checkpoints are given (lossnets.py)
+        self.percept_loss_weight, self.id_loss_weight = float(percept_loss_weight), float(id_loss_weight)
+        self.percept_loss = self.id_loss = None
+        if self.percept_loss_weight > 0 or self.id_loss_weight > 0:
+            from . import lossnets
+            torch.manual_seed(seed + 1)
+            cl = torch.channels_last if dev.type == "cuda" else torch.contiguous_format     # NHWC: the library's tensor-core path
+            if self.percept_loss_weight > 0:
+                self.percept_loss = lossnets.PerceptualLoss(lin_weights_path=lpips_weights).to(dev).to(memory_format=cl)
+            if self.id_loss_weight > 0:
+                self.id_loss = lossnets.IDLoss(arcface_path).to(dev).to(memory_format=cl)
+            self._loss_format = cl
 
     def grad_bytes(self):
         """fp32 gradient bytes all-reduced per iteration: D twice (logistic + R1 steps), G once."""
@@ -165,6 +179,13 @@ class TrainStep:
         with self._nosync(self.generator, sync):
             restored = self.generator(self.low_img, self._de_feats, self.codes, noise)
             g_loss = g_nonsaturating_loss(self.discriminator(restored))
+            if self.percept_loss is not None or self.id_loss is not None:
+                pred = restored.contiguous(memory_format=self._loss_format)
+                real = self.real_img.detach().contiguous(memory_format=self._loss_format)
+            if self.percept_loss is not None:          # restoration_train.py:236-239
+                g_loss = g_loss + self.percept_loss(pred, real).sum() * self.percept_loss_weight
+            if self.id_loss is not None:               # :242-245
+                g_loss = g_loss + self.id_loss(pred, real) * self.id_loss_weight
             self._zero(self.generator, self.flat_g)
             g_loss.backward()
         self._losses[2] = g_loss.detach()
