@@ -176,7 +176,7 @@ def test_grouped_linear_matches_equal_linear():
     lins = [m.to(DEV) for m in lins]
     for m in lins:
         m.bias.data.normal_()
-    for batch in (1, 3, 8, 11):
+    for batch in (1, 3, 8, 11, 32, 40):          # <= 8: warp-per-row kernel; > 8: lane-per-sample kernel (40: two passes)
         styles = torch.randn(batch, 6, 512, device=DEV)
         bank = fp.ModulationBank([(m, idx) for m, idx in zip(lins, (0, 5, 2, 2))])
         got, _ = bank(styles)
@@ -189,12 +189,13 @@ def test_grouped_linear_matches_equal_linear():
     owners = [object(), object()]
     bank = fp.ModulationBank([(lins[0], 1, (owners[0], lambda: mc.weight_sumsq(w1), 0.05, 1e-8)), (lins[1], 0),
                               (lins[3], 3, (owners[1], lambda: mc.weight_sumsq(w2), 0.2, 1e-8))])
-    styles = torch.randn(5, 4, 512, device=DEV)
-    s_out, d_out = bank(styles)
-    for lin, w, owner, idx, sc in ((lins[0], w1, owners[0], 1, 0.05), (lins[3], w2, owners[1], 3, 0.2)):
-        sv = lin(styles[:, idx])
-        want = torch.rsqrt(((sc * w[None] * sv[:, None, :, None, None]) ** 2).sum(dim=(2, 3, 4)) + 1e-8)
-        np.testing.assert_allclose(d_out[id(owner)].cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-4)
+    for batch in (5, 19):                        # 130 input channels: rows that are not 16-byte aligned
+        styles = torch.randn(batch, 4, 512, device=DEV)
+        s_out, d_out = bank(styles)
+        for lin, w, owner, idx, sc in ((lins[0], w1, owners[0], 1, 0.05), (lins[3], w2, owners[1], 3, 0.2)):
+            sv = lin(styles[:, idx])
+            want = torch.rsqrt(((sc * w[None] * sv[:, None, :, None, None]) ** 2).sum(dim=(2, 3, 4)) + 1e-8)
+            np.testing.assert_allclose(d_out[id(owner)].cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-4)
 
 
 @pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130), (256, 18), (512, 66), (1024, 6),

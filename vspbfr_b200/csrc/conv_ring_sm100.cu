@@ -281,7 +281,8 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
           const int rr = 2 * q + wg;
           nz[q] = 0.f;
           if (rr < reff && p.noise != nullptr && pix_ok)
-            nz[q] = nw * __ldg(p.noise + un.b * p.noise_bstride + (long long)(oh0 + rr * d) * p.full_w + ow);
+            nz[q] = (STAGED ? 1.f : nw) *       // staged form: raw value, scaled at its first use after the accumulator wait
+                    __ldg(p.noise + un.b * p.noise_bstride + (long long)(oh0 + rr * d) * p.full_w + ow);
         }
         // output rows alternate between the two epilogue warps of this lane quadrant: rows wg, wg + 2
         const int n_items = ((reff - wg + 1) >> 1) * NCH;
@@ -319,7 +320,7 @@ conv_ring_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a,
             for (int i = 0; i < CHUNK / 8; ++i)
               *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) =
                   epi_lean8(&r[8 * i], vec_rs + ch * CHUNK + 8 * i, vec_b1 + ch * CHUNK + 8 * i,
-                            vec_b2 + ch * CHUNK + 8 * i, nzv * lk.m2, lk);
+                            vec_b2 + ch * CHUNK + 8 * i, nw * nzv * lk.m2, lk);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {

@@ -86,7 +86,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
     }
     float nz0 = 0.f;
     if (p.noise != nullptr && pix_ok && !p.shuffle_cout)
-      nz0 = nw * __ldg(p.noise + b * p.noise_bstride + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);
+      nz0 = __ldg(p.noise + b * p.noise_bstride + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);   // raw: first use after the wait
     asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
 
     mbar_wait(&tmem_full[acc], acc_phase);
@@ -99,7 +99,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
       const int c0 = p.shuffle_cout ? n0 % p.shuffle_cout : n0;
       const int ctot = n0 < p.cout ? creal : 0;                   // padded tail of the channel tile: nothing to write
       const long long pix = (long long)(oh * p.os + p.oo_h + (cls >> 1)) * p.full_w + ow * p.os + p.oo_w + (cls & 1);
-      float nz = nz0;
+      float nz = nw * nz0;
       if (p.shuffle_cout && p.noise != nullptr && pix_ok) nz = nw * __ldg(p.noise + b * p.noise_bstride + pix);
       const float *rs_row = (p.tb > 1 && p.row_scale && pix_ok) ? p.row_scale + (long long)b * creal + c0 : nullptr;
       epi_chunk<C::CHUNK>(p, taddr + ch * C::CHUNK, c0, ctot, b, pix, plane, pix_ok, nz,
@@ -183,9 +183,9 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
 #pragma unroll
         for (int cls = 0; cls < 4; ++cls)
           if (cls >= c_lo && cls <= c_hi)
-            nzc[cls] = nw * __ldg(nb + (long long)(oh * 2 + (cls >> 1)) * p.full_w + ow * 2 + (cls & 1));
+            nzc[cls] = __ldg(nb + (long long)(oh * 2 + (cls >> 1)) * p.full_w + ow * 2 + (cls & 1));   // raw, scaled at first use
       } else {
-        nzc[0] = nw * __ldg(nb + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);
+        nzc[0] = __ldg(nb + (long long)(oh * p.os + p.oo_h) * p.full_w + ow * p.os + p.oo_w);
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // epilogue warps only
@@ -282,8 +282,8 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
 #pragma unroll
       for (int i = 0; i < PIECES; ++i) {
         float v[8];
-        if (prelu) epi_lean8f_prelu(&r[8 * i], vrs + 8 * i, vb2 + 8 * i, vec_a + acc * BLOCK_N + ch * CHUNK + 8 * i, nz * lk.m2, v);
-        else epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nz * lk.m2, lk, v);
+        if (prelu) epi_lean8f_prelu(&r[8 * i], vrs + 8 * i, vb2 + 8 * i, vec_a + acc * BLOCK_N + ch * CHUNK + 8 * i, nw * nz * lk.m2, v);
+        else epi_lean8f(&r[8 * i], vrs + 8 * i, vb1 + 8 * i, vb2 + 8 * i, nw * nz * lk.m2, lk, v);
         if (has_res) add2_bf16x8(v, own1[i], own2[i]);
         *reinterpret_cast<uint4 *>(buf + lane * ROW_BYTES + ((i ^ sw) << 4)) = pack8_bf16(v);
       }

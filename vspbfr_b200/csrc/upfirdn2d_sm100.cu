@@ -624,8 +624,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-template <bool EPI>
-__global__ void __launch_bounds__(kStripThreads, 3)
+// kEpiAhead: rows of look-ahead of the epilogue operand loads (< kStageRows)
+template <bool EPI, int kEpiAhead, int kMinBlocks>
+__global__ void __launch_bounds__(kStripThreads, kMinBlocks)
 blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y, const StripParams p, const NhwcEpi e,
                   const SepTaps t) {
   extern __shared__ __align__(128) unsigned char strip_smem[];
@@ -682,6 +683,25 @@ blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y
   const uint32_t tbase = smem_u32(strip_smem) + (uint32_t)(2 * cp) * 128u + (uint32_t)cg8 * 16u;
   const long long ybase = (long long)b * p.out_h * p.out_w * p.cg + cz * 8 + cg8;
 
+  // ring of epilogue operands, slot = input row % kStageRows (compile-time inside the unrolled stage)
+  uint4 r1[kStageRows][2], r2[kStageRows][2];
+  float nz[kStageRows][2];
+  auto epi_issue = [&](int i, int slot) {
+    if (!(i >= kK - 1 && i - (kK - 1) < rows_out)) return;
+    const long long pix = (long long)(q_lo + i - (kK - 1)) * p.out_w + ox;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const bool ok = c ? ok1 : ok0;
+      r1[slot][c] = (e.residual && ok) ? __ldg(e.residual + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
+      r2[slot][c] = (e.residual2 && ok) ? __ldg(e.residual2 + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
+      nz[slot][c] = (e.noise && ok) ? __ldg(e.noise + b * e.noise_bstride + pix + c) : 0.f;   // raw: no use at issue time
+    }
+  };
+  if (EPI) {
+#pragma unroll
+    for (int i = 0; i < kEpiAhead; ++i) epi_issue(i, i);
+  }
+
   for (int k = 0; k < n_stage; ++k) {
     const int s = k % kStripStages;
     const uint32_t phase = (uint32_t)(k / kStripStages) & 1u;
@@ -692,19 +712,9 @@ blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y
       const int i = k * kStageRows + rr;              // input row of this segment
       const int oy = q_lo + i - (kK - 1);             // the output row this input row completes
       const bool emit = i >= kK - 1 && i - (kK - 1) < rows_out;
-      // epilogue operands of the row to be emitted: issued before the arithmetic so their latency is covered
-      uint4 r1[2], r2[2];
-      float nz[2] = {0.f, 0.f};
-      if (EPI && emit) {
-        const long long pix = (long long)oy * p.out_w + ox;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const bool ok = c ? ok1 : ok0;
-          r1[c] = (e.residual && ok) ? __ldg(e.residual + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
-          r2[c] = (e.residual2 && ok) ? __ldg(e.residual2 + ybase + (pix + c) * p.cg) : make_uint4(0u, 0u, 0u, 0u);
-          nz[c] = (e.noise && ok) ? nw * __ldg(e.noise + b * e.noise_bstride + pix + c) : 0.f;
-        }
-      }
+      // epilogue operands: row i + kEpiAhead's residual / noise loads are issued here, kEpiAhead rows of arithmetic before
+      // their use (issued only one row ahead the kernel sat on these loads: 3.2 TB/s vs 5.5 TB/s without an epilogue)
+      if (EPI) epi_issue(i + kEpiAhead, (rr + kEpiAhead) % kStageRows);
       unsigned long long h0[4], h1[4];
 #pragma unroll
       for (int j = 0; j < kK + 1; ++j) {
@@ -743,15 +753,16 @@ blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y
           for (int q = 0; q < 4; ++q) unpk2(acc[slot][c][q], v[2 * q], v[2 * q + 1]);
           if (EPI) {
             if (e.noise != nullptr || e.bias != nullptr || e.act != 0) {
+              const float nzw = nw * nz[rr][c];
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                float u = v[q] + nz[c] + bias[q];
+                float u = v[q] + nzw + bias[q];
                 if (e.act == 3) u = (u > 0.f ? u : u * e.alpha) * e.scale;
                 v[q] = u;
               }
             }
-            if (e.residual) add_bf16x8(v, r1[c]);
-            if (e.residual2) add_bf16x8(v, r2[c]);
+            if (e.residual) add_bf16x8(v, r1[rr][c]);
+            if (e.residual2) add_bf16x8(v, r2[rr][c]);
           }
           uint4 o;
           __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
@@ -771,10 +782,10 @@ blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y
   }
 }
 
-template <bool EPI>
+template <bool EPI, int AHEAD = 0, int MINB = 3>
 int launch_blur_strip(const void *x, void *y, StripParams p, const NhwcEpi &e, const SepTaps &t, int64_t n, int64_t c,
                       cudaStream_t stream) {
-  auto kern = blur_strip_kernel<EPI>;
+  auto kern = blur_strip_kernel<EPI, AHEAD, MINB>;
   constexpr int smem = kStripStages * kStageBytes;
   static bool attr_done[64] = {false};
   int dev = 0;
@@ -1394,8 +1405,22 @@ extern "C" int vsp_blur_sep_nhwc_bf16(const void *x, const float *fy_host, const
     sp.in_h = (int)in_h; sp.in_w = (int)in_w; sp.out_h = (int)out_h; sp.out_w = (int)out_w;
     sp.pad_x0 = pad_x0; sp.pad_y0 = pad_y0;
     const bool has_epi = e.noise || e.bias || e.act != 0 || e.residual || e.residual2;
-    return has_epi ? launch_blur_strip<true>(x, y, sp, e, t, n, c, stream)
-                   : launch_blur_strip<false>(x, y, sp, e, t, n, c, stream);
+    if (!has_epi) return launch_blur_strip<false>(x, y, sp, e, t, n, c, stream);
+    // Epilogue form: at 3 CTAs/SM (168 registers) ptxas spills 124 B per thread INSIDE the row loop — ncu showed more local-
+    // memory requests (2.1 M loads + 2.2 M stores, 16 % L1 hits) than global loads (1.6 M) and the kernel at 2.9 TB/s.  With 2
+    // CTAs/SM (204 registers, no spills) and the operand loads three rows ahead: [32,129,129,256] 365 -> 312 us (3.5 TB/s).
+    // VSP_BLUR_EPI_BLOCKS=3 / VSP_BLUR_EPI_AHEAD=0..3 select the other forms (tools/bench_blur_epi.py).
+    static const int ahead = getenv("VSP_BLUR_EPI_AHEAD") ? atoi(getenv("VSP_BLUR_EPI_AHEAD")) : 3;
+    static const int minb = getenv("VSP_BLUR_EPI_BLOCKS") ? atoi(getenv("VSP_BLUR_EPI_BLOCKS")) : 2;
+    if (minb == 3)
+      return ahead == 0 ? launch_blur_strip<true, 0, 3>(x, y, sp, e, t, n, c, stream)
+                        : launch_blur_strip<true, 2, 3>(x, y, sp, e, t, n, c, stream);
+    switch (ahead) {
+      case 0: return launch_blur_strip<true, 0, 2>(x, y, sp, e, t, n, c, stream);
+      case 1: return launch_blur_strip<true, 1, 2>(x, y, sp, e, t, n, c, stream);
+      case 2: return launch_blur_strip<true, 2, 2>(x, y, sp, e, t, n, c, stream);
+      default: return launch_blur_strip<true, 3, 2>(x, y, sp, e, t, n, c, stream);
+    }
   }
   constexpr int R = 4;
   const int cg = (int)(c / 8);
