@@ -240,6 +240,10 @@ typedef struct vsp_linear_desc {
   int32_t in_dim, out_dim;
   float wscale, bscale;
   int64_t x_bstride;  /* elements between samples of this problem's input rows; 0 = the call's x_bstride */
+  int32_t act;        /* 0 = none; 3 = leaky relu: y = lrelu(w.x * wscale + bias * bscale, alpha) * gain
+                         (EqualLinear(activation="fused_lrelu"), models/RestoreNet.py:167-170: the style MLP) */
+  float alpha, gain;
+  int32_t pad_;
 } vsp_linear_desc;
 int vsp_grouped_linear_f32(const vsp_linear_desc *descs_dev, const int *row_start_dev, int n_problems,
                            int total_rows, const float *x, int64_t x_bstride, float *y, int batch, void *stream);

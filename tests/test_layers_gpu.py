@@ -183,6 +183,16 @@ def test_grouped_linear_matches_equal_linear():
         for m, idx in zip(lins, (0, 5, 2, 2)):
             want = m(styles[:, idx])
             np.testing.assert_allclose(got[id(m)].cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-5)
+    # enough rows for the four-groups-per-block form (>= 4 blocks per SM), with ragged problems between the wide ones so
+    # that a block's groups straddle problem boundaries
+    big = [L.EqualLinear(512, o, bias_init=1).to(DEV) for o in (512, 130, 512, 512, 24, 512, 512, 3, 512, 512, 512, 512, 512)]
+    for batch in (9, 32):
+        styles = torch.randn(batch, 3, 512, device=DEV)
+        bank = fp.ModulationBank([(m, i % 3) for i, m in enumerate(big)])
+        got, _ = bank(styles)
+        for i, m in enumerate(big):
+            want = m(styles[:, i % 3])
+            np.testing.assert_allclose(got[id(m)].cpu().numpy(), want.detach().cpu().numpy(), rtol=2e-5, atol=2e-5)
     # with demodulation problems attached: d[b,o] = rsqrt(scale^2 * sum_i s^2 * sum_t W^2 + eps) (models/RestoreNet.py:513-516)
     w1 = torch.randn(48, 64, 3, 3, device=DEV)
     w2 = torch.randn(20, 130, 3, 3, device=DEV)
@@ -196,6 +206,25 @@ def test_grouped_linear_matches_equal_linear():
             sv = lin(styles[:, idx])
             want = torch.rsqrt(((sc * w[None] * sv[:, None, :, None, None]) ** 2).sum(dim=(2, 3, 4)) + 1e-8)
             np.testing.assert_allclose(d_out[id(owner)].cpu().numpy(), want.detach().cpu().numpy(), rtol=1e-4)
+
+
+def test_style_mlp_on_grouped_linear_matches_module():
+    """Style MLP (PixelNorm + 8 x EqualLinear(fused_lrelu), lr_mul 0.01: models/RestoreNet.py:845-856) with each layer as one
+    grouped-linear launch (bias + leaky relu in its epilogue) == the module's own forward; other structures fall back."""
+    torch.manual_seed(9)
+    mods = [L.PixelNorm()] + [L.EqualLinear(512, 512, lr_mul=0.01, activation="fused_lrelu") for _ in range(8)]
+    mlp = torch.nn.Sequential(*mods).to(DEV)
+    for m in mods[1:]:
+        m.bias.data.normal_()
+    for batch in (1, 4, 32):
+        z = torch.randn(batch, 512, device=DEV)
+        with torch.no_grad():
+            want = mlp(z)
+            got = fp._style_mlp(mlp, z)
+        np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    plain = torch.nn.Sequential(L.PixelNorm(), L.EqualLinear(512, 64)).to(DEV)      # no activation: module path
+    z = torch.randn(3, 512, device=DEV)
+    assert torch.equal(fp._style_mlp(plain, z), plain(z))
 
 
 @pytest.mark.parametrize("c,h", [(512, 8), (64, 32), (128, 64), (32, 96), (64, 130), (256, 18), (512, 66), (1024, 6),

@@ -140,6 +140,10 @@ class LinearDesc(Structure):
         ("wscale", c_float),
         ("bscale", c_float),
         ("x_bstride", c_int64),
+        ("act", ctypes.c_int32),
+        ("alpha", c_float),
+        ("gain", c_float),
+        ("pad_", ctypes.c_int32),
     ]
 
 
