@@ -225,8 +225,9 @@ def main():
     # a shard that is ONE micro-batch (one rank of an 8-GPU job) has nothing to overlap its result copy with: for the
     # host-buffer path the restorer's last level runs in 4 sample groups whose rows leave while the next groups compute
     graphed_e2e = graphed
-    if graphed is not None and n_micro == 1 and micro % 4 == 0 and os.environ.get("VSP_NO_TAIL_GROUPS") is None:
-        graphed_e2e = fastpath.GraphedRestorer(net, dec, micro, device=dev, tail_groups=4)
+    tail_groups = int(os.environ.get("VSP_TAIL_GROUPS", "4"))
+    if graphed is not None and n_micro == 1 and micro % tail_groups == 0 and os.environ.get("VSP_NO_TAIL_GROUPS") is None:
+        graphed_e2e = fastpath.GraphedRestorer(net, dec, micro, device=dev, tail_groups=tail_groups)
 
     def step_resident():
         for m in range(n_micro):
