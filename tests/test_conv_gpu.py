@@ -201,6 +201,33 @@ def test_transposed_stride2(b, cin, cout, h, w_):
     assert_close_tight(out, want)
 
 
+@pytest.mark.parametrize("b,cin,cout,h,w_,shared", [(2, 64, 128, 32, 32, True), (2, 128, 256, 33, 40, False),
+                                                     (1, 64, 512, 32, 64, True), (2, 192, 128, 130, 129, False),
+                                                     (3, 64, 256, 64, 32, True)])
+def test_transposed_stride2_one_launch_class_mode(b, cin, cout, h, w_, shared):
+    """Stride-2 transposed conv with an NHWC bf16 output and Cout % 128 == 0: the four output parity classes as ONE
+    pixel-shuffle launch (each channel tile runs only its class's 4 / 2 / 2 / 1 taps) plus thin launches for the last row
+    and column, shared and per-sample weights, demodulation row scale in the epilogue; against conv_transpose2d
+    (models/RestoreNet.py:522-529) on the same bf16-rounded operands.  Every output element is checked, so a class
+    written to the wrong parity, a missing border row / column or a tile that ran another class's taps fails."""
+    torch.manual_seed(h * 11 + cout)
+    x = torch.randn(b, cin, h, w_, device=DEV)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / math.sqrt(cin * 9)
+    s = None if shared else torch.randn(b, cin, device=DEV) * 0.3 + 1
+    rs = torch.rand(b, cout, device=DEV) + 0.5
+    xq = mc.nchw_to_nhwc_bf16(x)
+    wq, _ = mc.pack_weights(w, s)
+    out = mc.conv_transpose_s2(xq, wq, cout, 3, 3, epi=mc.make_epilogue(row_scale=rs), out_nhwc=True)
+    assert out.shape == (b, 2 * h + 1, 2 * w_ + 1, cout)
+    if shared:
+        want = F.conv_transpose2d(bf16r(x), wr(w).transpose(0, 1), None, stride=2, padding=0)
+    else:
+        want = torch.cat([F.conv_transpose2d(bf16r(x[i:i + 1]), wr(w * s[i][None, :, None, None]).transpose(0, 1), None,
+                                             stride=2, padding=0) for i in range(b)])
+    want = want * rs[:, :, None, None]
+    assert_close_tight(out.permute(0, 3, 1, 2).float(), want, tol=1e-2)
+
+
 def test_dgrad_via_gather_matches_autograd():
     torch.manual_seed(21)
     b, cin, cout, h, k, dil = 2, 64, 96, 16, 3, 2

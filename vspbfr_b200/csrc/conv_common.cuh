@@ -38,6 +38,13 @@ struct ConvParams {
   // pixel-shuffle epilogue (fused up-conv): GEMM column n = class * shuffle_cout + channel, class = (pa, pb) in
   // row-major order, written to (2*oh + pa, 2*ow + pb); 0 = off
   int shuffle_cout;
+  // class mode (stride-2 transposed convolution as ONE launch): channel tile n_i belongs to output parity class
+  // n_i / cls_tpc and runs only that class's taps — tap j of class c reads the activation at shift
+  // (tap_dy, tap_dx)[cls_shift[c][j]] and weight tap cls_w[c][j], rows (n_i % cls_tpc) * BLOCK_N of the layer's OWN packed
+  // weights (no composite tensor, no structural zeros: 1x the layer's FLOPs).  Tiles are dealt so that a CTA's successive
+  // tiles cycle through the classes (their work is 4 : 2 : 2 : 1 taps).
+  int cls_mode, cls_tpc;
+  int cls_ntaps[4], cls_shift[4][4], cls_w[4][4];
   int staged;              // conv_fprop_kernel: epilogue through swizzled shared memory + TMA stores
   // epilogue
   const float *row_scale;
@@ -54,6 +61,12 @@ struct ConvParams {
   const void *residual2;
   const float *alpha_vec;  // per-channel negative slope (PReLU) replacing `alpha` in the second stage
 };
+
+// channel-tile index of a persistent-loop tile (rotated in class mode so that one CTA sees every class in turn)
+__device__ __forceinline__ int tile_n_index(const ConvParams &p, long long tile) {
+  const int n_i = (int)(tile % p.tiles_n);
+  return p.cls_mode ? (int)((n_i + tile / p.tiles_n) % p.tiles_n) : n_i;
+}
 
 __device__ __forceinline__ uint4 pack8_bf16(const float *v) {
   __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]);

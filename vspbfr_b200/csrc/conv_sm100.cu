@@ -64,7 +64,7 @@ __device__ __forceinline__ void epilogue_role(const ConvParams &p, float *epi_ve
   const long long plane = (long long)p.full_h * p.full_w;
   for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     long long t = tile;
-    const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+    const int n_i = tile_n_index(p, tile); t /= p.tiles_n;
     const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
     const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
     const int sp = p.th * p.tw;                                    // pixels of one sample inside the tile
@@ -150,7 +150,7 @@ __device__ __forceinline__ void epilogue_role_staged(const ConvParams &p, const 
   const long long t_end = PAIR ? p.total_pairs : p.total_tiles;
   for (long long tile = t_begin; tile < t_end; tile += t_step) {
     long long t = tile;
-    const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+    const int n_i = tile_n_index(p, tile); t /= p.tiles_n;
     int w_i, h_i;
     if (PAIR) {
       const int m = 2 * (int)(t % p.mpairs) + rank; t /= p.mpairs;
@@ -341,7 +341,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = p.ntaps * p.kc;
+  const int num_kb = p.ntaps * p.kc, num_kb_all = num_kb;
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
@@ -349,23 +349,28 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
     uint32_t phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long t = tile;
-      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int n_i = tile_n_index(p, tile); t /= p.tiles_n;
       const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
       const int h_i = (int)(t % p.tiles_h); t /= p.tiles_h;
       const int b = (int)t * p.tb;                       // first sample of the (possibly stacked) tile
       const int g = p.groups == 1 ? 0 : b;
       const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
       const int dmul = p.branch_mode ? p.n_dil[n_i] : 1;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int cls = p.cls_mode ? n_i / p.cls_tpc : 0;
+      const int tile_kb = p.cls_mode ? p.cls_ntaps[cls] * p.kc : num_kb;
+      const int brow = (p.cls_mode ? n_i % p.cls_tpc : n_i) * BLOCK_N;
+      for (int kb = 0; kb < tile_kb; ++kb) {
         const int tap = kb / p.kc;
         const int c0 = (kb - tap * p.kc) * kBlockK;
+        const int ts = p.cls_mode ? p.cls_shift[cls][tap] : tap;      // activation shift of this tap
+        const int tw = p.cls_mode ? p.cls_w[cls][tap] : p.tap_w[tap];  // weight tap
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           unsigned char *sa = smem + stage * C::STAGE_BYTES;
           unsigned char *sb = sa + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, iw0 + p.tap_dx[tap] * dmul, ih0 + p.tap_dy[tap] * dmul, b);
-          tma_load_4d(sb, &tmap_b, &full_bar[stage], c0, n_i * BLOCK_N, p.tap_w[tap], g);
+          tma_load_4d(sa, &tmap_a, &full_bar[stage], c0, iw0 + p.tap_dx[ts] * dmul, ih0 + p.tap_dy[ts] * dmul, b);
+          tma_load_4d(sb, &tmap_b, &full_bar[stage], c0, brow, tw, g);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -379,6 +384,7 @@ conv_fprop_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap_a
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int num_kb = p.cls_mode ? p.cls_ntaps[tile_n_index(p, tile) / p.cls_tpc] * p.kc : num_kb_all;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -483,7 +489,7 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_kb = p.ntaps * p.kc;
+  const int num_kb = p.ntaps * p.kc, num_kb_all = num_kb;
   const long long t_begin = blockIdx.x >> 1, t_step = gridDim.x >> 1;
 
   if (warp == 0) {
@@ -492,24 +498,29 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
     uint32_t phase = 0;
     for (long long tile = t_begin; tile < p.total_pairs; tile += t_step) {
       long long t = tile;
-      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int n_i = tile_n_index(p, tile); t /= p.tiles_n;
       const int m = 2 * (int)(t % p.mpairs) + rank; t /= p.mpairs;
       const int w_i = m % p.tiles_w, h_i = m / p.tiles_w;
       const int b = (int)t;
       const int g = p.groups == 1 ? 0 : b;
       const int iw0 = w_i * p.tw * p.stride, ih0 = h_i * p.th * p.stride;
       const int dmul = p.branch_mode ? p.n_dil[n_i] : 1;     // channel tile = SMART branch: its own dilation
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int cls = p.cls_mode ? n_i / p.cls_tpc : 0;
+      const int tile_kb = p.cls_mode ? p.cls_ntaps[cls] * p.kc : num_kb;
+      const int brow = (p.cls_mode ? n_i % p.cls_tpc : n_i) * BLOCK_N + rank * (BLOCK_N / 2);
+      for (int kb = 0; kb < tile_kb; ++kb) {
         const int tap = kb / p.kc;
         const int c0 = (kb - tap * p.kc) * kBlockK;
+        const int ts = p.cls_mode ? p.cls_shift[cls][tap] : tap;      // activation shift of this tap
+        const int tw = p.cls_mode ? p.cls_w[cls][tap] : p.tap_w[tap];  // weight tap
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           unsigned char *sa = smem + stage * P::STAGE_BYTES;
           unsigned char *sb = sa + kABytes;
           const uint32_t lead_full = mapa_shared(smem_u32(&full_bar[stage]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * P::STAGE_BYTES);
-          tma_load_4d_2cta(sa, &tmap_a, lead_full, c0, iw0 + p.tap_dx[tap] * dmul, ih0 + p.tap_dy[tap] * dmul, b);
-          tma_load_4d_2cta(sb, &tmap_b, lead_full, c0, n_i * BLOCK_N + rank * (BLOCK_N / 2), p.tap_w[tap], g);
+          tma_load_4d_2cta(sa, &tmap_a, lead_full, c0, iw0 + p.tap_dx[ts] * dmul, ih0 + p.tap_dy[ts] * dmul, b);
+          tma_load_4d_2cta(sb, &tmap_b, lead_full, c0, brow, tw, g);
         }
         __syncwarp();
         if (++stage == P::STAGES) { stage = 0; phase ^= 1; }
@@ -524,6 +535,7 @@ conv_fprop_pair_kernel(const ConvParams p, const __grid_constant__ CUtensorMap t
       int acc = 0;
       uint32_t acc_phase = 0;
       for (long long tile = t_begin; tile < p.total_pairs; tile += t_step) {
+        const int num_kb = p.cls_mode ? p.cls_ntaps[tile_n_index(p, tile) / p.cls_tpc] * p.kc : num_kb_all;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -636,7 +648,7 @@ conv_rowhalo_kernel(const ConvParams p, const __grid_constant__ CUtensorMap tmap
     long long cur_key = -1;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       long long t = tile;
-      const int n_i = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int n_i = tile_n_index(p, tile); t /= p.tiles_n;
       const int w_i = (int)(t % p.tiles_w); t /= p.tiles_w;
       const int oh = (int)(t % p.tiles_h); t /= p.tiles_h;
       const int b = (int)t;
@@ -822,7 +834,7 @@ int launch_conv_impl(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
   CUtensorMap tb;
   {
     // visible rows = cout (a channel slice of a wider packed tensor is legal); strides use cout_pad
-    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)(p.cls_mode ? p.shuffle_cout : p.cout), (uint64_t)taps_total, (uint64_t)p.groups};
     uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
                            (uint64_t)p.cin * cout_pad * taps_total * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)BLOCK_N, 1, 1};
@@ -883,7 +895,7 @@ int launch_conv_pair(ConvParams &p, const CUtensorMap &ta, const void *wq, int64
   if (state[dev] < 1) return -1;
   CUtensorMap tb;
   {
-    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)p.cout, (uint64_t)taps_total, (uint64_t)p.groups};
+    uint64_t dims[4] = {(uint64_t)p.cin, (uint64_t)(p.cls_mode ? p.shuffle_cout : p.cout), (uint64_t)taps_total, (uint64_t)p.groups};
     uint64_t strides[4] = {0, (uint64_t)p.cin * 2, (uint64_t)p.cin * cout_pad * 2,
                            (uint64_t)p.cin * cout_pad * taps_total * 2};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(BLOCK_N / 2), 1, 1};
@@ -933,6 +945,11 @@ inline int next_pow2(int v) {
 
 }  // namespace
 
+// class-mode tap table (ConvParams::cls_*): per output parity class, its taps as (shift index, weight tap)
+struct ClassTaps {
+  int ntaps[4], shift[4][4], w[4][4];
+};
+
 // Shared by the public entry points below and by the transposed-conv helper.
 int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t groups, int64_t in_h,
                        int64_t in_w, int64_t cin, int64_t cout, int64_t cout_pad, int taps_total,
@@ -940,10 +957,10 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
                        int64_t out_h, int64_t out_w, void *out, int out_nhwc, int64_t full_h,
                        int64_t full_w, int os, int oo_h, int oo_w, int64_t ldo, int64_t co_off,
                        const vsp_conv_epilogue *epi, cudaStream_t stream, int shuffle_cout = 0, int n_branches = 0,
-                       const int *branch_dils = nullptr) {
+                       const int *branch_dils = nullptr, const ClassTaps *cls = nullptr) {
   VSP_REQUIRE(batch >= 1 && (groups == 1 || groups == batch), "conv: groups must be 1 or batch");
   VSP_REQUIRE(cin >= 8 && cin % 8 == 0, "conv: cin must be a multiple of 8 (pad NHWC channels), got %lld", (long long)cin);
-  VSP_REQUIRE(cout >= 1 && cout_pad >= cout, "conv: bad cout");
+  VSP_REQUIRE(cout >= 1 && cout_pad >= (cls != nullptr ? shuffle_cout : cout), "conv: bad cout");
   VSP_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "conv: 1..16 taps supported");
   VSP_REQUIRE(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
   VSP_REQUIRE(x && wq && out, "conv: null pointer");
@@ -981,6 +998,15 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   p.kc = ((int)cin + kBlockK - 1) / kBlockK;
   p.out = out; p.out_nhwc = out_nhwc;
   p.shuffle_cout = shuffle_cout;
+  if (cls != nullptr) {
+    VSP_REQUIRE(shuffle_cout > 0 && cout == 4 * shuffle_cout && shuffle_cout % 128 == 0 && n_branches == 0,
+                "conv: class mode needs the pixel-shuffle mapping with Cout %% 128 == 0");
+    p.cls_mode = 1;
+    for (int c = 0; c < 4; ++c) {
+      p.cls_ntaps[c] = cls->ntaps[c];
+      for (int j = 0; j < 4; ++j) { p.cls_shift[c][j] = cls->shift[c][j]; p.cls_w[c][j] = cls->w[c][j]; }
+    }
+  }
   p.full_h = (int)full_h; p.full_w = (int)full_w; p.os = os; p.oo_h = oo_h; p.oo_w = oo_w;
   p.ldo = ldo; p.co_off = co_off;
   if (epi) {
@@ -1008,7 +1034,8 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
   }
 
   // Row-ring path (conv_ring_sm100.cu): wide, shallow stride-1 3x3 (dilated) / 1x1 layers (scalar slopes only)
-  if (p.alpha_vec == nullptr) {
+  if (p.cls_mode) VSP_REQUIRE(p.staged, "conv: class mode needs the staged (NHWC bf16, TMA store) epilogue");
+  if (p.alpha_vec == nullptr && !p.cls_mode) {
     const int rc = conv_ring_try_launch(p, x, wq, in_h, in_w, cout_pad, taps_total, ntaps == 9 ? tap_dx[8] : 1, stream);
     if (rc >= 0) return rc;
   }
@@ -1063,6 +1090,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
     const long long m_tiles = (long long)p.tiles_b * p.tiles_h * p.tiles_w;
     for (int bn = 256; bn >= 16; bn >>= 1) {
       if (p.branch_mode && bn != (int)cout / n_branches) continue;   // one channel tile per branch
+      if (p.cls_mode && bn != (shuffle_cout % 256 == 0 ? 256 : 128)) continue;   // whole channel tiles per parity class
       if (bn > 16 && bn >= 2 * cout) continue;               // more than half of the tile would be padding
       const long long tiles = m_tiles * ((cout + bn - 1) / bn);
       const long long waves = (tiles + num_sms() - 1) / num_sms();
@@ -1070,6 +1098,7 @@ int conv_gather_launch(const void *x, const void *wq, int64_t batch, int64_t gro
       if (cost < best) { best = cost; best_bn = bn; }
     }
   }
+  if (p.cls_mode) p.cls_tpc = shuffle_cout / best_bn;
   if ((best_bn == 256 || best_bn == 128) && p.staged && p.tb == 1) {
     // CTA pairs (tcgen05 cta_group::2) for the N = 256 / 128 layers; VSP_CONV_PAIR=0 keeps the single-CTA kernel
     static const int pair_on = getenv("VSP_CONV_PAIR") == nullptr ? 3 : atoi(getenv("VSP_CONV_PAIR"));   // bit 0: N = 256, bit 1: N = 128
@@ -1145,6 +1174,58 @@ extern "C" int vsp_conv_transpose2d_s2_bf16(const void *x, const void *wq, void 
   const int64_t full_h = (in_h - 1) * 2 + kh, full_w = (in_w - 1) * 2 + kw;
   if (!out_nhwc_bf16) { ldo = cout; co_off = 0; }
   // out[2a+pa, 2b+pb] = sum_{kh_i = pa (mod 2), kw_i = pb (mod 2)} x[a - (kh_i-pa)/2, b - (kw_i-pb)/2] * w[kh_i, kw_i]
+  //
+  // 3x3, NHWC bf16 output, Cout % 128 == 0: the 2H x 2W block of the output as ONE launch in class mode.  The four parity
+  // classes are the four column groups of a pixel-shuffle GEMM over the H x W low-resolution grid; each channel tile runs
+  // only its class's 4 / 2 / 2 / 1 taps straight from the layer's packed weights.  As four launches every class re-read x
+  // and was bound by its own ramp, tail and epilogue (256->128 @128^2 x 32: 670 us = 461 TFLOP/s).  The last output row and
+  // column (index 2H, 2W: the even classes have one more row / column than the grid) are four thin gather launches.
+  // VSP_TCONV_CLASSES=0 keeps the four-launch form.
+  {
+    static const bool one_launch = getenv("VSP_TCONV_CLASSES") == nullptr || atoi(getenv("VSP_TCONV_CLASSES")) != 0;
+    const bool epi_ok = epi == nullptr || (epi->noise == nullptr && epi->residual == nullptr && epi->residual2 == nullptr &&
+                                           epi->alpha_vec == nullptr && epi->alpha >= 0.f && epi->alpha <= 1.f &&
+                                           (epi->scale > 0.f || (epi->act == 0 && epi->pre_act == 0)));
+    const int tw = next_pow2((int)in_w) < kBlockM ? next_pow2((int)in_w) : kBlockM;
+    const bool stacked = groups == 1 && next_pow2((int)in_h) < kBlockM / tw;
+    if (one_launch && kh == 3 && kw == 3 && out_nhwc_bf16 && cout % 128 == 0 && epi_ok && tw >= 32 && !stacked &&
+        (ldo % 8) == 0 && (co_off % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && getenv("VSP_NO_STAGED") == nullptr) {
+      cudaStream_t st = static_cast<cudaStream_t>(stream_);
+      ClassTaps ct;
+      memset(&ct, 0, sizeof(ct));
+      for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb) {
+          const int c = pa * 2 + pb;
+          for (int i = pa; i < 3; i += 2)
+            for (int j = pb; j < 3; j += 2) {
+              const int n = ct.ntaps[c]++;
+              ct.shift[c][n] = ((i - pa) / 2) * 2 + (j - pb) / 2;     // shift index: bit 1 = row shift -1, bit 0 = column shift -1
+              ct.w[c][n] = i * 3 + j;
+            }
+        }
+      const int tw4[4] = {0, 0, 0, 0}, dy4[4] = {0, 0, -1, -1}, dx4[4] = {0, -1, 0, -1};
+      if (int rc = conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, 4 * cout, cout_pad, 9, 4, tw4, dy4, dx4, 1, in_h,
+                                      in_w, out, 1, full_h, full_w, 2, 0, 0, ldo, co_off, epi, st, (int)cout, 0, nullptr, &ct))
+        return rc;
+      for (int pb = 0; pb < 2; ++pb) {          // output row 2H (class row parity 0, a = H): columns of parity pb
+        int tw_[4], dy[4], dx[4], nt = 0;
+        for (int i = 0; i < 3; i += 2)
+          for (int j = pb; j < 3; j += 2) { tw_[nt] = i * 3 + j; dy[nt] = (int)in_h - i / 2; dx[nt] = -(j - pb) / 2; ++nt; }
+        if (int rc = conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout_pad, 9, nt, tw_, dy, dx, 1, 1,
+                                        (full_w - pb + 1) / 2, out, 1, full_h, full_w, 2, 2 * (int)in_h, pb, ldo, co_off, epi, st))
+          return rc;
+      }
+      for (int pa = 0; pa < 2; ++pa) {          // output column 2W (column parity 0, b = W): rows 2a + pa, a < H
+        int tw_[4], dy[4], dx[4], nt = 0;
+        for (int i = pa; i < 3; i += 2)
+          for (int j = 0; j < 3; j += 2) { tw_[nt] = i * 3 + j; dy[nt] = -(i - pa) / 2; dx[nt] = (int)in_w - j / 2; ++nt; }
+        if (int rc = conv_gather_launch(x, wq, batch, groups, in_h, in_w, cin, cout, cout_pad, 9, nt, tw_, dy, dx, 1, in_h, 1,
+                                        out, 1, full_h, full_w, 2, pa, 2 * (int)in_w, ldo, co_off, epi, st))
+          return rc;
+      }
+      return 0;
+    }
+  }
   for (int pa = 0; pa < 2; ++pa)
     for (int pb = 0; pb < 2; ++pb) {
       int tw_[kMaxTaps], dy[kMaxTaps], dx[kMaxTaps], nt = 0;
