@@ -352,7 +352,8 @@ def main():
         result["config2_module"] = config2_module(pk, dev)
         result["config3_batch4"] = config3_batch4(net, dec, dev)
         result["hbm_roofline"] = isolated_upfirdn(upfirdn2d_raw, pk, dev)
-        result["cpu_baseline"] = cpu_baseline(args)
+        if world == 1:      # the contract's CPU baseline is an N = 1 figure (at N > 1 the other ranks spin on the host cores)
+            result["cpu_baseline"] = cpu_baseline(args)
     if not args.light:
         # BASELINE configs[4] next to the headline: every rank takes part (DDP all-reduce); rank 0 reports
         del graphed
@@ -666,12 +667,16 @@ def run_train(args):
 
 def conv_traffic(micro):
     """DRAM bytes (read + written) of all tcgen05 conv launches of one micro-batch, from the committed ncu launch list
-    (profiles/r01_launches_microbatch32_v33.*: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,
-    dram__bytes_write.sum` over tools/prof_step.py 32); None when the bench runs at another micro-batch size."""
-    path = os.path.join(ROOT, "profiles", "r01_launches_microbatch32_v33.json")
-    if micro != 32 or not os.path.exists(path):
+    (profiles/r02_final_launches_microbatch32.*, the current kernels — else round 1's list: `ncu --metrics
+    gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` over tools/prof_step.py 32); None when the bench
+    runs at another micro-batch size."""
+    if micro != 32:
         return None
-    return json.load(open(path))["conv_kernels"]["dram_bytes"]
+    for name in ("r02_final_launches_microbatch32.json", "r01_launches_microbatch32_v33.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            return json.load(open(path))["conv_kernels"]["dram_bytes"]
+    return None
 
 
 def _time_rotating(fns, rounds=5):
