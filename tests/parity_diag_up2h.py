@@ -1,5 +1,5 @@
 """Diagnostics (not a test): decoder-image error of the fused pipeline vs the fp32 CPU oracle with the half-composed
-up-convolution on / off, over a few seeds.  python tests/dbg_up2h_parity.py [seeds...]"""
+up-convolution on / off, over a few seeds.  python tests/parity_diag_up2h.py [seeds...]"""
 import math
 import os
 import sys

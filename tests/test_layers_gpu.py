@@ -366,7 +366,7 @@ def test_full_size_hot_path_matches_cpu_oracle():
     # The style decoder's image is an INTERMEDIATE of the path (the w+ preview, psp.py:245-246), produced by plain bf16
     # operands end to end.  Its max-abs is a 6-sigma tail statistic of ~5e5 pixels: on this seed the pipeline measures
     # 0.99e-2 of the range with the dense up-convolutions and 1.02e-2 with the half-composed ones at IDENTICAL rms
-    # (1.68e-3, tests/dbg_up2h_parity.py), while the CPU oracle with bf16 operands and stores (policy "bf16_all", computed
+    # (1.68e-3, tests/parity_diag_up2h.py), while the CPU oracle with bf16 operands and stores (policy "bf16_all", computed
     # here on the same inputs) sits at 1.54e-2 / rms 1.61e-3.  So: PSNR > 45 dB, rms no worse than 1.15 x the all-bf16
     # oracle's, max-abs <= max(1e-2, that oracle's max-abs).  north_star's hard 1e-2 is asserted on the full-network
     # output below.

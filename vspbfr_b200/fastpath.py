@@ -515,7 +515,7 @@ def large_conv_layer(m: LargeConvLayer, x):
 #   conv(x, w) ~= conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)            (error ~2^-17 instead of 2^-9)
 # expressed to the SAME tcgen05 kernels as one convolution over 3*Cin channels: activation [hi | lo | hi], weight
 # [w_hi | w_hi | w_lo]; activations between these layers stay fp32 NCHW (they are at most 32x32).
-# Measured on the B200 (tests/dbg_fullsize.py, parity test's seed): no two-term layers 1.51e-2 of the range / 51.5 dB;
+# Measured on the B200 (tests/parity_diag_fullsize.py, parity test's seed): no two-term layers 1.51e-2 of the range / 51.5 dB;
 # <= 16x16: 1.06e-2 / 55.6 dB; <= 32x32 (default): 0.77e-2 / 57.7 dB, for 4 % of the throughput (1024 -> 983 faces/s).
 _SPLIT_PIXELS = 0 if os.environ.get("VSP_NO_SPLIT_LOWRES") is not None else int(os.environ.get("VSP_SPLIT_PIXELS", "1024"))
 
