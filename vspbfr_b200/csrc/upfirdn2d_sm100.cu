@@ -782,6 +782,227 @@ blur_strip_kernel(const __grid_constant__ CUtensorMap tmx, uint4 *__restrict__ y
   }
 }
 
+// ---- epilogue form with its operands on the bulk-copy path ------------------------------------------------------------
+// ncu on blur_strip_kernel<EPI> with both skip residuals (profiles/r02_ncu_prof_blur_epi*.summary.txt): 54 % of the stall
+// samples sit on the FIRST use of the epilogue operands of a row although their loads were issued three rows earlier — a
+// row of a 4-warp CTA takes ~300 issue slots, three rows cover ~0.7 us, a loaded-DRAM round trip is longer, and registers
+// for a deeper ring do not exist (204 at three rows).  Here the residual rows of a stage arrive like the input rows do: one
+// TMA box [64 ch, 32 cols, 4 rows] per residual into the SAME stage buffer (the four output rows a stage completes are
+// rows q_lo + 4k - 3 ... q_lo + 4k: out-of-range rows / columns zero-fill and are never emitted), so they are in flight a
+// whole stage ahead at no register cost, read back with one conflict-free LDS.128 per pixel; the noise values of the NEXT
+// stage (8 floats) are fetched while the current one is processed.  NRES = 0 / 1 / 2 residuals: 4 / 3 / 2 stages of
+// 17.5 / 33.5 / 49.5 KB, two CTAs per SM.
+template <int NRES>
+struct StripEpiCfg {
+  static constexpr int kResBytes = kStageRows * kStripW * 128;                     // one residual's rows of a stage
+  static constexpr int kBytes = kStageBytes + NRES * kResBytes;
+  static constexpr int kStages = NRES == 0 ? 4 : (NRES == 1 ? 3 : 2);
+};
+
+template <int NRES>
+__global__ void __launch_bounds__(kStripThreads, NRES == 0 ? 3 : 2)
+blur_strip_epi_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmr1,
+                      const __grid_constant__ CUtensorMap tmr2, uint4 *__restrict__ y, const StripParams p, const NhwcEpi e,
+                      const SepTaps t) {
+  using Cfg = StripEpiCfg<NRES>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ __align__(128) unsigned char strip_smem[];
+  __shared__ uint64_t full[kStages], empty[kStages];
+  const int tid = threadIdx.x, lane = tid & 31;
+  int bid = blockIdx.x;
+  const int sx = bid % p.n_strips; bid /= p.n_strips;
+  const int cz = bid % p.n_chunks; bid /= p.n_chunks;
+  const int sy = bid % p.n_seg;
+  const int b = bid / p.n_seg;
+  const int q_lo = sy * p.seg_rows;
+  const int rows_out = min(p.seg_rows, p.out_h - q_lo);
+  const int n_stage = (rows_out + kK - 1 + kStageRows - 1) / kStageRows;
+  const int ox0 = sx * kStripW, ix0 = ox0 - p.pad_x0, iy0 = q_lo - p.pad_y0;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kStripThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_stage = [&](int k) {                // one elected thread: input rows + the residual rows of the outputs they complete
+    unsigned char *dst = strip_smem + (k % kStages) * Cfg::kBytes;
+    uint64_t *bar = &full[k % kStages];
+    mbar_arrive_expect_tx(bar, Cfg::kBytes);
+    tma_load_4d(dst, &tmx, bar, cz * 64, ix0, iy0 + k * kStageRows, b);
+    if (NRES >= 1) tma_load_4d(dst + kStageBytes, &tmr1, bar, cz * 64, ox0, q_lo + k * kStageRows - (kK - 1), b);
+    if (NRES >= 2) tma_load_4d(dst + kStageBytes + Cfg::kResBytes, &tmr2, bar, cz * 64, ox0, q_lo + k * kStageRows - (kK - 1), b);
+  };
+  if (tid == 0) {
+    tma_prefetch_desc(&tmx);
+    if (NRES >= 1) tma_prefetch_desc(&tmr1);
+    if (NRES >= 2) tma_prefetch_desc(&tmr2);
+    for (int k = 0; k < kStages && k < n_stage; ++k) issue_stage(k);
+  }
+  const int cg8 = tid & 7, cp = tid >> 3;
+  const int ox = ox0 + 2 * cp;
+  const bool ok0 = ox < p.out_w, ok1 = ox + 1 < p.out_w;
+  unsigned long long fxp[kK], fyp[kK];
+#pragma unroll
+  for (int j = 0; j < kK; ++j) {
+    fxp[j] = pk2(t.fx[j], t.fx[j]);
+    fyp[j] = pk2(t.fy[j], t.fy[j]);
+  }
+  unsigned long long acc[kK][2][4];
+#pragma unroll
+  for (int q = 0; q < kK; ++q)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[q][c][i] = 0ull;
+  float bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = e.bias ? __ldg(e.bias + (cz * 8 + cg8) * 8 + i) : 0.f;
+  const float nw = e.noise ? (e.noise_weight_dev ? __ldg(e.noise_weight_dev) : e.noise_weight) : 0.f;
+  const bool pointwise = e.noise != nullptr || e.bias != nullptr || e.act != 0;
+  const uint32_t tbase = smem_u32(strip_smem) + (uint32_t)(2 * cp) * 128u + (uint32_t)cg8 * 16u;
+  const long long ybase = (long long)b * p.out_h * p.out_w * p.cg + cz * 8 + cg8;
+  // noise of the rows a stage emits, fetched one stage ahead (raw values: scaled at their use)
+  float nz_cur[kStageRows][2], nz_nxt[kStageRows][2];
+  auto fetch_noise = [&](int k, float (&nz)[kStageRows][2]) {
+#pragma unroll
+    for (int rr = 0; rr < kStageRows; ++rr) {
+      const int i = k * kStageRows + rr;
+      const bool emit = e.noise != nullptr && i >= kK - 1 && i - (kK - 1) < rows_out;
+      const long long pix = (long long)(q_lo + i - (kK - 1)) * p.out_w + ox;
+      nz[rr][0] = (emit && ok0) ? __ldg(e.noise + b * e.noise_bstride + pix) : 0.f;
+      nz[rr][1] = (emit && ok1) ? __ldg(e.noise + b * e.noise_bstride + pix + 1) : 0.f;
+    }
+  };
+  fetch_noise(0, nz_cur);
+
+  for (int k = 0; k < n_stage; ++k) {
+    const int s = k % kStages;
+    const uint32_t phase = (uint32_t)(k / kStages) & 1u;
+    if (k + 1 < n_stage) fetch_noise(k + 1, nz_nxt);
+    mbar_wait(&full[s], phase);
+    const uint32_t st = tbase + (uint32_t)s * Cfg::kBytes;
+#pragma unroll
+    for (int rr = 0; rr < kStageRows; ++rr) {
+      const int i = k * kStageRows + rr;              // input row of this segment
+      const int oy = q_lo + i - (kK - 1);             // the output row this input row completes
+      const bool emit = i >= kK - 1 && i - (kK - 1) < rows_out;
+      unsigned long long h0[4], h1[4];
+#pragma unroll
+      for (int j = 0; j < kK + 1; ++j) {
+        const uint4 v = lds128(st + (uint32_t)(rr * kStripCols + j) * 128u);
+        const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned long long xv = pk2(__uint_as_float(wd[q] << 16), __uint_as_float(wd[q] & 0xFFFF0000u));
+          if (j == 0) h0[q] = fmul2_(xv, fxp[0]);
+          else if (j < kK) h0[q] = ffma2_(xv, fxp[j], h0[q]);
+          if (j == 1) h1[q] = fmul2_(xv, fxp[0]);
+          else if (j > 1) h1[q] = ffma2_(xv, fxp[j - 1], h1[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[rr][0][q] = fmul2_(h0[q], fyp[0]);
+        acc[rr][1][q] = fmul2_(h1[q], fyp[0]);
+#pragma unroll
+        for (int j = 1; j < kK; ++j) {
+          acc[(rr + kK - j) % kK][0][q] = ffma2_(h0[q], fyp[j], acc[(rr + kK - j) % kK][0][q]);
+          acc[(rr + kK - j) % kK][1][q] = ffma2_(h1[q], fyp[j], acc[(rr + kK - j) % kK][1][q]);
+        }
+      }
+      if (emit) {
+        const int slot = (rr + 1) % kK;               // the row that has now seen all kK taps
+        const long long pix = (long long)oy * p.out_w + ox;
+        // residual rows of this stage: [row rr][column][64 channels], this thread's pixel pair at column 2 cp
+        const uint32_t rbase = st - (uint32_t)(2 * cp) * 128u + kStageBytes + (uint32_t)(rr * kStripW + 2 * cp) * 128u;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!(c ? ok1 : ok0)) continue;
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) unpk2(acc[slot][c][q], v[2 * q], v[2 * q + 1]);
+          if (pointwise) {
+            const float nzw = nw * nz_cur[rr][c];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float u = v[q] + nzw + bias[q];
+              if (e.act == 3) u = (u > 0.f ? u : u * e.alpha) * e.scale;
+              v[q] = u;
+            }
+          }
+          if (NRES >= 1) add_bf16x8(v, lds128(rbase + (uint32_t)c * 128u));
+          if (NRES >= 2) add_bf16x8(v, lds128(rbase + Cfg::kResBytes + (uint32_t)c * 128u));
+          uint4 o;
+          __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+          y[ybase + (pix + c) * p.cg] = o;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+    if (tid == 0 && k + kStages < n_stage) {
+      mbar_wait(&empty[s], phase);
+      issue_stage(k + kStages);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kStageRows; ++rr) { nz_cur[rr][0] = nz_nxt[rr][0]; nz_cur[rr][1] = nz_nxt[rr][1]; }
+  }
+}
+
+template <int NRES>
+int launch_blur_strip_epi(const void *x, void *y, StripParams p, const NhwcEpi &e, const void *r1, const void *r2,
+                          const SepTaps &t, int64_t n, int64_t c, cudaStream_t stream) {
+  using Cfg = StripEpiCfg<NRES>;
+  auto kern = blur_strip_epi_kernel<NRES>;
+  constexpr int smem = Cfg::kStages * Cfg::kBytes;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  VSP_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    VSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  p.n_strips = (p.out_w + kStripW - 1) / kStripW;
+  p.n_chunks = (int)(c / 64);
+  p.cg = (int)(c / 8);
+  const long long base_blocks = (long long)p.n_strips * p.n_chunks * n;
+  long long n_seg = ((long long)num_sms() * (NRES == 0 ? 6 : 4) + base_blocks - 1) / base_blocks;     // two waves of resident CTAs
+  const long long max_seg = p.out_h >= 32 ? p.out_h / 32 : 1;
+  if (n_seg > max_seg) n_seg = max_seg;
+  if (n_seg < 1) n_seg = 1;
+  p.seg_rows = (int)((p.out_h + n_seg - 1) / n_seg);
+  p.n_seg = (p.out_h + p.seg_rows - 1) / p.seg_rows;
+  const long long blocks = base_blocks * p.n_seg;
+  VSP_REQUIRE(blocks < 2147483647LL, "blur_strip_epi: grid too large (%lld blocks)", blocks);
+  CUtensorMap tmx, tmr[2];
+  memset(&tmx, 0, sizeof(tmx));
+  memset(tmr, 0, sizeof(tmr));
+  {
+    uint64_t dims[4] = {(uint64_t)c, (uint64_t)p.in_w, (uint64_t)p.in_h, (uint64_t)n};
+    uint64_t strides[4] = {0, (uint64_t)c * 2, (uint64_t)c * p.in_w * 2, (uint64_t)c * p.in_w * p.in_h * 2};
+    uint32_t box[4] = {64, (uint32_t)kStripCols, (uint32_t)kStageRows, 1};
+    if (int rc = encode_tma(&tmx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
+  }
+  const void *res[2] = {r1, r2};
+  for (int i = 0; i < NRES; ++i) {
+    uint64_t dims[4] = {(uint64_t)c, (uint64_t)p.out_w, (uint64_t)p.out_h, (uint64_t)n};
+    uint64_t strides[4] = {0, (uint64_t)c * 2, (uint64_t)c * p.out_w * 2, (uint64_t)c * p.out_w * p.out_h * 2};
+    uint32_t box[4] = {64, (uint32_t)kStripW, (uint32_t)kStageRows, 1};
+    if (int rc = encode_tma(&tmr[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, res[i], dims, strides, box, nullptr,
+                            CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
+  }
+  kern<<<(unsigned)blocks, kStripThreads, smem, stream>>>(tmx, tmr[0], tmr[1], static_cast<uint4 *>(y), p, e, t);
+  return check_launch("blur_strip_epi_kernel");
+}
+
 template <bool EPI, int AHEAD = 0, int MINB = 3>
 int launch_blur_strip(const void *x, void *y, StripParams p, const NhwcEpi &e, const SepTaps &t, int64_t n, int64_t c,
                       cudaStream_t stream) {
@@ -1410,6 +1631,19 @@ extern "C" int vsp_blur_sep_nhwc_bf16(const void *x, const float *fy_host, const
     // memory requests (2.1 M loads + 2.2 M stores, 16 % L1 hits) than global loads (1.6 M) and the kernel at 2.9 TB/s.  With 2
     // CTAs/SM (204 registers, no spills) and the operand loads three rows ahead: [32,129,129,256] 365 -> 312 us (3.5 TB/s).
     // VSP_BLUR_EPI_BLOCKS=3 / VSP_BLUR_EPI_AHEAD=0..3 select the other forms (tools/bench_blur_epi.py).
+    // operands of the epilogue on the bulk-copy path (blur_strip_epi_kernel); VSP_BLUR_EPI_TMA=0 keeps the register ring
+    static const bool epi_tma = getenv("VSP_BLUR_EPI_TMA") == nullptr || atoi(getenv("VSP_BLUR_EPI_TMA")) != 0;
+    if (epi_tma) {
+      const void *r1 = e.residual ? (const void *)e.residual : (const void *)e.residual2;
+      const void *r2 = e.residual ? (const void *)e.residual2 : nullptr;
+      const int nres = (r1 != nullptr) + (r2 != nullptr);
+      const bool aligned = (reinterpret_cast<uintptr_t>(r1) & 15) == 0 && (reinterpret_cast<uintptr_t>(r2) & 15) == 0;
+      if (aligned) {
+        if (nres == 2) return launch_blur_strip_epi<2>(x, y, sp, e, r1, r2, t, n, c, stream);
+        if (nres == 1) return launch_blur_strip_epi<1>(x, y, sp, e, r1, nullptr, t, n, c, stream);
+        return launch_blur_strip_epi<0>(x, y, sp, e, nullptr, nullptr, t, n, c, stream);
+      }
+    }
     static const int ahead = getenv("VSP_BLUR_EPI_AHEAD") ? atoi(getenv("VSP_BLUR_EPI_AHEAD")) : 3;
     static const int minb = getenv("VSP_BLUR_EPI_BLOCKS") ? atoi(getenv("VSP_BLUR_EPI_BLOCKS")) : 2;
     if (minb == 3)
