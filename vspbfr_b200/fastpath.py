@@ -35,11 +35,12 @@ _UP2H = os.environ.get("VSP_UP2H", "1") != "0"          # half-composed up-convo
 # weights, demodulation in the epilogue: models/RestoreNet.py:481-508): below it the per-sample weight prologue
 # costs more than scaling the activation, and shared weights let one 128-row tile stack several samples
 _LOWRES_PIXELS = int(os.environ.get("VSP_LOWRES_PIXELS", "1024"))
-# Low-resolution up-convolutions with at least this many input pixels (16x16 and 32x32 at 512 channels) run as transposed conv
-# (1x the layer's FLOPs) + blur instead of the composite dense form (4x the FLOPs).  The kernels take the same time either way
-# (32x32: 228 + 115 us vs 359 us per 32 faces), but the step runs under the board's power cap (SM clock 1640 of 1965 MHz in
-# the bench), so 1.2 TFLOP less per micro-batch is +1 % throughput: same-box A/B 1075 / 1081 / 1072 -> 1086 / 1087 faces/s.
-_LOWRES_UP_SPLIT_PIXELS = int(os.environ.get("VSP_LOWRES_UP_SPLIT_PIXELS", "256"))
+# Low-resolution up-convolutions with at least this many input pixels (the 512-channel 32x32 layers) run as transposed conv
+# (1x the layer's FLOPs, one class-mode launch) + blur instead of the composite dense form (4x the FLOPs): 175 + 72 us vs
+# 359 us per 32 faces (with both skip residuals 171 + 109 vs 380), and 0.9 TFLOP less per micro-batch under the power cap.
+# The 16x16 layers stay dense: their transposed conv is not eligible for the one-launch form (122 + 39 us vs 133 us), and
+# with them split the full-size parity test sits at 0.99e-2 of the range (0.87e-2 with this default, 0.92e-2 all dense).
+_LOWRES_UP_SPLIT_PIXELS = int(os.environ.get("VSP_LOWRES_UP_SPLIT_PIXELS", "1024"))
 # SMART layers up to this width run their four dilated branches as one launch of the generic kernel
 _BRANCH_MAX_W = int(os.environ.get("VSP_BRANCH_MAX_W", "64"))
 _SEP_BLUR = os.environ.get("VSP_NO_SEP_BLUR") is None
