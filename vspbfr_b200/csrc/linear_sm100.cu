@@ -3,8 +3,10 @@
 // Reference: EqualLinear (models/RestoreNet.py:142-176) as used by ModulatedConv2d.modulation / SMART_layer.modulation
 // (:467,:510,:211,:227): s_j = F.linear(style_j, W_j * scale_j, bias_j * lr_mul_j), one tiny [B,512..2048] x
 // [Cin, 512..2048] product per layer — 60+ library launches per forward in the reference.  All styles of a pass are
-// known up front, so the host builds one descriptor table and this kernel computes every output row (problem j,
-// channel o) with one warp: the weight row is streamed once (128-bit loads) and dotted with the B style rows.
+// known up front, so the host builds one descriptor table and one launch computes every output row (problem j,
+// channel o).  Two kernels: micro-batches <= 8 use one warp per row (the weight row streamed once with 128-bit loads and
+// dotted with the staged style rows), 9..32 samples the lane-per-sample split-K form further down.  With `act` set in the
+// descriptor the same launch is a layer of the style MLP (bias * lr_mul + leaky relu * sqrt 2 in the epilogue).
 // Memory-bound on the weights (HBM/L2), fp32 throughout.
 #include "common.cuh"
 
@@ -17,9 +19,9 @@ __device__ __forceinline__ float lin_act(const vsp_linear_desc &d, float v) {
 
 constexpr int kLinThreads = 256;
 constexpr int kLinRows = 8;     // output rows per block (one per warp)
-// kLinB samples are accumulated per pass over kLinK staged style elements (kLinB x kLinK floats of shared memory).
-// Two instantiations: 8 x 512 for small batches, 32 x 256 (32 KB) for micro-batches > 8 — a 32-face micro-batch then streams every
-// weight row ONCE (with 8 samples per pass it was re-streamed and the styles re-staged four times: 0.37 TB/s on the weights).
+// kLinB samples are accumulated per pass over kLinK staged style elements (kLinB x kLinK floats of shared memory);
+// instantiated as 8 x 512 (batch > 8 goes to grouped_linear_lanes_kernel: with 8 samples per pass a 32-face micro-batch
+// re-streamed every weight row and re-staged the styles four times, 0.37 TB/s on the weights).
 
 // One block = kLinRows consecutive output rows of ONE problem (the host pads every problem to a multiple of
 // kLinRows rows in `row_start`), so the block's warps share the problem's style rows: they are staged in shared
