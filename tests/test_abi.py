@@ -64,3 +64,36 @@ def test_op_surface_names():
         assert hasattr(op.conv2d_gradfix, name)
     m = op.FusedLeakyReLU(8)
     assert list(m.state_dict().keys()) == ["bias"]
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the ABI structs (vsp_linear_desc, vsp_conv_epilogue) must have the size and field offsets a C
+    compiler gives the declarations in include/vsp_b200.h — a field added on one side only would silently shift every
+    later field (the header is what a cgo / JNI / ctypes binding of the reference would compile against)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from vspbfr_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    structs = {"vsp_linear_desc": _lib.LinearDesc, "vsp_conv_epilogue": _lib.ConvEpilogue}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "vsp_b200.h"', "int main(void) {"]
+    for cname, mirror in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in mirror._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    include = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([gcc, "-I", include, str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.splitlines():
+        cname, field, value = line.split()
+        mirror = structs[cname]
+        want = ctypes.sizeof(mirror) if field == "size" else getattr(mirror, field).offset
+        assert int(value) == want, f"{cname}.{field}: header {value} vs ctypes {want}"
